@@ -1,0 +1,12 @@
+"""halo2-svd041_b200 -- B200-native ZkMatrix / ZkVector witness path (sm_100a CUDA behind a C ABI).
+
+The directory name is not a Python identifier; import it with
+    importlib.import_module("halo2-svd041_b200")
+Importing the package does NOT load the CUDA library (so CPU-only tooling can inspect it);
+`Handle()` / `_ffi.load()` do, and fail loudly if it has not been built.  There is no CPU fallback.
+"""
+from . import _ffi  # noqa: F401
+from ._ffi import H2svdError  # noqa: F401
+from .gpu import Handle, set_matmul_variant  # noqa: F401
+
+__all__ = ["Handle", "H2svdError", "set_matmul_variant"]

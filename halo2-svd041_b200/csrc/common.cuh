@@ -1,0 +1,106 @@
+// Shared host/device plumbing of libh2svd_b200: handle, error reporting, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/h2svd_b200.h"
+#include "fr.cuh"
+
+struct h2svd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    // grow-only device workspace (scratch for transposes, host-pointer entry points, ...)
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // second stream + events for copy/compute overlap in the host-pointer entry points
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int* d_flag = nullptr;  // device flag for validation kernels
+    uint64_t launches = 0;
+};
+
+namespace h2svd {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+// Ensures ctx->ws has at least `bytes`; returns H2SVD_OK / H2SVD_ENOMEM.
+int ws_reserve(h2svd_ctx* ctx, size_t bytes);
+
+#define H2SVD_CUDA(call)                                                        \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return h2svd::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define H2SVD_LAUNCH_CHECK(ctx)                 \
+    do {                                        \
+        (ctx)->launches++;                      \
+        H2SVD_CUDA(cudaGetLastError());         \
+    } while (0)
+
+#define H2SVD_TRY(expr)                 \
+    do {                                \
+        int _rc = (expr);               \
+        if (_rc != H2SVD_OK) return _rc; \
+    } while (0)
+
+using fr::Fr;
+
+static inline const Fr* as_fr(const h2svd_fr* p) { return reinterpret_cast<const Fr*>(p); }
+static inline Fr* as_fr(h2svd_fr* p) { return reinterpret_cast<Fr*>(p); }
+
+// ---- device-side load/store of one field element as two 128-bit accesses ---------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = q[0], hi = q[1];
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = __ldg(q), hi = __ldg(q + 1);
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// streaming store: witness arrays are written once and read back by the host, never re-read here
+__device__ __forceinline__ void st_fr_cs(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    __stcs(q, make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]));
+    __stcs(q + 1, make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]));
+}
+#endif
+
+// ---- kernel launchers (one per .cu) -----------------------------------------------------------------
+int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m);
+int launch_fr_matmul_naive(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k,
+                           size_t m);
+int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t cols);
+int launch_gamma_powers(h2svd_ctx* ctx, const Fr* gamma, size_t d, Fr* out);
+int launch_mat_vec_prefix(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t len,
+                          size_t v_row_stride, Fr* out);
+int launch_gather(h2svd_ctx* ctx, const Fr* src, size_t count, size_t stride, size_t offset,
+                  Fr* out);
+int launch_is_equal(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, Fr* diff, Fr* is_zero,
+                    Fr* inv);
+int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, int S, int A, Fr* out_q,
+                   Fr* out_wit);
+int launch_sub(h2svd_ctx* ctx, const Fr* a, const Fr* b, size_t count, Fr* out);
+int launch_isqrt(h2svd_ctx* ctx, const Fr* a, size_t count, int P, Fr* out);
+int launch_quantize(h2svd_ctx* ctx, const double* x, size_t count, int P, Fr* out);
+int launch_check_canonical(h2svd_ctx* ctx, const Fr* x, size_t count, int* d_flag);
+int launch_microbench(h2svd_ctx* ctx, int kind, int iters, double* ops_per_s);
+
+}  // namespace h2svd

@@ -1,0 +1,243 @@
+"""Thin object wrapper over the C ABI (one Handle == one h2svd_ctx == one GPU + stream).
+
+Two families of methods, mirroring the header:
+  * host methods take/return numpy uint64[..., 4] arrays (bn256::Fr Montgomery limbs) and go
+    through the host-pointer entry points (H2D + kernels + D2H inside the call);
+  * `*_dev` methods take torch int64[..., 4] CUDA tensors (same bytes) and only enqueue kernels
+    on the handle's stream.
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+from typing import Optional
+
+import numpy as np
+
+from . import _ffi
+
+
+def _np_fr(*shape) -> np.ndarray:
+    return np.empty(shape + (4,), dtype=np.uint64)
+
+
+def _np_ptr(a: np.ndarray) -> ct.c_void_p:
+    if a.dtype != np.uint64 and a.dtype != np.float64:
+        raise TypeError(f"expected uint64/float64 array, got {a.dtype}")
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return ct.c_void_p(a.ctypes.data)
+
+
+def _fr_shape(a, ndim: int):
+    if a.shape[-1] != 4 or a.ndim != ndim + 1:
+        raise ValueError(f"expected a [{', '.join('?' * ndim)}, 4] limb array, got {tuple(a.shape)}")
+    return a.shape[:-1]
+
+
+class Handle:
+    """h2svd_ctx wrapper.  Not thread-safe (mirrors the reference's `&mut Context`)."""
+
+    def __init__(self, device: int = -1, stream: Optional[int] = None) -> None:
+        self._lib = _ffi.load()
+        h = ct.c_void_p()
+        _ffi.check(self._lib.h2svd_create(ct.byref(h), device, ct.c_void_p(stream or 0)))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.h2svd_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self) -> "Handle":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    # ---- properties ----
+    @property
+    def device(self) -> int:
+        return self._lib.h2svd_device(self._h)
+
+    @property
+    def sm_count(self) -> int:
+        return self._lib.h2svd_sm_count(self._h)
+
+    @property
+    def stream(self) -> int:
+        return self._lib.h2svd_stream(self._h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.h2svd_launch_count(self._h))
+
+    def sync(self) -> None:
+        _ffi.check(self._lib.h2svd_sync(self._h))
+
+    # ---- host-pointer entry points (numpy) ----
+    def fr_matmul(self, a: np.ndarray, b: np.ndarray, b_transposed: bool = False,
+                  out: Optional[np.ndarray] = None) -> np.ndarray:
+        n, k = _fr_shape(a, 2)
+        if b_transposed:
+            m, k2 = _fr_shape(b, 2)
+        else:
+            k2, m = _fr_shape(b, 2)
+        if k != k2:
+            raise ValueError("fr_matmul: inner dimensions differ")  # reference :515
+        c = _np_fr(n, m) if out is None else out
+        _ffi.check(self._lib.h2svd_fr_matmul(self._h, _np_ptr(a), _np_ptr(b), _np_ptr(c), n, k, m,
+                                            int(b_transposed)))
+        return c
+
+    def freivalds_witness(self, a: np.ndarray, b: np.ndarray, c_s: np.ndarray,
+                          gamma: np.ndarray) -> dict:
+        n, k = _fr_shape(a, 2)
+        k2, m = _fr_shape(b, 2)
+        n2, m2 = _fr_shape(c_s, 2)
+        if k != k2 or n != n2 or m != m2:  # reference :307-309
+            raise ValueError("freivalds_witness: shape mismatch")
+        out = dict(powers=_np_fr(m), prefix_cv=_np_fr(n, m), prefix_bv=_np_fr(k, m),
+                   prefix_abv=_np_fr(n, k), diff=_np_fr(n), is_zero=_np_fr(n), inv=_np_fr(n))
+        g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
+        _ffi.check(self._lib.h2svd_freivalds_witness(
+            self._h, _np_ptr(a), _np_ptr(b), _np_ptr(c_s), _np_ptr(g), n, k, m,
+            _np_ptr(out["powers"]), _np_ptr(out["prefix_cv"]), _np_ptr(out["prefix_bv"]),
+            _np_ptr(out["prefix_abv"]), _np_ptr(out["diff"]), _np_ptr(out["is_zero"]),
+            _np_ptr(out["inv"])))
+        return out
+
+    def rescale_witness_count(self, precision_bits: int, lookup_bits: int, shift_bits: int = -1,
+                              a_num_bits: int = -1) -> int:
+        w = self._lib.h2svd_rescale_witness_count(precision_bits, lookup_bits, shift_bits, a_num_bits)
+        if w < 0:
+            _ffi.check(w)
+        return w
+
+    def rescale_witness(self, c_s: np.ndarray, precision_bits: int, lookup_bits: int,
+                        shift_bits: int = -1, a_num_bits: int = -1, out_q: Optional[np.ndarray] = None,
+                        out_wit: Optional[np.ndarray] = None):
+        flat = c_s.reshape(-1, 4)
+        count = flat.shape[0]
+        W = self.rescale_witness_count(precision_bits, lookup_bits, shift_bits, a_num_bits)
+        q = _np_fr(count) if out_q is None else out_q
+        wit = _np_fr(count, W) if out_wit is None else out_wit
+        _ffi.check(self._lib.h2svd_rescale_witness(self._h, _np_ptr(flat), count, precision_bits,
+                                                  lookup_bits, shift_bits, a_num_bits, _np_ptr(q),
+                                                  _np_ptr(wit)))
+        return q.reshape(c_s.shape), wit
+
+    def zkvec_inner_prefix(self, x: np.ndarray, self_: np.ndarray) -> np.ndarray:
+        batch, ln = _fr_shape(x, 2)
+        if _fr_shape(self_, 2) != (batch, ln):
+            raise ValueError("zkvec_inner_prefix: shape mismatch")  # reference :86
+        out = _np_fr(batch, ln)
+        _ffi.check(self._lib.h2svd_zkvec_inner_prefix(self._h, _np_ptr(x), _np_ptr(self_), batch, ln,
+                                                     _np_ptr(out)))
+        return out
+
+    def zkvec_sub(self, self_: np.ndarray, x: np.ndarray) -> np.ndarray:
+        if self_.shape != x.shape:
+            raise ValueError("zkvec_sub: shape mismatch")  # reference :142
+        out = np.empty_like(self_)
+        _ffi.check(self._lib.h2svd_zkvec_sub(self._h, _np_ptr(self_), _np_ptr(x), self_.size // 4,
+                                            _np_ptr(out)))
+        return out
+
+    def isqrt_fixed(self, a: np.ndarray, precision_bits: int) -> np.ndarray:
+        out = np.empty_like(a)
+        _ffi.check(self._lib.h2svd_isqrt_fixed(self._h, _np_ptr(a), a.size // 4, precision_bits,
+                                              _np_ptr(out)))
+        return out
+
+    def quantize(self, x: np.ndarray, precision_bits: int) -> np.ndarray:
+        xs = np.ascontiguousarray(x, dtype=np.float64)
+        out = _np_fr(*xs.shape)
+        _ffi.check(self._lib.h2svd_quantize(self._h, _np_ptr(xs), xs.size, precision_bits, _np_ptr(out)))
+        return out
+
+    def microbench_imad(self, kind: int, iters: int = 2000) -> float:
+        v = ct.c_double()
+        _ffi.check(self._lib.h2svd_microbench_imad(self._h, kind, iters, ct.byref(v)))
+        return v.value
+
+    # ---- device-pointer entry points (torch CUDA tensors, int64[..., 4]) ----
+    @staticmethod
+    def _tp(t) -> ct.c_void_p:
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError("expected a contiguous CUDA tensor")
+        return ct.c_void_p(t.data_ptr())
+
+    def fr_matmul_dev(self, a, b, c, b_transposed: bool = False) -> None:
+        n, k = a.shape[0], a.shape[1]
+        m = b.shape[0] if b_transposed else b.shape[1]
+        _ffi.check(self._lib.h2svd_fr_matmul_dev(self._h, self._tp(a), self._tp(b), self._tp(c), n, k, m,
+                                                int(b_transposed)))
+
+    def fr_matmul_naive_dev(self, a, b, c) -> None:
+        n, k = a.shape[0], a.shape[1]
+        m = b.shape[1]
+        _ffi.check(self._lib.h2svd_debug_fr_matmul_naive_dev(self._h, self._tp(a), self._tp(b),
+                                                            self._tp(c), n, k, m))
+
+    def freivalds_witness_dev(self, a, b, c_s, gamma, powers, prefix_cv, prefix_bv, prefix_abv, diff,
+                              is_zero, inv) -> None:
+        n, k = a.shape[0], a.shape[1]
+        m = b.shape[1]
+        _ffi.check(self._lib.h2svd_freivalds_witness_dev(
+            self._h, self._tp(a), self._tp(b), self._tp(c_s), self._tp(gamma), n, k, m,
+            self._tp(powers), self._tp(prefix_cv), self._tp(prefix_bv), self._tp(prefix_abv),
+            self._tp(diff), self._tp(is_zero), self._tp(inv)))
+
+    def gamma_powers_dev(self, gamma, d: int, out) -> None:
+        _ffi.check(self._lib.h2svd_gamma_powers_dev(self._h, self._tp(gamma), d, self._tp(out)))
+
+    def mat_vec_prefix_dev(self, a, v, out) -> None:
+        rows, ln = a.shape[0], a.shape[1]
+        _ffi.check(self._lib.h2svd_mat_vec_prefix_dev(self._h, self._tp(a), self._tp(v), rows, ln,
+                                                     self._tp(out)))
+
+    def gather_dev(self, src, count: int, stride: int, offset: int, out) -> None:
+        _ffi.check(self._lib.h2svd_gather_dev(self._h, self._tp(src), count, stride, offset,
+                                             self._tp(out)))
+
+    def is_equal_witness_dev(self, x, y, diff, is_zero, inv) -> None:
+        _ffi.check(self._lib.h2svd_is_equal_witness_dev(self._h, self._tp(x), self._tp(y), x.shape[0],
+                                                       self._tp(diff), self._tp(is_zero), self._tp(inv)))
+
+    def rescale_witness_dev(self, c_s, count: int, precision_bits: int, lookup_bits: int, out_q, out_wit,
+                            shift_bits: int = -1, a_num_bits: int = -1) -> None:
+        _ffi.check(self._lib.h2svd_rescale_witness_dev(self._h, self._tp(c_s), count, precision_bits,
+                                                      lookup_bits, shift_bits, a_num_bits,
+                                                      self._tp(out_q), self._tp(out_wit)))
+
+    def zkvec_inner_prefix_dev(self, x, self_, out) -> None:
+        batch, ln = x.shape[0], x.shape[1]
+        _ffi.check(self._lib.h2svd_zkvec_inner_prefix_dev(self._h, self._tp(x), self._tp(self_), batch, ln,
+                                                         self._tp(out)))
+
+    def zkvec_sub_dev(self, self_, x, out) -> None:
+        _ffi.check(self._lib.h2svd_zkvec_sub_dev(self._h, self._tp(self_), self._tp(x),
+                                                self_.numel() // 4, self._tp(out)))
+
+    def isqrt_fixed_dev(self, a, precision_bits: int, out) -> None:
+        _ffi.check(self._lib.h2svd_isqrt_fixed_dev(self._h, self._tp(a), a.numel() // 4, precision_bits,
+                                                  self._tp(out)))
+
+    def quantize_dev(self, x, precision_bits: int, out) -> None:
+        _ffi.check(self._lib.h2svd_quantize_dev(self._h, self._tp(x), x.numel(), precision_bits,
+                                               self._tp(out)))
+
+    def check_canonical_dev(self, x) -> None:
+        _ffi.check(self._lib.h2svd_check_canonical_dev(self._h, self._tp(x), x.numel() // 4))
+
+
+def set_matmul_variant(v: int) -> None:
+    """Triage/tuning hook (not part of the public header)."""
+    _ffi.load().h2svd_debug_set_matmul_variant(v)

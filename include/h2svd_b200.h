@@ -1,0 +1,167 @@
+/* h2svd_b200 -- C ABI of the B200-native ZkMatrix / ZkVector witness path.
+ *
+ * This is the drop-in boundary for ONE hot path of neilcouture/halo2-svd041: the value computation
+ * of src/matrix/mod.rs (field mat-mul, Freivalds mat-vecs, rescale, ZkVector witnesses).  The
+ * reference has no FFI of its own (pure Rust); these entry points are what a Rust `extern "C"`
+ * block in the reference's src/matrix would bind (see INTEGRATION.md for the stub).  Every entry
+ * point cites the reference function (file:line under /root/reference) whose value computation it
+ * replaces.
+ *
+ * Conventions
+ *  - Field elements are halo2curves bn256::Fr exactly as they sit in Rust memory: 32 bytes,
+ *    4 x u64 little-endian limbs of x*2^256 mod r (Montgomery form), canonical (< r).  Arrays are
+ *    row-major and contiguous.  No conversion happens on either side of the boundary.
+ *  - Every function returns 0 on success or a negative H2SVD_E* code; nothing unwinds, nothing
+ *    aborts.  h2svd_last_error() returns a static/thread-local description of the last failure.
+ *  - A handle owns one CUDA device, one stream and a grow-only device workspace.  It is NOT
+ *    thread-safe (it mirrors the reference's `&mut Context`): one handle per thread / per GPU.
+ *  - Functions without suffix take HOST pointers (pageable or pinned) and do H2D + kernels + D2H
+ *    before returning.  Functions ending in _dev take DEVICE pointers on the handle's device, are
+ *    asynchronous on the handle's stream (h2svd_sync to wait) and never touch host memory.
+ *  - There is no CPU fallback: without a usable sm_100-class GPU h2svd_create fails.
+ */
+#ifndef H2SVD_B200_H
+#define H2SVD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct h2svd_fr { uint64_t l[4]; } h2svd_fr;      /* bn256::Fr, Montgomery, canonical */
+typedef struct h2svd_ctx h2svd_ctx;                       /* opaque handle */
+
+enum {
+    H2SVD_OK = 0,
+    H2SVD_EINVAL = -1,    /* bad argument (null pointer, shape mismatch, parameter out of range) */
+    H2SVD_ECUDA = -2,     /* CUDA runtime error (message in h2svd_last_error) */
+    H2SVD_ENOMEM = -3,    /* device or host allocation failed */
+    H2SVD_ENODEV = -4,    /* no usable GPU: there is no CPU fallback */
+    H2SVD_ERANGE = -5     /* a non-canonical field element (>= r) was found in an input */
+};
+
+const char *h2svd_last_error(void);
+const char *h2svd_version(void);
+
+/* ---- handle ------------------------------------------------------------------------------------ */
+/* device < 0 selects the current CUDA device.  `stream` is a cudaStream_t to adopt (e.g. a torch
+ * stream) or NULL to let the handle create its own non-blocking stream. */
+int h2svd_create(h2svd_ctx **out, int device, void *stream);
+void h2svd_destroy(h2svd_ctx *ctx);
+int h2svd_sync(h2svd_ctx *ctx);
+void *h2svd_stream(h2svd_ctx *ctx);
+int h2svd_device(h2svd_ctx *ctx);
+int h2svd_sm_count(h2svd_ctx *ctx);
+/* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
+uint64_t h2svd_launch_count(h2svd_ctx *ctx);
+
+/* ---- K1: field mat-mul ---------------------------------------------------------------------------
+ * Replaces field_mat_mul (src/matrix/mod.rs:510-537), the O(N^3) loop inside
+ * honest_prover_mat_mul (:546-568).  c[n x m] = a[n x k] * b[k x m] over Fr.  With
+ * b_transposed != 0, `b` holds the m x k matrix B^T (what ZkMatrix::transpose_matrix, :408, would
+ * have been called on), so callers such as check_svd_phase0 (src/svd/mod.rs:96,109,112) need not
+ * materialise the transpose.  Asserts of the reference (:515) become H2SVD_EINVAL. */
+int h2svd_fr_matmul(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *c, size_t n,
+                    size_t k, size_t m, int b_transposed);
+int h2svd_fr_matmul_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *c,
+                        size_t n, size_t k, size_t m, int b_transposed);
+
+/* ---- K2/K3: Freivalds witness ----------------------------------------------------------------------
+ * Replaces the value computation of ZkMatrix::verify_mul (src/matrix/mod.rs:299-342):
+ *   powers[m]       v_i = gamma^i               (:316-326; v_0 = 1 is the `one` witness of :318)
+ *   prefix_cv[n*m]  running sums of c_s . v     (:335 -> field_mat_vec_mul :574-599)
+ *   prefix_bv[k*m]  running sums of b . v       (:336)
+ *   prefix_abv[n*k] running sums of a . (b v)   (:337)
+ *   diff[n], is_zero[n], inv[n]                 the Witness cells of gate.is_equal (:339-341):
+ *                                               diff = (c_s v)_i - (a b v)_i, is_zero in {0,1},
+ *                                               inv = 1 if diff == 0 else diff^-1
+ * i.e. every `Witness`-kind advice value of verify_mul; Existing/Constant cells are re-emitted by
+ * the caller from its own inputs.  Shape asserts (:307-310) -> H2SVD_EINVAL. */
+int h2svd_freivalds_witness(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b,
+                            const h2svd_fr *c_s, const h2svd_fr *gamma, size_t n, size_t k,
+                            size_t m, h2svd_fr *powers, h2svd_fr *prefix_cv, h2svd_fr *prefix_bv,
+                            h2svd_fr *prefix_abv, h2svd_fr *diff, h2svd_fr *is_zero,
+                            h2svd_fr *inv);
+int h2svd_freivalds_witness_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b,
+                                const h2svd_fr *c_s, const h2svd_fr *gamma, size_t n, size_t k,
+                                size_t m, h2svd_fr *powers, h2svd_fr *prefix_cv,
+                                h2svd_fr *prefix_bv, h2svd_fr *prefix_abv, h2svd_fr *diff,
+                                h2svd_fr *is_zero, h2svd_fr *inv);
+
+/* Building blocks of the above, exposed for row-sharded (multi-GPU) callers:
+ * gamma powers (:316-326) and one prefix-sum mat-vec (field_mat_vec_mul :574-599). */
+int h2svd_gamma_powers_dev(h2svd_ctx *ctx, const h2svd_fr *gamma, size_t d, h2svd_fr *out);
+int h2svd_mat_vec_prefix_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, size_t rows,
+                             size_t len, h2svd_fr *out_prefix);
+/* out[i] = src[i*stride + offset]  (gathers the last running sum of every row) */
+int h2svd_gather_dev(h2svd_ctx *ctx, const h2svd_fr *src, size_t count, size_t stride,
+                     size_t offset, h2svd_fr *out);
+/* is_equal witness cells (:339-341) for two vectors of row totals */
+int h2svd_is_equal_witness_dev(h2svd_ctx *ctx, const h2svd_fr *x, const h2svd_fr *y, size_t count,
+                               h2svd_fr *diff, h2svd_fr *is_zero, h2svd_fr *inv);
+
+/* ---- K4: rescale witness -----------------------------------------------------------------------------
+ * Replaces the value computation of ZkMatrix::rescale_matrix (src/matrix/mod.rs:354-375), i.e. one
+ * FixedPointChip041::signed_div_scale per element (:369; also ZkVector::inner_product :104).
+ * For each of `count` elements: out_q = floor(a_signed / 2^P) as a field element (the returned
+ * matrix entry), and out_wit[e*W .. (e+1)*W) = the W `Witness`-kind advice values of that call in
+ * assignment order (a_shift, rem, div, 4 limb-decomposition blocks, q).
+ * shift_bits / a_num_bits are the chip's constants (third-party, unpinned): pass -1 for the
+ * defaults 3P / 4P.  h2svd_rescale_witness_count returns W (= 4 + 4(n_d + n_r)) or <0. */
+int h2svd_rescale_witness_count(int precision_bits, int lookup_bits, int shift_bits,
+                                int a_num_bits);
+int h2svd_rescale_witness(h2svd_ctx *ctx, const h2svd_fr *c_s, size_t count, int precision_bits,
+                          int lookup_bits, int shift_bits, int a_num_bits, h2svd_fr *out_q,
+                          h2svd_fr *out_wit);
+int h2svd_rescale_witness_dev(h2svd_ctx *ctx, const h2svd_fr *c_s, size_t count,
+                              int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
+                              h2svd_fr *out_q, h2svd_fr *out_wit);
+
+/* ---- K5/K6: ZkVector witnesses -------------------------------------------------------------------------
+ * h2svd_zkvec_inner_prefix: running sums of gate.inner_product(u = x, v = self) for `batch`
+ *   independent vector pairs (ZkVector::inner_product, src/matrix/mod.rs:79-100; _norm_square :111
+ *   is the x == self case).  out_prefix[b*len + j] = sum_{t<=j} x[b][t]*self[b][t]; the caller feeds
+ *   out_prefix[b*len + len-1] to h2svd_rescale_witness for the signed_div_scale of :104.
+ * h2svd_zkvec_sub: diff[i] = self[i] - x[i], the Witness cell of each fpchip.qsub in
+ *   ZkVector::_dist_square (:143-146).
+ * h2svd_isqrt_fixed: value model of fpchip.qsqrt (:130, :163): floor(sqrt(a * 2^P)) for a < 2^128
+ *   (third-party semantics, parity unpinned -- SURVEY.md A.6). */
+int h2svd_zkvec_inner_prefix(h2svd_ctx *ctx, const h2svd_fr *x, const h2svd_fr *self, size_t batch,
+                             size_t len, h2svd_fr *out_prefix);
+int h2svd_zkvec_inner_prefix_dev(h2svd_ctx *ctx, const h2svd_fr *x, const h2svd_fr *self,
+                                 size_t batch, size_t len, h2svd_fr *out_prefix);
+int h2svd_zkvec_sub(h2svd_ctx *ctx, const h2svd_fr *self, const h2svd_fr *x, size_t count,
+                    h2svd_fr *out);
+int h2svd_zkvec_sub_dev(h2svd_ctx *ctx, const h2svd_fr *self, const h2svd_fr *x, size_t count,
+                        h2svd_fr *out);
+int h2svd_isqrt_fixed(h2svd_ctx *ctx, const h2svd_fr *a, size_t count, int precision_bits,
+                      h2svd_fr *out);
+int h2svd_isqrt_fixed_dev(h2svd_ctx *ctx, const h2svd_fr *a, size_t count, int precision_bits,
+                          h2svd_fr *out);
+
+/* ---- quantization ------------------------------------------------------------------
+ * FixedPointChip041::quantization as used by ZkMatrix::new / ZkVector::new
+ * (src/matrix/mod.rs:29-40, :230-252): f64 -> Fr, sign-magnitude round-half-up of |x|*2^P,
+ * negatives as r - q. */
+int h2svd_quantize(h2svd_ctx *ctx, const double *x, size_t count, int precision_bits,
+                   h2svd_fr *out);
+int h2svd_quantize_dev(h2svd_ctx *ctx, const double *x, size_t count, int precision_bits,
+                       h2svd_fr *out);
+
+/* ---- input validation ----------------------------------------------------------------------------------------
+ * Returns H2SVD_OK if all `count` device-resident elements are canonical (< r), else H2SVD_ERANGE. */
+int h2svd_check_canonical_dev(h2svd_ctx *ctx, const h2svd_fr *x, size_t count);
+
+/* ---- measurement aids -------------------------------------------------------------------------------------------
+ * Integer-pipe micro-benchmark used as the mat-mul roofline denominator.  kind: 0 = mad.lo.u32
+ * (IMAD), 1 = mad.wide.u32 (IMAD.WIDE.U32), 2 = IMAD.WIDE.U32.X carry chains exactly as the mat-mul
+ * inner loop issues them, 3 = full 8x8 lazy multiply-accumulate (64 IMAD.WIDE + 16 IADD3.X).
+ * Writes achieved multiply instructions per second (thread-level ops) to *ops_per_s. */
+int h2svd_microbench_imad(h2svd_ctx *ctx, int kind, int iters, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2SVD_B200_H */

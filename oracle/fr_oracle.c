@@ -257,7 +257,7 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int orc_rescale_witness_count(int P, int lb, int S, int A) {
     if (S < 0) S = 3 * P;
     if (A < 0) A = 4 * P;
-    if (P < 1 || P > 63 || lb < 1 || lb > 32 || S < P || S > 252 || A < P) return -1;
+    if (P < 1 || P > 63 || lb < 1 || lb > 32 || S < P || S > 252 || A <= P) return -1;
     int n_d = ceil_div(A - P + 1, lb), n_r = ceil_div(P + 1, lb);
     if (n_d * lb > 253 || n_r * lb > 253) return -1;
     return 4 + 4 * (n_d + n_r);

@@ -13,7 +13,7 @@ IS pinned:
   * the in-tree loop semantics of src/matrix/mod.rs (cited per function);
   * the halo2-base 0.4.1 cell layout, validated against the advice / lookup
     cell-count formulas of the reference README.md:67 (135N^2 / 26N^2 at P=32,
-    201N^2 / 48N^2 at P=63) in tests/test_oracle_layout.py.
+    201N^2 / 48N^2 at P=63) in tests/test_oracle.py.
 Unpinned: FixedPointChip041::signed_div_scale's shift / a_num_bits constants
 (runtime parameters here, defaults S=3P, A=4P) and qsqrt.
 
@@ -219,16 +219,18 @@ def isqrt_fixed(a: int, precision_bits: int) -> int:
 class AssignedValue:
     value: int
     index: int
+    ctx_id: int = 0   # which virtual column (phase-0 / phase-1 context) the cell lives in
 
 
 class Context:
     """Virtual advice column of one halo2-base Context (A.2)."""
 
-    def __init__(self) -> None:
+    def __init__(self, ctx_id: int = 0) -> None:
+        self.ctx_id = ctx_id
         self.advice: List[int] = []
         self.kind: List[str] = []        # 'W' | 'E' | 'C' per cell
         self.selector: List[bool] = []
-        self.copies: List[Tuple[int, int]] = []
+        self.copies: List[Tuple[Tuple[int, int], Tuple[int, int]]] = []  # ((ctx, cell), (ctx, cell))
         self.constants: List[Tuple[int, int]] = []  # (cell, value)
         self.lookups: List[int] = []
 
@@ -237,7 +239,7 @@ class Context:
         idx = len(self.advice)
         if kind == "E":
             self.advice.append(x.value)
-            self.copies.append((x.index, idx))
+            self.copies.append(((x.ctx_id, x.index), (self.ctx_id, idx)))
         elif kind == "C":
             self.advice.append(x % R_MOD)
             self.constants.append((idx, x % R_MOD))
@@ -257,7 +259,7 @@ class Context:
     def get(self, i: int) -> AssignedValue:
         if i < 0:
             i += len(self.advice)
-        return AssignedValue(self.advice[i], i)
+        return AssignedValue(self.advice[i], i, self.ctx_id)
 
     def load_witness(self, v: int) -> AssignedValue:
         self._push(("W", v))
@@ -268,7 +270,7 @@ class Context:
         return self.get(-1)
 
     def constrain_equal(self, a: AssignedValue, b: AssignedValue) -> None:
-        self.copies.append((a.index, b.index))
+        self.copies.append(((a.ctx_id, a.index), (b.ctx_id, b.index)))
 
     def witness_values(self) -> List[int]:
         return [v for v, k in zip(self.advice, self.kind) if k == "W"]
@@ -600,26 +602,31 @@ def check_svd_phase1(ctx, fp, m, u, v, u_t, v_t, m_times_vt, u_times_ut, v_times
 
 # --- MockProver-equivalent check of one Context ------------------------------
 
-def mock_prove(ctx: Context, lookup_bits: int) -> List[str]:
-    """Returns the list of violated constraints (empty == satisfied):
-    gate q*(a + b*c - d) on every selected row, copy constraints, constant
-    equalities and lookup-range membership (value < 2^lookup_bits)."""
+def mock_prove(contexts, lookup_bits: int) -> List[str]:
+    """MockProver-equivalent check of one Context or a list of Contexts (phase 0, phase 1, ...).
+    Returns the list of violated constraints (empty == satisfied): gate q*(a + b*c - d) on every
+    selected row, copy constraints (also across contexts), constant equalities and lookup-range
+    membership (value < 2^lookup_bits)."""
+    if isinstance(contexts, Context):
+        contexts = [contexts]
+    by_id = {c.ctx_id: c for c in contexts}
     errs = []
-    adv = ctx.advice
-    for i, sel in enumerate(ctx.selector):
-        if sel:
-            a, b, c, d = adv[i:i + 4]
-            if (a + b * c - d) % R_MOD != 0:
-                errs.append(f"gate@{i}")
-    for x, y in ctx.copies:
-        if adv[x] != adv[y]:
-            errs.append(f"copy@{x},{y}")
-    for i, v in ctx.constants:
-        if adv[i] != v:
-            errs.append(f"const@{i}")
-    for i in ctx.lookups:
-        if adv[i] >= (1 << lookup_bits):
-            errs.append(f"lookup@{i}")
+    for ctx in contexts:
+        adv, cid = ctx.advice, ctx.ctx_id
+        for i, sel in enumerate(ctx.selector):
+            if sel:
+                a, b, c, d = adv[i:i + 4]
+                if (a + b * c - d) % R_MOD != 0:
+                    errs.append(f"gate@{cid}:{i}")
+        for (ca, ia), (cb, ib) in ctx.copies:
+            if by_id[ca].advice[ia] != by_id[cb].advice[ib]:
+                errs.append(f"copy@{ca}:{ia},{cb}:{ib}")
+        for i, v in ctx.constants:
+            if adv[i] != v:
+                errs.append(f"const@{cid}:{i}")
+        for i in ctx.lookups:
+            if adv[i] >= (1 << lookup_bits):
+                errs.append(f"lookup@{cid}:{i}")
     return errs
 
 

@@ -1,0 +1,46 @@
+// Host build of the product's field-arithmetic headers (fr.cuh / fr_acc.cuh) so that the exact
+// code the GPU runs outside the PTX chains is unit-tested on the CPU against the oracle.
+// Compiled by tests/test_fr_host.py with g++; never shipped.
+#include <cstddef>
+#include <cstring>
+
+#include "../../halo2-svd041_b200/csrc/fr_acc.cuh"
+
+using fr::Fr;
+
+extern "C" {
+void hs_mont_mul(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::mont_mul(a[i], b[i]); }
+void hs_add(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::add(a[i], b[i]); }
+void hs_sub(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::sub(a[i], b[i]); }
+void hs_to_mont(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::to_mont(a[i]); }
+void hs_from_mont(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::from_mont(a[i]); }
+void hs_shr(const Fr* a, int s, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::shr(a[i], s); }
+void hs_low_bits(const Fr* a, int bits, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::low_bits(a[i], bits); }
+void hs_pow2(int s, Fr* o) { *o = fr::pow2(s); }
+int hs_is_canonical(const Fr* a) { return fr::is_canonical(*a) ? 1 : 0; }
+void hs_one(Fr* o) { *o = fr::one(); }
+// lazy dot product exactly as the mat-mul inner loop accumulates it (host fallback of chain4)
+void hs_lazy_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {
+    fr::WideAcc w;
+    fr::acc_clear(w);
+    for (size_t i = 0; i < k; i++) fr::mul_acc(w, a[i].l, b[i].l);
+    *o = fr::acc_finalize(w);
+}
+// C = A*B with the same lazy accumulation (row-major), for shape/ragged checks of the arithmetic
+void hs_lazy_matmul(const Fr* A, const Fr* B, Fr* C, size_t n, size_t k, size_t m) {
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = 0; j < m; j++) {
+            fr::WideAcc w;
+            fr::acc_clear(w);
+            for (size_t t = 0; t < k; t++) fr::mul_acc(w, A[i * k + t].l, B[t * m + j].l);
+            C[i * m + j] = fr::acc_finalize(w);
+        }
+}
+// worst-case accumulator stress: k copies of the same product
+void hs_lazy_repeat(const Fr* a, const Fr* b, size_t k, Fr* o) {
+    fr::WideAcc w;
+    fr::acc_clear(w);
+    for (size_t i = 0; i < k; i++) fr::mul_acc(w, a->l, b->l);
+    *o = fr::acc_finalize(w);
+}
+}

@@ -1,0 +1,110 @@
+"""CPU tests of the PRODUCT's field-arithmetic headers (csrc/fr.cuh, csrc/fr_acc.cuh) compiled for
+the host: the portable code is what the GPU runs outside the PTX carry chains, and the host
+fallback of the chain mirrors the PTX bit for bit (positions, carry counters, final fold + REDC)."""
+import ctypes as ct
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import ROOT, raw_limbs
+
+R = po.R_MOD
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("frhost") / "libfrhost.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "host", "fr_host_shim.cpp")])
+    return ct.CDLL(so)
+
+
+def P(a):
+    return a.ctypes.data_as(ct.c_void_p)
+
+
+def unraw(a):
+    return [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a.reshape(-1, 4)]
+
+
+def _vals():
+    rng = random.Random(7)
+    edge = [0, 1, 2, R - 1, R - 2, 1 << 253, (1 << 252) - 1, po.MONT_R, po.MONT_R2, (R - 1) // 2]
+    return edge + [rng.randrange(R) for _ in range(200)]
+
+
+def test_field_ops_match_bigint(shim):
+    vals = _vals()
+    n = len(vals)
+    a, b = raw_limbs(vals), raw_limbs(vals[::-1])
+    o = np.zeros_like(a)
+    shim.hs_mont_mul(P(a), P(b), P(o), n)
+    assert unraw(o) == [x * y * po.MONT_RINV % R for x, y in zip(vals, vals[::-1])]
+    shim.hs_add(P(a), P(b), P(o), n)
+    assert unraw(o) == [(x + y) % R for x, y in zip(vals, vals[::-1])]
+    shim.hs_sub(P(a), P(b), P(o), n)
+    assert unraw(o) == [(x - y) % R for x, y in zip(vals, vals[::-1])]
+    shim.hs_to_mont(P(a), P(o), n)
+    assert unraw(o) == [po.to_mont(x) for x in vals]
+    shim.hs_from_mont(P(a), P(o), n)
+    assert unraw(o) == [po.from_mont(x) for x in vals]
+    one = np.zeros((1, 4), dtype=np.uint64)
+    shim.hs_one(P(one))
+    assert unraw(one) == [po.MONT_R]
+    assert shim.hs_is_canonical(P(raw_limbs([R - 1]))) == 1
+    assert shim.hs_is_canonical(P(raw_limbs([R]))) == 0
+    assert shim.hs_is_canonical(P(raw_limbs([(1 << 256) - 1]))) == 0
+
+
+def test_shift_and_mask_helpers(shim):
+    vals = _vals()
+    n = len(vals)
+    a = raw_limbs(vals)
+    o = np.zeros_like(a)
+    for s in [0, 1, 19, 31, 32, 33, 63, 64, 65, 127, 128, 129, 190, 255]:
+        shim.hs_shr(P(a), s, P(o), n)
+        assert unraw(o) == [x >> s for x in vals]
+        shim.hs_low_bits(P(a), s, P(o), n)
+        assert unraw(o) == [x & ((1 << s) - 1) for x in vals]
+        shim.hs_pow2(s, P(o))
+        assert unraw(o[:1]) == [1 << s]
+    shim.hs_low_bits(P(a), 256, P(o), n)
+    assert unraw(o) == vals
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 17, 64, 1000])
+def test_lazy_dot_product(shim, k):
+    rng = random.Random(k)
+    A = [rng.randrange(R) for _ in range(k)]
+    B = [rng.randrange(R) for _ in range(k)]
+    o = np.zeros((1, 4), dtype=np.uint64)
+    shim.hs_lazy_dot(P(raw_limbs(A)), P(raw_limbs(B)), k, P(o))
+    assert unraw(o) == [sum(x * y for x, y in zip(A, B)) * po.MONT_RINV % R]
+
+
+def test_lazy_accumulator_headroom(shim):
+    """Largest operands repeated k times: exercises every carry counter and the 2^480 fold."""
+    mx = raw_limbs([R - 1])
+    o = np.zeros((1, 4), dtype=np.uint64)
+    for k in [1, 7, 100000, 3000000]:
+        shim.hs_lazy_repeat(P(mx), P(mx), k, P(o))
+        assert unraw(o) == [k * (R - 1) * (R - 1) * po.MONT_RINV % R]
+    top = raw_limbs([(1 << 256) - 1])  # non-canonical limbs: still exact as integers
+    shim.hs_lazy_repeat(P(top), P(top), 1000, P(o))
+    assert unraw(o) == [1000 * ((1 << 256) - 1) ** 2 * po.MONT_RINV % R]
+
+
+def test_lazy_matmul_ragged(shim):
+    rng = random.Random(5)
+    n, k, m = 5, 9, 3
+    A = [rng.randrange(R) for _ in range(n * k)]
+    B = [rng.randrange(R) for _ in range(k * m)]
+    C = np.zeros((n * m, 4), dtype=np.uint64)
+    shim.hs_lazy_matmul(P(raw_limbs(A)), P(raw_limbs(B)), P(C), n, k, m)
+    exp = [sum(A[i * k + t] * B[t * m + j] for t in range(k)) * po.MONT_RINV % R
+           for i in range(n) for j in range(m)]
+    assert unraw(C) == exp

@@ -1,0 +1,145 @@
+"""CPU tests of the oracle itself: constants, C restatement vs Python big-int spec, layout KATs
+against the reference README's published cell counts, and the config-0 accept/reject behaviour."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import corac
+from oracle import pyoracle as po
+
+
+def test_field_constants_match_halo2curves():
+    # bn256::Fr constants as published by halo2curves
+    assert po.R_MOD == 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert po.R_MOD.bit_length() == 254
+    assert po.MONT_R == 0x0E0A77C19A07DF2F666EA36F7879462E36FC76959F60CD29AC96341C4FFFFFFB
+    assert po.MONT_R2 == 0x0216D0B17F4E44A58C49833D53BB808553FE3AB1E35C59E31BB8E645AE216DA7
+    assert po.MONT_INV64 == 0xC2E1F593EFFFFFFF
+    # 2-adicity 28: r - 1 = 2^28 * odd
+    assert (po.R_MOD - 1) % (1 << 28) == 0 and ((po.R_MOD - 1) >> 28) % 2 == 1
+    one = po.pack_mont([1])[0]
+    assert [int(x) for x in one] == [0xAC96341C4FFFFFFB, 0x36FC76959F60CD29, 0x666EA36F7879462E,
+                                     0x0E0A77C19A07DF2F]
+
+
+def _rnd(rng, n):
+    return [rng.randrange(po.R_MOD) for _ in range(n)]
+
+
+def test_c_oracle_matches_python_oracle():
+    rng = random.Random(1)
+    n, k, m = 5, 7, 4
+    A = [_rnd(rng, k) for _ in range(n)]
+    B = [_rnd(rng, m) for _ in range(k)]
+    a = po.pack_mont(sum(A, [])).reshape(n, k, 4)
+    b = po.pack_mont(sum(B, [])).reshape(k, m, 4)
+    assert po.unpack_mont(corac.field_mat_mul(a, b)) == sum(po.field_mat_mul(A, B), [])
+    g = _rnd(rng, 1)
+    assert po.unpack_mont(corac.gamma_powers(po.pack_mont(g), 9)) == po.gamma_powers(g[0], 9)
+    v = _rnd(rng, k)
+    assert po.unpack_mont(corac.mat_vec_prefix(a, po.pack_mont(v))) == sum(po.mat_vec_prefix(A, v), [])
+    # threaded == single-threaded
+    assert (corac.field_mat_mul(a, b, threads=0) == corac.field_mat_mul(a, b)).all()
+
+
+@pytest.mark.parametrize("P,lb", [(32, 19), (42, 19), (63, 19), (32, 12), (63, 8), (32, 20)])
+def test_c_oracle_rescale_matches_python(P, lb):
+    rng = random.Random(P * 100 + lb)
+    prm = po.RescaleParams(P, lb)
+    vals = [rng.randrange(-(1 << (3 * P - 1)), 1 << (3 * P - 1)) % po.R_MOD for _ in range(40)]
+    vals += [0, 1, po.R_MOD - 1, (1 << (3 * P)) - 1, (po.R_MOD - (1 << (3 * P))) % po.R_MOD] + _rnd(rng, 5)
+    q, rem, wit = corac.rescale_witness(po.pack_mont(vals), P, lb)
+    assert corac.rescale_witness_count(P, lb) == prm.W
+    for i, x in enumerate(vals):
+        qq, rr, ww = po.signed_div_scale_witness(x, prm)
+        assert po.unpack_mont(wit[i]) == ww
+        assert po.unpack_mont(q[i:i + 1]) == [qq] and po.unpack_mont(rem[i:i + 1]) == [rr]
+
+
+def test_rescale_is_floor_division_of_signed_value():
+    P, lb = 32, 19
+    prm = po.RescaleParams(P, lb)
+    for s in [5 << 40, -(5 << 40), (1 << 32) + 1, -((1 << 32) + 1), -1, 0, 12345678901234567]:
+        q, rem, _ = po.signed_div_scale_witness(s % po.R_MOD, prm)
+        assert po.signed(q) == s >> P  # floor toward -inf
+        assert rem == s & ((1 << P) - 1)
+        assert po.signed(q) * (1 << P) + rem == s
+
+
+def test_rescale_witness_count_matches_readme_cost_hints():
+    # README.md:51 "60N^2 to 100N^2 depending on the lookup table size" and src/matrix/mod.rs:78
+    # "+ 90 constraints" at P=32: A = 4P reproduces 60 (lb=20), 90 (lb=12), 102 (lb=10)
+    assert po.RescaleParams(32, 20).cells == 60
+    assert po.RescaleParams(32, 12).cells == 90
+    assert po.RescaleParams(32, 10).cells == 102
+    assert po.RescaleParams(63, 19).W == 60 and po.RescaleParams(63, 19).cells == 102
+
+
+def test_quantize_and_isqrt():
+    xs = np.array([0.0, 1.5, -1.5, 3.14159, -99.999, 1e-12, -1e-12, 0.5 / (1 << 32), -0.5 / (1 << 32)])
+    for P in (32, 42, 63):
+        assert po.unpack_mont(corac.quantize(xs, P)) == [po.quantize(float(x), P) for x in xs]
+    vals = [0, 1, 2, 3, 4, (1 << 64) + 5, (1 << 100) + 12345, (1 << 127)]
+    assert po.unpack_mont(corac.isqrt_fixed(po.pack_mont(vals), 32)) == [po.isqrt_fixed(x, 32) for x in vals]
+
+
+def _svd_circuit(inputs, P, lb, err_size):
+    fp = po.FixedPointChip(P, lb)
+    ctx = po.Context()
+    m = po.ZkMatrix.new(ctx, fp, inputs["m"])
+    u = po.ZkMatrix.new(ctx, fp, inputs["u"])
+    v = po.ZkMatrix.new(ctx, fp, inputs["v"])
+    d = po.ZkVector.new(ctx, fp, inputs["d"])
+    err_svd, err_u = po.err_calc(P, err_size, 100.0, 1e-10, 1e-10)
+    out = po.check_svd_phase0(ctx, fp, m, u, v, d, err_svd, err_u, 30)
+    ctx1 = po.Context(ctx_id=1)
+    gamma = ctx1.load_witness(0x1234567890ABCDEF1234567890ABCDEF % po.R_MOD)
+    po.check_svd_phase1(ctx1, fp, m, u, v, *out, gamma)
+    return ctx, ctx1
+
+
+@pytest.mark.parametrize("P,cells0,lookups,cells1", [(32, 135, 26, 27), (63, 201, 48, 27)])
+def test_layout_reproduces_readme_cell_counts(P, cells0, lookups, cells1):
+    """README.md:67: 135N^2 (+27N^2) advice cells, 26N^2 lookups at P=32/lb=19;
+    201N^2 (+27N^2), 48N^2 at P=63.  N^2 coefficient via second differences at N=4,8,12."""
+    r = {}
+    for N in (4, 8, 12):
+        good, _ = po.make_svd_inputs(N, N, 1)
+        ctx, ctx1 = _svd_circuit(good, P, 19, 1000)
+        r[N] = (len(ctx.advice), len(ctx.lookups), len(ctx1.advice))
+    coef = [(r[12][i] - 2 * r[8][i] + r[4][i]) / 32 for i in range(3)]
+    assert coef == [cells0, lookups, cells1]
+
+
+def test_config0_matrix_passes_and_matrix_wrong_fails():
+    """BASELINE.json configs[0]: 8x8 input-creator.py matrix, P=42, lb=19 (examples/svd_example.rs:69,319):
+    `matrix` satisfies every gate / copy / lookup, `matrix-wrong` violates a check_mat_diff lookup."""
+    good, wrong = po.make_svd_inputs(8, 8, 2024)
+    ctx, ctx1 = _svd_circuit(good, 42, 19, 8)
+    assert po.mock_prove([ctx, ctx1], 19) == []
+    ctxw, ctxw1 = _svd_circuit(wrong, 42, 19, 8)
+    errs = po.mock_prove([ctxw, ctxw1], 19)
+    # rejected by the phase-0 range check check_mat_diff(u*d, m*v^T, err_svd) (src/svd/mod.rs:104):
+    # limb running-sum != value (copy) and/or limb out of the lookup table -- never by a phase-1
+    # cell: verify_mul checks only a*b = c_s, which an honest prover satisfies for any m
+    assert errs and all(e.startswith(("lookup@0", "copy@0")) for e in errs)
+
+
+def test_freivalds_oracle_detects_wrong_product():
+    rng = random.Random(3)
+    n, k, m = 4, 5, 3
+    A = [_rnd(rng, k) for _ in range(n)]
+    B = [_rnd(rng, m) for _ in range(k)]
+    CS = po.field_mat_mul(A, B)
+    a = po.pack_mont(sum(A, [])).reshape(n, k, 4)
+    b = po.pack_mont(sum(B, [])).reshape(k, m, 4)
+    cs = po.pack_mont(sum(CS, [])).reshape(n, m, 4)
+    g = po.pack_mont(_rnd(rng, 1))
+    fw = corac.freivalds_witness(a, b, cs, g)
+    assert not np.any(fw["diff"]) and po.unpack_mont(fw["is_zero"]) == [1] * n
+    cs2 = cs.copy()
+    cs2[2, 1] = po.pack_mont([5])[0]
+    fw2 = corac.freivalds_witness(a, b, cs2, g)
+    d, iv, z = (po.unpack_mont(fw2[x]) for x in ("diff", "inv", "is_zero"))
+    assert d[2] != 0 and d[2] * iv[2] % po.R_MOD == 1 and z[2] == 0 and z[0] == 1
