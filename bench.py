@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Headline benchmark: Fr mul-add/s for the mat-mul + Freivalds + rescale witness, N=1024, P=63,
+LOOKUP_BITS=19 (BASELINE.json metric / configs[3]) on 1..8 B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA kernels)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU restatement on the host cores
+
+A "step" = one pass of the hot path over one (A, B) pair: honest_prover_mat_mul (C = A.B),
+rescale_matrix witnesses of C, verify_mul (Freivalds) witnesses.  Rows of A/C are sharded over the
+ranks ("strong" scaling: the job is fixed at N=1024), B is replicated, (B v) is all-gathered (NCCL).
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DEFAULT, P_BITS, LOOKUP_BITS = 1024, 63, 19
+METRIC = "Fr mul-add/s for mat-mul+Freivalds+rescale witness, N=1024"
+UNIT = "Fr mul-add/s"
+
+
+def make_inputs(n: int, k: int, m: int, seed: int = 20261018):
+    """Seeded re-implementation of the reference's input-creator.py:23-28 distribution (f64)."""
+    rng = np.random.default_rng(seed)
+
+    def mat(r, c):
+        x = rng.uniform(-10.0, 10.0, size=(r, c))
+        return x / np.linalg.norm(x, ord=2) * rng.uniform(1, 100)
+
+    a, b = mat(n, k), mat(k, m)
+    gamma = rng.integers(0, 1 << 64, size=4, dtype=np.uint64)
+    gamma[3] &= np.uint64((1 << 60) - 1)   # a fixed non-trivial canonical challenge
+    return a, b, gamma
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks() -> dict:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except OSError:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(n: int, threads: int, mm_rows: int, rs_elems: int) -> dict:
+    """Times the C oracle (CPU restatement of the reference loops) on a bounded sample of the same
+    workload and extrapolates linearly to the full job.  The only place bench.py executes oracle/."""
+    from oracle import corac
+    a_f, b_f, gamma = make_inputs(n, n, n)
+    mm_rows = min(mm_rows, n)
+    a = corac.quantize(a_f[:mm_rows], P_BITS)
+    b = corac.quantize(b_f, P_BITS)
+    t0 = time.perf_counter()
+    c = corac.field_mat_mul(a, b, threads=threads)                       # mm_rows of n rows
+    t_mm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    powers = corac.gamma_powers(gamma.reshape(1, 4), n)
+    corac.mat_vec_prefix(c, powers, threads=threads)                     # rows of C.v
+    pbv = corac.mat_vec_prefix(b[:mm_rows], powers, threads=threads)     # rows of B.v
+    t_fr_rows = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    flat = np.ascontiguousarray(c.reshape(-1, 4)[:rs_elems])
+    corac.rescale_witness(flat, P_BITS, LOOKUP_BITS, threads=threads)
+    t_rs = time.perf_counter() - t0
+    del pbv
+    # extrapolate: mat-mul rows -> n rows; 2 sampled mat-vecs of mm_rows rows -> 3 mat-vecs of n rows
+    full = t_mm * n / mm_rows + t_fr_rows * (3 * n) / (2 * mm_rows) + t_rs * (n * n) / flat.shape[0]
+    units = n ** 3 + 3 * n * n + (n - 1)
+    return {"value": units / full, "seconds_full_job_extrapolated": full,
+            "sample": f"{mm_rows}/{n} rows of the mat-mul and of 2 of the 3 Freivalds mat-vecs, "
+                      f"{flat.shape[0]}/{n * n} rescale elements; linear extrapolation",
+            "t_sample_s": t_mm + t_fr_rows + t_rs}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.n
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(n, threads, mm_rows=max(16, 2 * threads), rs_elems=16384)
+        if i >= args.warmup:
+            vals.append(r)
+            secs.append(r["seconds_full_job_extrapolated"])
+    ms = float(np.mean(secs)) * 1e3
+    units = n ** 3 + 3 * n * n + (n - 1)
+    value = units / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr, 256-bit modular)",
+        "data": "synthetic",
+        "config": {"workload": f"honest_prover_mat_mul + rescale_matrix + verify_mul witness, square N={n}, "
+                               f"PRECISION_BITS={P_BITS}, LOOKUP_BITS={LOOKUP_BITS}", "n": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": vals[-1]["sample"] + " (C restatement of the reference loops; the Rust "
+                                                        "reference cannot be built here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    pkg = importlib.import_module("halo2-svd041_b200")
+    wl = importlib.import_module("halo2-svd041_b200.workload")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        comm = dist.group.WORLD
+
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+    h = pkg.Handle(local_rank, stream.cuda_stream)
+
+    n = k = m = args.n
+    plan = wl.ShardPlan(n, k, m, world, rank)
+    W = h.rescale_witness_count(P_BITS, LOOKUP_BITS)
+    bufs = wl.alloc_buffers(torch, plan, W, device)
+    r0, r1 = plan.rows
+    b0, b1 = plan.brows
+
+    # ---- synthetic inputs: f64 matrices -> pinned host -> GPU quantization kernel (product path)
+    a_f, b_f, gamma = make_inputs(n, k, m)
+    a_host = torch.from_numpy(np.ascontiguousarray(a_f[r0:r1])).pin_memory()
+    b_host = torch.from_numpy(np.ascontiguousarray(b_f)).pin_memory()
+    a_dev_f, b_dev_f = a_host.to(device, non_blocking=True), b_host.to(device, non_blocking=True)
+    h.quantize_dev(a_dev_f, P_BITS, bufs.a_slab)
+    h.quantize_dev(b_dev_f, P_BITS, bufs.b)
+    bufs.gamma.copy_(torch.from_numpy(gamma.view(np.int64).reshape(1, 4)))
+    h.sync()
+    # pinned host copies of the Fr inputs / outputs for the end-to-end leg
+    host_in = {"a": bufs.a_slab.cpu().pin_memory(), "b_rows": bufs.b[b0:b1].cpu().pin_memory(),
+               "b_full": bufs.b.cpu().pin_memory(), "gamma": bufs.gamma.cpu().pin_memory()}
+    out_names = ["c_slab", "q_slab", "wit_slab", "powers", "prefix_cv", "prefix_bv", "prefix_abv", "diff",
+                 "is_zero", "inv"]
+    host_out = {nm: torch.empty(getattr(bufs, nm).shape, dtype=torch.int64).pin_memory() for nm in out_names}
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def device_step(times=None):
+        e = [ev() for _ in range(4)] if times is not None else None
+        if e: e[0].record(stream)
+        wl.step_matmul(h, plan, bufs)
+        if e: e[1].record(stream)
+        wl.step_rescale(h, plan, bufs, P_BITS, LOOKUP_BITS)
+        if e: e[2].record(stream)
+        wl.step_freivalds(h, plan, bufs, dist, comm)
+        if e:
+            e[3].record(stream)
+            times.append(e)
+
+    def e2e_step():
+        # host -> device of this step's inputs (pinned), B row-slices all-gathered over NVLink
+        bufs.a_slab.copy_(host_in["a"], non_blocking=True)
+        bufs.gamma.copy_(host_in["gamma"], non_blocking=True)
+        if world > 1 and k % world == 0:
+            bufs.b[b0:b1].copy_(host_in["b_rows"], non_blocking=True)
+            dist.all_gather_into_tensor(bufs.b.view(-1, 4), bufs.b[b0:b1].reshape(-1, 4), group=comm)
+        else:
+            bufs.b.copy_(host_in["b_full"], non_blocking=True)
+        wl.run_step(h, plan, bufs, P_BITS, LOOKUP_BITS, dist, comm)
+        for nm in out_names:
+            host_out[nm].copy_(getattr(bufs, nm), non_blocking=True)
+        stream.synchronize()   # the step's result is on the host
+
+    launches0 = h.launch_count
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_events = []
+    launches_before = h.launch_count
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_buf.fill_(1)              # L2 flush between timed iterations (outside the event brackets)
+        device_step(step_events)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    gpu_launches = h.launch_count - launches_before
+    clocks = sampler.stop()
+    tot = [e[0].elapsed_time(e[3]) for e in step_events]
+    t_mm = [e[0].elapsed_time(e[1]) for e in step_events]
+    t_rs = [e[1].elapsed_time(e[2]) for e in step_events]
+    t_fr = [e[2].elapsed_time(e[3]) for e in step_events]
+    my_ms = torch.tensor([sum(tot) / len(tot), float(np.mean(t_mm)), float(np.mean(t_rs)), float(np.mean(t_fr))],
+                         dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(my_ms, op=dist.ReduceOp.MAX)
+    ms_step, ms_mm, ms_rs, ms_fr = [float(x) for x in my_ms.cpu()]
+
+    # ---- end-to-end timing (host buffers, copies inside the timed region) ----
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    e0, e1 = ev(), ev()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e2e_wall = (time.perf_counter() - t0) / e2e_steps
+    e2e_ms_t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms_t.cpu()[0])
+    h2d = sum(int(host_in[x].numel()) * 8 for x in (("a", "gamma", "b_rows") if (world > 1 and k % world == 0)
+                                                    else ("a", "gamma", "b_full")))
+    d2h = sum(int(host_out[x].numel()) * 8 for x in out_names)
+    bytes_t = torch.tensor([h2d, d2h], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
+    h2d_all, d2h_all = [int(x) for x in bytes_t.cpu()]
+
+    # ---- sanity: the timed buffers hold a correct witness (honest product => every diff is zero)
+    ok = bool((bufs.diff == 0).all().item()) and bool((host_out["diff"] == 0).all().item())
+    if not ok:
+        raise SystemExit("bench: Freivalds diff != 0 -- refusing to report a number for wrong results")
+
+    units = plan.mul_adds()
+    value = units / (ms_step * 1e-3)
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        # roofline of the dominant kernel (fr_matmul): integer-pipe bound.  Algorithmic work = 128
+        # IMAD-pipe slots per Fr mul-add; peak = IMAD issue rate measured live.
+        imad_peak = h.microbench_imad(0, 3000)
+        wide_peak = h.microbench_imad(2, 3000)
+        rows = r1 - r0
+        mm_imads = rows * k * m * 128.0
+        achieved = mm_imads / (ms_mm * 1e-3)
+        rs_bytes = rows * m * 32.0 * (1 + W)
+        fr_bytes = 2.0 * 32.0 * (rows * m + (b1 - b0) * m + rows * k)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32x8 (BN254 Fr, 256-bit modular)", "data": "synthetic",
+            "config": {"workload": f"honest_prover_mat_mul + rescale_matrix + verify_mul witness, square N={n}, "
+                                   f"PRECISION_BITS={P_BITS}, LOOKUP_BITS={LOOKUP_BITS} (BASELINE configs[3] + "
+                                   f"Freivalds)", "n": n, "sharding": f"rows of A/C over {world} rank(s), B replicated, "
+                                   "(B v) all-gathered", "l2": "256 MiB flush write between timed steps",
+                       "inputs": "input-creator.py distribution, seeded, quantized on the GPU"},
+            "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds": ms_fr},
+            "roofline": {"bound": "imad", "kernel": "fr_matmul_kernel", "achieved": achieved / 1e12,
+                         "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": achieved / imad_peak,
+                         "peak_source": "measured live: mad.lo.u32 micro-benchmark, all SMs (h2svd_microbench_imad kind 0)",
+                         "imad_wide_chain_peak": wide_peak / 1e12,
+                         "frac_of_wide_chain_peak": (rows * k * m * 64.0 / (ms_mm * 1e-3)) / wide_peak,
+                         "algorithmic": "128 IMAD slots per Fr mul-add = 64 IMAD.WIDE.U32 (half rate)",
+                         "traffic": None},
+            "roofline_hbm": {
+                "rescale": {"bound": "hbm", "achieved": rs_bytes / (ms_rs * 1e-3) / 1e9, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": rs_bytes / (ms_rs * 1e-3) / 1e9 / hbm_peak},
+                "freivalds": {"bound": "hbm", "achieved": fr_bytes / (ms_fr * 1e-3) / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": fr_bytes / (ms_fr * 1e-3) / 1e9 / hbm_peak},
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "wall_ms_per_step": e2e_wall * 1e3, "h2d_bytes_per_step": h2d_all,
+                    "d2h_bytes_per_step": d2h_all,
+                    "api": "workload.run_step on pinned host buffers (H2D inputs, all witnesses D2H) per rank"},
+            "gpu_launches": int(gpu_launches) * world, "clocks": clocks, "wall_s_timed_region": t_wall,
+            "verified": "Freivalds diff == 0 on the timed buffers",
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_sample(n, 1, mm_rows=64, rs_elems=65536)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": cb["sample"] + f" ({cb['t_sample_s']:.1f} s of CPU work, 1 thread: "
+                                                             "the reference is single-threaded)"}
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3   # timing rules: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

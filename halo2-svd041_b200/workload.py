@@ -1,0 +1,138 @@
+"""The hot path as one "step": honest_prover_mat_mul -> rescale_matrix -> verify_mul witnesses for
+one (A, B) pair, row-sharded over `world` GPUs (one process per GPU).
+
+Sharding: rank g owns rows [r0, r1) of A and of C (mat-mul, rescale, C.v and A.(Bv)
+witnesses are row-local); B is replicated; the k rows of B are split for the B.v running sums and the
+k row totals (B v) are exchanged with ONE all-gather (NCCL over NVLink) -- the only collective on the
+path.  Field addition is exact, so the sharded witnesses are byte-identical to the single-GPU ones.
+
+`backend` is any object with the `*_dev` methods of gpu.Handle (the tests inject a CPU stand-in to
+cover the sharding logic under gloo); `comm` is a torch.distributed process group or None.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+
+def split_range(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous near-equal split: the first (total % world) ranks get one extra row."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    n: int
+    k: int
+    m: int
+    world: int = 1
+    rank: int = 0
+
+    @property
+    def rows(self) -> Tuple[int, int]:      # rows of A / C owned by this rank
+        return split_range(self.n, self.world, self.rank)
+
+    @property
+    def brows(self) -> Tuple[int, int]:     # rows of B whose B.v running sums this rank produces
+        return split_range(self.k, self.world, self.rank)
+
+    @property
+    def kmax(self) -> int:                  # padded per-rank row count of the all-gather
+        return -(-self.k // self.world)
+
+    def mul_adds(self) -> int:
+        """Fr multiply-adds of the whole job (all ranks): mat-mul + Freivalds."""
+        return self.n * self.k * self.m + (self.m - 1) + self.n * self.m + self.k * self.m + self.n * self.k
+
+
+@dataclass
+class StepBuffers:
+    """Device tensors of one rank (int64[..., 4] == bn256::Fr limbs).  Inputs: a_slab, b, gamma."""
+    a_slab: object
+    b: object
+    gamma: object
+    c_slab: object
+    q_slab: object
+    wit_slab: object
+    powers: object
+    prefix_cv: object
+    prefix_bv: object      # local rows of B only
+    prefix_abv: object
+    bv_local: object       # [kmax, 4] zero-padded row totals of the local B rows
+    bv_all: object         # [world * kmax, 4] all-gather target
+    bv: object             # [k, 4] compacted (B v)
+    csv: object
+    abv: object
+    diff: object
+    is_zero: object
+    inv: object
+    bv_index: Optional[object] = None   # compaction gather indices when k % world != 0
+
+
+def alloc_buffers(torch, plan: ShardPlan, W: int, device) -> StepBuffers:
+    r0, r1 = plan.rows
+    b0, b1 = plan.brows
+    rows, brows = r1 - r0, b1 - b0
+
+    def fr(*shape):
+        return torch.zeros(shape + (4,), dtype=torch.int64, device=device)
+
+    idx = None
+    if plan.world > 1 and plan.k % plan.world != 0:
+        pos = []
+        for g in range(plan.world):
+            lo, hi = split_range(plan.k, plan.world, g)
+            pos += [g * plan.kmax + i for i in range(hi - lo)]
+        idx = torch.tensor(pos, dtype=torch.int64, device=device)
+    return StepBuffers(
+        a_slab=fr(rows, plan.k), b=fr(plan.k, plan.m), gamma=fr(1), c_slab=fr(rows, plan.m),
+        q_slab=fr(rows, plan.m), wit_slab=fr(rows * plan.m, W), powers=fr(plan.m),
+        prefix_cv=fr(rows, plan.m), prefix_bv=fr(max(brows, 1), plan.m), prefix_abv=fr(rows, plan.k),
+        bv_local=fr(plan.kmax), bv_all=fr(plan.world * plan.kmax), bv=fr(plan.k), csv=fr(rows), abv=fr(rows),
+        diff=fr(rows), is_zero=fr(rows), inv=fr(rows), bv_index=idx)
+
+
+def step_matmul(backend, plan: ShardPlan, bufs: StepBuffers) -> None:
+    """honest_prover_mat_mul (reference src/matrix/mod.rs:546): this rank's rows of C = A.B"""
+    backend.fr_matmul_dev(bufs.a_slab, bufs.b, bufs.c_slab)
+
+
+def step_rescale(backend, plan: ShardPlan, bufs: StepBuffers, precision_bits: int, lookup_bits: int) -> None:
+    """ZkMatrix::rescale_matrix (:354) witnesses for this rank's rows of C"""
+    r0, r1 = plan.rows
+    backend.rescale_witness_dev(bufs.c_slab, (r1 - r0) * plan.m, precision_bits, lookup_bits, bufs.q_slab,
+                                bufs.wit_slab)
+
+
+def step_freivalds(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None) -> None:
+    """ZkMatrix::verify_mul (:299) witnesses, row-sharded, one all-gather of (B v)."""
+    r0, r1 = plan.rows
+    b0, b1 = plan.brows
+    rows, brows = r1 - r0, b1 - b0
+    backend.gamma_powers_dev(bufs.gamma, plan.m, bufs.powers)                        # :316-326
+    backend.mat_vec_prefix_dev(bufs.c_slab, bufs.powers, bufs.prefix_cv)             # :335 (local rows)
+    if brows > 0:
+        backend.mat_vec_prefix_dev(bufs.b[b0:b1], bufs.powers, bufs.prefix_bv[:brows])   # :336 (local B rows)
+        backend.gather_dev(bufs.prefix_bv, brows, plan.m, plan.m - 1, bufs.bv_local)
+    if plan.world > 1:
+        dist.all_gather_into_tensor(bufs.bv_all, bufs.bv_local, group=comm)          # the one exchange step
+        if bufs.bv_index is not None:
+            bufs.bv.copy_(bufs.bv_all.index_select(0, bufs.bv_index))
+            bv = bufs.bv
+        else:
+            bv = bufs.bv_all
+    else:
+        bv = bufs.bv_local
+    backend.mat_vec_prefix_dev(bufs.a_slab, bv, bufs.prefix_abv)                      # :337 (local rows)
+    backend.gather_dev(bufs.prefix_cv, rows, plan.m, plan.m - 1, bufs.csv)
+    backend.gather_dev(bufs.prefix_abv, rows, plan.k, plan.k - 1, bufs.abv)
+    backend.is_equal_witness_dev(bufs.csv, bufs.abv, bufs.diff, bufs.is_zero, bufs.inv)   # :339-341
+
+
+def run_step(backend, plan: ShardPlan, bufs: StepBuffers, precision_bits: int, lookup_bits: int, dist=None,
+             comm=None) -> None:
+    step_matmul(backend, plan, bufs)
+    step_rescale(backend, plan, bufs, precision_bits, lookup_bits)
+    step_freivalds(backend, plan, bufs, dist, comm)

@@ -164,7 +164,7 @@ def test_rescale_of_matmul_output_properties(handle):
         assert a_shift == (csi[e] + (1 << prm.S)) % po.R_MOD
         assert div * (1 << P) + rem == a_shift and rem < (1 << P)
         assert qi[e] == (div - (1 << (prm.S - P))) % po.R_MOD == w[-1]
-        limbs = [w[3], w[4]] + [w[5 + 2 * i] for i in range(1, prm.n_d - 1)]
+        limbs = [w[3], w[4]] + [w[4 + 2 * i] for i in range(1, prm.n_d - 1)]  # l0, l1, s1, l2, s2, ...
         assert all(l < (1 << lb) for l in limbs)
         assert sum(l << (lb * i) for i, l in enumerate(limbs)) == div
         # dequantized product is close to the float product

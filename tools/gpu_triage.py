@@ -37,7 +37,9 @@ def timeit(fn, stream, reps=5, warm=2):
 def main():
     out = {}
     torch.cuda.set_device(0)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h = pkg.Handle(0, stream.cuda_stream)
     out["sm_count"] = h.sm_count
     names = {0: "imad_lo", 1: "imad_wide", 2: "wide_chain", 3: "mulacc_8x8"}
