@@ -40,6 +40,8 @@ SIGNATURES = {
     "h2svd_freivalds_witness_dev": (_I, [_P, _P, _P, _P, _P, _Z, _Z, _Z, _P, _P, _P, _P, _P, _P, _P]),
     "h2svd_gamma_powers_dev": (_I, [_P, _P, _Z, _P]),
     "h2svd_mat_vec_prefix_dev": (_I, [_P, _P, _P, _Z, _Z, _P]),
+    "h2svd_mat_vec_prefix_totals_dev": (_I, [_P, _P, _P, _Z, _Z, _P, _P]),
+    "h2svd_mat_vec_prefix_pair_dev": (_I, [_P, _P, _Z, _P, _P, _P, _Z, _P, _P, _P, _Z]),
     "h2svd_gather_dev": (_I, [_P, _P, _Z, _Z, _Z, _P]),
     "h2svd_is_equal_witness_dev": (_I, [_P, _P, _P, _Z, _P, _P, _P]),
     "h2svd_rescale_witness_count": (_I, [_I, _I, _I, _I]),
@@ -60,6 +62,7 @@ SIGNATURES = {
 DEBUG_SIGNATURES = {
     "h2svd_debug_fr_matmul_naive_dev": (_I, [_P, _P, _P, _P, _Z, _Z, _Z]),
     "h2svd_debug_set_matmul_variant": (_I, [_I]),
+    "h2svd_debug_set_rescale_generic": (_I, [_I]),
 }
 
 _LIB = None

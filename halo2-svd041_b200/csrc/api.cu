@@ -92,14 +92,10 @@ static int freivalds_dev(h2svd_ctx* ctx, const Fr* a, const Fr* b, const Fr* cs,
     Fr* bv = scratch;
     Fr* csv = scratch + k;
     Fr* abv = scratch + k + n;
-    H2SVD_TRY(launch_gamma_powers(ctx, gamma, m, powers));              // reference :316-326
-    H2SVD_TRY(launch_mat_vec_prefix(ctx, cs, powers, n, m, 0, pcv));    // :335
-    H2SVD_TRY(launch_mat_vec_prefix(ctx, b, powers, k, m, 0, pbv));     // :336
-    H2SVD_TRY(launch_gather(ctx, pbv, k, m, m - 1, bv));
-    H2SVD_TRY(launch_mat_vec_prefix(ctx, a, bv, n, k, 0, pabv));        // :337
-    H2SVD_TRY(launch_gather(ctx, pcv, n, m, m - 1, csv));
-    H2SVD_TRY(launch_gather(ctx, pabv, n, k, k - 1, abv));
-    H2SVD_TRY(launch_is_equal(ctx, csv, abv, n, diff, is_zero, inv));   // :339-341
+    H2SVD_TRY(launch_gamma_powers(ctx, gamma, m, powers));                                  // reference :316-326
+    H2SVD_TRY(launch_mat_vec_prefix2(ctx, cs, n, pcv, csv, b, k, pbv, bv, powers, m));      // :335, :336 (one launch)
+    H2SVD_TRY(launch_mat_vec_prefix(ctx, a, bv, n, k, 0, pabv, abv));                       // :337
+    H2SVD_TRY(launch_is_equal(ctx, csv, abv, n, diff, is_zero, inv));                       // :339-341
     return H2SVD_OK;
 }
 
@@ -240,7 +236,25 @@ int h2svd_mat_vec_prefix_dev(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* 
                              h2svd_fr* out_prefix) {
     REQUIRE(ctx && a && v && out_prefix, "mat_vec_prefix: null argument");
     H2SVD_CUDA(cudaSetDevice(ctx->device));
-    return launch_mat_vec_prefix(ctx, as_fr(a), as_fr(v), rows, len, 0, as_fr(out_prefix));
+    return launch_mat_vec_prefix(ctx, as_fr(a), as_fr(v), rows, len, 0, as_fr(out_prefix), nullptr);
+}
+int h2svd_mat_vec_prefix_totals_dev(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* v, size_t rows, size_t len,
+                                    h2svd_fr* out_prefix, h2svd_fr* out_totals) {
+    REQUIRE(ctx && a && v && out_prefix, "mat_vec_prefix_totals: null argument");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_mat_vec_prefix(ctx, as_fr(a), as_fr(v), rows, len, 0, as_fr(out_prefix),
+                                 out_totals ? as_fr(out_totals) : nullptr);
+}
+int h2svd_mat_vec_prefix_pair_dev(h2svd_ctx* ctx, const h2svd_fr* a0, size_t rows0, h2svd_fr* out_prefix0,
+                                  h2svd_fr* out_totals0, const h2svd_fr* a1, size_t rows1, h2svd_fr* out_prefix1,
+                                  h2svd_fr* out_totals1, const h2svd_fr* v, size_t len) {
+    REQUIRE(ctx && v, "mat_vec_prefix_pair: null argument");
+    REQUIRE(rows0 == 0 || (a0 && out_prefix0), "mat_vec_prefix_pair: null argument (first matrix)");
+    REQUIRE(rows1 == 0 || (a1 && out_prefix1), "mat_vec_prefix_pair: null argument (second matrix)");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_mat_vec_prefix2(ctx, as_fr(a0), rows0, as_fr(out_prefix0), out_totals0 ? as_fr(out_totals0) : nullptr,
+                                  as_fr(a1), rows1, as_fr(out_prefix1), out_totals1 ? as_fr(out_totals1) : nullptr,
+                                  as_fr(v), len);
 }
 int h2svd_gather_dev(h2svd_ctx* ctx, const h2svd_fr* src, size_t count, size_t stride, size_t offset,
                      h2svd_fr* out) {
@@ -377,7 +391,7 @@ int h2svd_zkvec_inner_prefix_dev(h2svd_ctx* ctx, const h2svd_fr* x, const h2svd_
     REQUIRE(ctx && x && self && out_prefix, "zkvec_inner_prefix: null argument");
     H2SVD_CUDA(cudaSetDevice(ctx->device));
     // gate.inner_product(u = x, v = self): reference src/matrix/mod.rs:100
-    return launch_mat_vec_prefix(ctx, as_fr(x), as_fr(self), batch, len, len, as_fr(out_prefix));
+    return launch_mat_vec_prefix(ctx, as_fr(x), as_fr(self), batch, len, len, as_fr(out_prefix), nullptr);
 }
 int h2svd_zkvec_inner_prefix(h2svd_ctx* ctx, const h2svd_fr* x, const h2svd_fr* self, size_t batch, size_t len,
                              h2svd_fr* out_prefix) {
@@ -394,7 +408,7 @@ int h2svd_zkvec_inner_prefix(h2svd_ctx* ctx, const h2svd_fr* x, const h2svd_fr* 
     H2SVD_TRY(h2d(ctx, ds, self, cnt * F));
     H2SVD_TRY(launch_check_canonical(ctx, dx, cnt, ctx->d_flag));
     H2SVD_TRY(launch_check_canonical(ctx, ds, cnt, ctx->d_flag));
-    H2SVD_TRY(launch_mat_vec_prefix(ctx, dx, ds, batch, len, len, dout));
+    H2SVD_TRY(launch_mat_vec_prefix(ctx, dx, ds, batch, len, len, dout, nullptr));
     H2SVD_TRY(d2h(ctx, out_prefix, dout, cnt * F));
     return check_flag(ctx, "zkvec_inner_prefix");
 }

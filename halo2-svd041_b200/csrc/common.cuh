@@ -89,8 +89,11 @@ int launch_fr_matmul_naive(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size
                            size_t m);
 int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t cols);
 int launch_gamma_powers(h2svd_ctx* ctx, const Fr* gamma, size_t d, Fr* out);
+// totals (optional): last running sum of every row
 int launch_mat_vec_prefix(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t len,
-                          size_t v_row_stride, Fr* out);
+                          size_t v_row_stride, Fr* out, Fr* totals);
+int launch_mat_vec_prefix2(h2svd_ctx* ctx, const Fr* a0, size_t rows0, Fr* out0, Fr* totals0, const Fr* a1,
+                           size_t rows1, Fr* out1, Fr* totals1, const Fr* v, size_t len);
 int launch_gather(h2svd_ctx* ctx, const Fr* src, size_t count, size_t stride, size_t offset,
                   Fr* out);
 int launch_is_equal(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, Fr* diff, Fr* is_zero,

@@ -9,6 +9,7 @@
 //    is a warp-shuffle inclusive scan in the field plus the carry from the previous 32-block.
 //  * is_equal cells (:339-341).
 #include "common.cuh"
+#include "fr_fast.cuh"
 
 namespace h2svd {
 
@@ -34,39 +35,120 @@ __global__ void gamma_powers_kernel(const Fr* __restrict__ gamma, Fr* __restrict
     Fr acc = fr::one();
     unsigned e = i;
     while (e) {
-        if (e & 1u) acc = fr::mont_mul(acc, base);
+        if (e & 1u) acc = fr::mont_mul_fast(acc, base);
         e >>= 1;
-        if (e) base = fr::mont_mul(base, base);
+        if (e) base = fr::mont_mul_fast(base, base);
     }
     st_fr_cs(out + i, acc);
 }
 
-// out[row*len + j] = sum_{t<=j} a[row*len + t] * v[row*v_row_stride + t]
-__global__ void __launch_bounds__(256)
-mat_vec_prefix_kernel(const Fr* __restrict__ a, const Fr* __restrict__ v, Fr* __restrict__ out, size_t rows,
-                      size_t len, size_t v_row_stride) {
-    const int lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t row = warp; row < rows; row += nwarps) {
-        const Fr* ar = a + row * len;
-        const Fr* vr = v + row * v_row_stride;
-        Fr* orow = out + row * len;
-        Fr carry = fr::zero();
-        for (size_t base = 0; base < len; base += 32) {
-            const size_t j = base + lane;
-            Fr p = fr::zero();
-            if (j < len) p = fr::mont_mul(ldg_fr(ar + j), ldg_fr(vr + j));
-            // inclusive scan over the 32 lanes (Hillis-Steele, field adds)
+// inclusive scan of one field element per lane over the first `width` lanes (width = 32 or 8)
+template <int WIDTH>
+__device__ __forceinline__ Fr warp_scan_fr(Fr p, int lane) {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                Fr t = shfl_up_fr(p, d);
-                if (lane >= d) p = fr::add(p, t);
+    for (int d = 1; d < WIDTH; d <<= 1) {
+        const Fr t = shfl_up_fr(p, d);
+        const Fr s = fr::add_fast(p, t);
+        if (lane >= d) p = s;
+    }
+    return p;
+}
+
+constexpr int MV_WARPS = 8;   // warps per CTA
+constexpr int MV_C = 4;       // 32-element chunks per warp per tile
+constexpr int MV_MAX_JOBS = 2;
+
+struct MvJob {
+    const Fr* a;     // rows x len
+    Fr* out;         // rows x len running sums
+    Fr* totals;      // rows (last running sum of every row) or nullptr
+    size_t rows;
+};
+struct MvJobs {
+    MvJob job[MV_MAX_JOBS];
+    int njobs;
+};
+
+// out[row*len + j] = sum_{t<=j} a[row*len + t] * v[row*v_row_stride + t]   for every row of every job
+// (all jobs share v, len and v_row_stride).  WPR warps cooperate on one row: inside a tile of
+// WPR*128 elements warp w owns the contiguous elements [w*128, (w+1)*128) as four coalesced 32-lane
+// chunks; it keeps its four un-offset running sums in registers, the warps exchange their segment
+// totals through shared memory, and every running sum is written exactly once.
+template <int WPR>
+__global__ void __launch_bounds__(MV_WARPS * 32, 2)
+mat_vec_prefix_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len, size_t v_row_stride) {
+    constexpr int RPC = MV_WARPS / WPR;       // rows per CTA pass
+    constexpr int TILE = WPR * 32 * MV_C;
+    __shared__ Fr wtot[MV_WARPS];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int rloc = warp / WPR, wr = warp % WPR;
+    size_t total_rows = 0;
+#pragma unroll
+    for (int q = 0; q < MV_MAX_JOBS; q++) total_rows += q < jobs.njobs ? jobs.job[q].rows : 0;
+
+    for (size_t row_base = (size_t)blockIdx.x * RPC; row_base < total_rows; row_base += (size_t)gridDim.x * RPC) {
+        size_t row = row_base + rloc;
+        const bool active = row < total_rows;
+        const Fr* a = nullptr;
+        Fr* out = nullptr;
+        Fr* totals = nullptr;
+        if (active) {
+            int q = 0;
+            if (jobs.njobs > 1 && row >= jobs.job[0].rows) {
+                row -= jobs.job[0].rows;
+                q = 1;
             }
-            p = fr::add(p, carry);
-            if (j < len) st_fr_cs(orow + j, p);
-            carry = shfl_fr(p, 31);
+            a = jobs.job[q].a + row * len;
+            out = jobs.job[q].out + row * len;
+            totals = jobs.job[q].totals ? jobs.job[q].totals + row : nullptr;
         }
+        const Fr* vr = v + (active ? row * v_row_stride : 0);
+        Fr carry = fr::zero();  // sum of all complete tiles of this row (identical in every warp of the row)
+        for (size_t t0 = 0; t0 < len; t0 += TILE) {
+            const size_t seg0 = t0 + (size_t)wr * 32 * MV_C;
+            Fr res[MV_C];
+            Fr run = fr::zero();
+#pragma unroll
+            for (int c = 0; c < MV_C; c++) {
+                const size_t j = seg0 + c * 32 + lane;
+                Fr p = fr::zero();
+                if (seg0 + c * 32 < len) {  // warp-uniform
+                    if (active && j < len) p = fr::mont_mul_fast(ldg_fr(a + j), ldg_fr(vr + j));
+                    p = warp_scan_fr<32>(p, lane);
+                    p = fr::add_fast(p, run);
+                    run = shfl_fr(p, 31);
+                }
+                res[c] = p;
+            }
+            if (WPR > 1) {
+                if (lane == 0) st_fr(&wtot[warp], run);
+                __syncthreads();
+                // lanes 0..WPR-1 scan the segment totals of this row
+                Fr t = fr::zero();
+                if (lane < WPR) t = ld_fr(&wtot[rloc * WPR + lane]);
+                t = warp_scan_fr<WPR>(t, lane);
+                const Fr incl_prev = shfl_fr(t, wr > 0 ? wr - 1 : 0);
+                const Fr tile_total = shfl_fr(t, WPR - 1);
+                Fr off = carry;
+                if (wr > 0) off = fr::add_fast(off, incl_prev);
+                carry = fr::add_fast(carry, tile_total);
+                __syncthreads();  // wtot is rewritten by the next tile
+#pragma unroll
+                for (int c = 0; c < MV_C; c++) {
+                    const size_t j = seg0 + c * 32 + lane;
+                    if (active && j < len) st_fr_cs(out + j, fr::add_fast(res[c], off));
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < MV_C; c++) {
+                    const size_t j = seg0 + c * 32 + lane;
+                    if (active && j < len) st_fr_cs(out + j, fr::add_fast(res[c], carry));
+                }
+                carry = fr::add_fast(carry, run);
+            }
+        }
+        if (totals && wr == 0 && lane == 0) st_fr(totals, carry);
     }
 }
 
@@ -88,8 +170,8 @@ __device__ Fr fr_inverse(const Fr& a) {
 #pragma unroll
         for (int i = 0; i < 8; i++) word = (i == w) ? e[i] : word;
         for (int bit = 31; bit >= 0; bit--) {
-            acc = fr::mont_mul(acc, acc);
-            if ((word >> bit) & 1u) acc = fr::mont_mul(acc, a);
+            acc = fr::mont_mul_fast(acc, acc);
+            if ((word >> bit) & 1u) acc = fr::mont_mul_fast(acc, a);
         }
     }
     return acc;
@@ -123,16 +205,48 @@ int launch_gamma_powers(h2svd_ctx* ctx, const Fr* gamma, size_t d, Fr* out) {
     return H2SVD_OK;
 }
 
-int launch_mat_vec_prefix(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t len, size_t v_row_stride,
-                          Fr* out) {
-    if (rows == 0 || len == 0) return H2SVD_OK;
-    const size_t warps_per_block = 8;
-    size_t blocks = (rows + warps_per_block - 1) / warps_per_block;
-    const size_t max_blocks = (size_t)ctx->sm_count * 8;  // grid-stride beyond that
-    if (blocks > max_blocks) blocks = max_blocks;
-    mat_vec_prefix_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, v, out, rows, len, v_row_stride);
+template <int WPR>
+static int launch_mv(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, const Fr* v, size_t len, size_t vs) {
+    constexpr int RPC = MV_WARPS / WPR;
+    size_t blocks = (total_rows + RPC - 1) / RPC;
+    const size_t cap = (size_t)ctx->sm_count * 2 * 4;  // 2 resident CTAs per SM, grid-stride beyond 4 waves
+    if (blocks > cap) blocks = cap;
+    mat_vec_prefix_kernel<WPR><<<(unsigned)blocks, MV_WARPS * 32, 0, ctx->stream>>>(jobs, v, len, vs);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
+}
+
+static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_t len, size_t vs) {
+    size_t total_rows = 0;
+    for (int q = 0; q < jobs.njobs; q++) total_rows += jobs.job[q].rows;
+    if (total_rows == 0 || len == 0) return H2SVD_OK;
+    // warps per row: enough to cover the row with 128-element segments, and enough to fill the GPU
+    int wpr = 1;
+    while (wpr < MV_WARPS && (size_t)wpr * 128 < len) wpr <<= 1;
+    switch (wpr) {
+        case 1: return launch_mv<1>(ctx, jobs, total_rows, v, len, vs);
+        case 2: return launch_mv<2>(ctx, jobs, total_rows, v, len, vs);
+        case 4: return launch_mv<4>(ctx, jobs, total_rows, v, len, vs);
+        default: return launch_mv<8>(ctx, jobs, total_rows, v, len, vs);
+    }
+}
+
+int launch_mat_vec_prefix(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t len, size_t v_row_stride,
+                          Fr* out, Fr* totals) {
+    MvJobs jobs{};
+    jobs.njobs = 1;
+    jobs.job[0] = MvJob{a, out, totals, rows};
+    return launch_mv_jobs(ctx, jobs, v, len, v_row_stride);
+}
+
+// two matrices against the same vector in one launch (C.v and B.v of verify_mul)
+int launch_mat_vec_prefix2(h2svd_ctx* ctx, const Fr* a0, size_t rows0, Fr* out0, Fr* totals0, const Fr* a1,
+                           size_t rows1, Fr* out1, Fr* totals1, const Fr* v, size_t len) {
+    MvJobs jobs{};
+    jobs.njobs = 2;
+    jobs.job[0] = MvJob{a0, out0, totals0, rows0};
+    jobs.job[1] = MvJob{a1, out1, totals1, rows1};
+    return launch_mv_jobs(ctx, jobs, v, len, 0);
 }
 
 int launch_gather(h2svd_ctx* ctx, const Fr* src, size_t count, size_t stride, size_t offset, Fr* out) {

@@ -13,25 +13,45 @@
 //   check_less_than(x, B, bits): x + 2^bits - B,  x + 2^bits
 //   range_check(x + 2^bits - B, bits): 2n-1 values again.
 //
-// All of it is shifts and masks on the canonical integer (the divisor is a power of two), followed
-// by a conversion of every emitted value to Montgomery form.  One thread per element; each witness is
-// written as one aligned 32-byte sector.
+// The kernel is bound by the HBM write of W 32-byte witnesses per element (1920 B at P=63, lb=19), so
+// the design minimises integer work per witness and makes every store a full-line bulk write:
+//  * Montgomery form is linear, so a limb l at position i enters the running sum as
+//    M(l * 2^(lb*i)) = l * c_i * 2^-32 mod r with c_i = 2^(lb*i) * 2^288 mod r precomputed on the host:
+//    ONE single-limb Montgomery step (16 IMAD.WIDE, fr_fast.cuh) instead of a full 8x8 conversion
+//    (~264 IMAD) per witness; running sums are modular adds; x + 2^bits, x + 2^bits - B and q are modular
+//    adds/subs of M(x) with host-precomputed Montgomery constants.
+//  * one thread per element; each lane stages its witnesses in its own shared-memory row
+//    (double-buffered, 16-byte skew => conflict-free) and ships every CH witnesses with one TMA bulk
+//    store (cp.async.bulk.global.shared::cta): all global writes are contiguous CH*32-byte bursts
+//    issued by the copy engine, no thread ever issues a 32-byte scattered store.
 #include "common.cuh"
+#include "fr_fast.cuh"
 
 namespace h2svd {
 
 namespace {
 
+constexpr int MAX_POS = 32;  // limb positions the staged kernel supports (n_d, n_r <= 32)
+
 struct RescaleParams {
     int P, lb, S, A, n_d, n_r, W;
 };
 
+// Host-precomputed constants of one (P, lb, S, A) configuration, passed by value (constant bank).
+struct RescaleConsts {
+    RescaleParams p;
+    uint32_t lb_mask;
+    Fr i_2S, i_pow_d, i_bound_d, i_pow_r, i_bound_r;   // canonical integers
+    Fr m_2S, m_2SP, m_pow_d, m_bound_d, m_pow_r, m_bound_r;  // Montgomery forms
+    Fr c[MAX_POS];  // c[i] = 2^(lb*i) * 2^288 mod r
+};
+
+// ---------------------------------------------------------------------------------------------------
+// generic fallback (any lb >= 1): full Montgomery conversion per witness, scattered 32-byte stores.
 __device__ __forceinline__ Fr* emit(Fr* w, const Fr& x_int) {
     st_fr_cs(w, fr::to_mont(x_int));
     return w + 1;
 }
-
-// RangeChip::range_check(x, n*lb): limbs are the low n chunks of the canonical value
 __device__ __forceinline__ Fr* emit_range_check(Fr* w, const Fr& x, int n, int lb) {
     if (n == 1) return w;
     for (int i = 0; i < n; i++) {
@@ -40,8 +60,6 @@ __device__ __forceinline__ Fr* emit_range_check(Fr* w, const Fr& x, int n, int l
     }
     return w;
 }
-
-// RangeChip::check_big_less_than_safe(x, bound), n = ceil(bound.bits()/lb)
 __device__ __forceinline__ Fr* emit_cbls(Fr* w, const Fr& x, const Fr& bound, int n, int lb) {
     w = emit_range_check(w, x, n, lb);
     const Fr xp = fr::add(x, fr::pow2(n * lb));  // x + 2^bits      (mod r)
@@ -50,10 +68,9 @@ __device__ __forceinline__ Fr* emit_cbls(Fr* w, const Fr& x, const Fr& bound, in
     w = emit(w, xp);
     return emit_range_check(w, chk, n, lb);
 }
-
 __global__ void __launch_bounds__(128)
-rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
-               RescaleParams p) {
+rescale_generic_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
+                       RescaleParams p) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
     const Fr a = fr::from_mont(ldg_fr(cs + e));            // canonical integer
@@ -74,6 +91,117 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
     st_fr(out_q + e, q);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// staged kernel
+constexpr int RS_THREADS = 128;
+constexpr int RS_CH = 8;                      // witnesses per bulk store (256 B)
+constexpr int RS_ROW_U4 = RS_CH * 2 + 1;      // staging row in 16-byte units: 256 B + 16 B skew
+constexpr size_t RS_SMEM = (size_t)RS_THREADS * 2 * RS_ROW_U4 * sizeof(uint4);
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Per-lane witness stream: values go to this lane's shared-memory row; every RS_CH values (and at the
+// end of the element) the row is shipped to its place in out_wit by one bulk copy.
+struct WitnessStream {
+    uint4* row0;  // two consecutive rows of RS_ROW_U4 16-byte units
+    Fr* gdst;
+    int buf, fill;
+
+    __device__ __forceinline__ uint4* row() const { return row0 + buf * RS_ROW_U4; }
+    __device__ __forceinline__ void put(const Fr& v) {
+        uint4* s = row() + 2 * fill;
+        s[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        s[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        if (++fill == RS_CH) flush();
+    }
+    __device__ __forceinline__ void flush() {
+        if (fill == 0) return;
+        // generic-proxy writes of this thread -> visible to the async proxy, then bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                     "r"(smem_addr(row())), "r"((uint32_t)(fill * sizeof(Fr)))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        gdst += fill;
+        fill = 0;
+        buf ^= 1;
+        // the row we switch to was shipped one flush ago: wait until the engine has read it
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+};
+
+__device__ __forceinline__ Fr shr_small(const Fr& y, int s) {  // 1 <= s <= 32
+    Fr o;
+#pragma unroll
+    for (int j = 0; j < 7; j++) o.l[j] = __funnelshift_rc(y.l[j], y.l[j + 1], s);
+    o.l[7] = __funnelshift_rc(y.l[7], 0u, s);
+    return o;
+}
+
+// RangeChip::range_check(x, n*lb): limbs l_i and running sums s_i = x mod 2^(lb*(i+1)), Montgomery form
+__device__ __forceinline__ void stream_range_check(WitnessStream& ws, const RescaleConsts& k, Fr y, int n) {
+    if (n == 1) return;
+    Fr sum;
+    for (int i = 0; i < n; i++) {
+        const uint32_t l = y.l[0] & k.lb_mask;
+        y = shr_small(y, k.p.lb);
+        const Fr ml = fr::mont_mul_small(l, k.c[0]);
+        ws.put(ml);
+        if (i == 0) {
+            sum = ml;
+        } else {
+            sum = fr::add_fast(sum, fr::mont_mul_small(l, k.c[i]));
+            ws.put(sum);
+        }
+    }
+}
+
+// RangeChip::check_big_less_than_safe(x, B)
+__device__ __forceinline__ void stream_cbls(WitnessStream& ws, const RescaleConsts& k, const Fr& x_int,
+                                            const Fr& x_mont, int n, const Fr& i_pow, const Fr& i_bound,
+                                            const Fr& m_pow, const Fr& m_bound) {
+    stream_range_check(ws, k, x_int, n);
+    const Fr chk_int = fr::sub_fast(fr::add_fast(x_int, i_pow), i_bound);  // x + 2^bits - B (mod r)
+    const Fr m_xp = fr::add_fast(x_mont, m_pow);
+    ws.put(fr::sub_fast(m_xp, m_bound));
+    ws.put(m_xp);
+    stream_range_check(ws, k, chk_int, n);
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
+               const __grid_constant__ RescaleConsts k) {
+    extern __shared__ __align__(16) uint4 rs_stage[];
+    WitnessStream ws;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * 2 * RS_ROW_U4;
+    ws.buf = 0;
+    ws.fill = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
+        ws.gdst = out_wit + e * (size_t)k.p.W;
+        const Fr am = ldg_fr(cs + e);
+        const Fr a = fr::from_mont_fast(am);                    // canonical integer
+        const Fr ash = fr::add_fast(a, k.i_2S);                 // gate.add(a, Constant(2^S))
+        const Fr div = fr::shr(ash, k.p.P);                     // div_mod_floor by 2^P
+        const Fr rem = fr::low_bits(ash, k.p.P);
+        const Fr m_div = fr::to_mont_fast(div);
+        const Fr m_rem = fr::to_mont_fast(rem);
+        ws.put(fr::add_fast(am, k.m_2S));
+        ws.put(m_rem);
+        ws.put(m_div);
+        stream_cbls(ws, k, div, m_div, k.p.n_d, k.i_pow_d, k.i_bound_d, k.m_pow_d, k.m_bound_d);
+        stream_cbls(ws, k, rem, m_rem, k.p.n_r, k.i_pow_r, k.i_bound_r, k.m_pow_r, k.m_bound_r);
+        const Fr q = fr::sub_fast(m_div, k.m_2SP);              // gate.sub(div, Constant(2^(S-P)))
+        ws.put(q);
+        ws.flush();
+        st_fr(out_q + e, q);
+    }
+    // shared memory must outlive every bulk read, and the writes must be complete at kernel end
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -89,6 +217,8 @@ int rescale_params(int P, int lb, int S, int A, int* n_d, int* n_r) {
     return 4 + 4 * (nd + nr);
 }
 
+static int g_force_generic = 0;
+
 int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, int S, int A, Fr* out_q,
                    Fr* out_wit) {
     if (S < 0) S = 3 * P;
@@ -101,9 +231,48 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
         return H2SVD_EINVAL;
     }
     if (count == 0) return H2SVD_OK;
-    rescale_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(cs, out_q, out_wit, count, p);
+    if (p.n_d > MAX_POS || p.n_r > MAX_POS || g_force_generic) {
+        rescale_generic_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(cs, out_q, out_wit, count, p);
+        H2SVD_LAUNCH_CHECK(ctx);
+        return H2SVD_OK;
+    }
+    // constants of this configuration (fr.cuh is host-callable)
+    RescaleConsts k;
+    k.p = p;
+    k.lb_mask = lb == 32 ? 0xffffffffu : ((1u << lb) - 1u);
+    k.i_2S = fr::pow2(S);
+    k.i_pow_d = fr::pow2(p.n_d * lb);
+    k.i_bound_d = fr::pow2(A - P);
+    k.i_bound_d.l[0] |= 1u;  // 2^A / 2^P + 1   (A > P)
+    k.i_pow_r = fr::pow2(p.n_r * lb);
+    k.i_bound_r = fr::pow2(P);
+    k.m_2S = fr::to_mont(k.i_2S);
+    k.m_2SP = fr::to_mont(fr::pow2(S - P));
+    k.m_pow_d = fr::to_mont(k.i_pow_d);
+    k.m_bound_d = fr::to_mont(k.i_bound_d);
+    k.m_pow_r = fr::to_mont(k.i_pow_r);
+    k.m_bound_r = fr::to_mont(k.i_bound_r);
+    const Fr m_2_32 = fr::to_mont(fr::pow2(32));
+    const int npos = p.n_d > p.n_r ? p.n_d : p.n_r;
+    for (int i = 0; i < MAX_POS; i++)
+        k.c[i] = i < npos ? fr::mont_mul(fr::to_mont(fr::pow2(lb * i)), m_2_32) : fr::zero();
+
+    static bool configured = false;
+    if (!configured) {
+        H2SVD_CUDA(cudaFuncSetAttribute(rescale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+        configured = true;
+    }
+    size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
+    const size_t cap = (size_t)ctx->sm_count * 3;  // 3 CTAs (69.6 KB of staging each) per SM, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    rescale_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }
 
 }  // namespace h2svd
+
+extern "C" int h2svd_debug_set_rescale_generic(int v) {
+    h2svd::g_force_generic = v;
+    return 0;
+}

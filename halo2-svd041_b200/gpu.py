@@ -198,10 +198,21 @@ class Handle:
     def gamma_powers_dev(self, gamma, d: int, out) -> None:
         _ffi.check(self._lib.h2svd_gamma_powers_dev(self._h, self._tp(gamma), d, self._tp(out)))
 
-    def mat_vec_prefix_dev(self, a, v, out) -> None:
+    def mat_vec_prefix_dev(self, a, v, out, totals=None) -> None:
         rows, ln = a.shape[0], a.shape[1]
-        _ffi.check(self._lib.h2svd_mat_vec_prefix_dev(self._h, self._tp(a), self._tp(v), rows, ln,
-                                                     self._tp(out)))
+        _ffi.check(self._lib.h2svd_mat_vec_prefix_totals_dev(
+            self._h, self._tp(a), self._tp(v), rows, ln, self._tp(out),
+            self._tp(totals) if totals is not None else ct.c_void_p(0)))
+
+    def mat_vec_prefix_pair_dev(self, a0, out0, totals0, a1, out1, totals1, v) -> None:
+        """(a0 . v) and (a1 . v) running sums in one launch; a1 may have zero rows."""
+        rows0, ln = a0.shape[0], a0.shape[1]
+        rows1 = a1.shape[0]
+        null = ct.c_void_p(0)
+        _ffi.check(self._lib.h2svd_mat_vec_prefix_pair_dev(
+            self._h, self._tp(a0), rows0, self._tp(out0), self._tp(totals0) if totals0 is not None else null,
+            self._tp(a1) if rows1 else null, rows1, self._tp(out1) if rows1 else null,
+            self._tp(totals1) if (rows1 and totals1 is not None) else null, self._tp(v), ln))
 
     def gather_dev(self, src, count: int, stride: int, offset: int, out) -> None:
         _ffi.check(self._lib.h2svd_gather_dev(self._h, self._tp(src), count, stride, offset,
@@ -236,6 +247,11 @@ class Handle:
 
     def check_canonical_dev(self, x) -> None:
         _ffi.check(self._lib.h2svd_check_canonical_dev(self._h, self._tp(x), x.numel() // 4))
+
+
+def set_rescale_generic(v: bool) -> None:
+    """Triage hook: force the generic (unstaged) rescale kernel."""
+    _ffi.load().h2svd_debug_set_rescale_generic(int(v))
 
 
 def set_matmul_variant(v: int) -> None:

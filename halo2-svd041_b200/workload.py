@@ -112,10 +112,9 @@ def step_freivalds(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=
     b0, b1 = plan.brows
     rows, brows = r1 - r0, b1 - b0
     backend.gamma_powers_dev(bufs.gamma, plan.m, bufs.powers)                        # :316-326
-    backend.mat_vec_prefix_dev(bufs.c_slab, bufs.powers, bufs.prefix_cv)             # :335 (local rows)
-    if brows > 0:
-        backend.mat_vec_prefix_dev(bufs.b[b0:b1], bufs.powers, bufs.prefix_bv[:brows])   # :336 (local B rows)
-        backend.gather_dev(bufs.prefix_bv, brows, plan.m, plan.m - 1, bufs.bv_local)
+    # :335 (local rows of C) and :336 (local rows of B) in one launch; row totals come out with them
+    backend.mat_vec_prefix_pair_dev(bufs.c_slab, bufs.prefix_cv, bufs.csv,
+                                    bufs.b[b0:b1], bufs.prefix_bv[:brows], bufs.bv_local[:brows], bufs.powers)
     if plan.world > 1:
         dist.all_gather_into_tensor(bufs.bv_all, bufs.bv_local, group=comm)          # the one exchange step
         if bufs.bv_index is not None:
@@ -125,9 +124,7 @@ def step_freivalds(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=
             bv = bufs.bv_all
     else:
         bv = bufs.bv_local
-    backend.mat_vec_prefix_dev(bufs.a_slab, bv, bufs.prefix_abv)                      # :337 (local rows)
-    backend.gather_dev(bufs.prefix_cv, rows, plan.m, plan.m - 1, bufs.csv)
-    backend.gather_dev(bufs.prefix_abv, rows, plan.k, plan.k - 1, bufs.abv)
+    backend.mat_vec_prefix_dev(bufs.a_slab, bv, bufs.prefix_abv, bufs.abv)            # :337 (local rows)
     backend.is_equal_witness_dev(bufs.csv, bufs.abv, bufs.diff, bufs.is_zero, bufs.inv)   # :339-341
 
 

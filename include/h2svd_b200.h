@@ -95,6 +95,16 @@ int h2svd_freivalds_witness_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_f
 int h2svd_gamma_powers_dev(h2svd_ctx *ctx, const h2svd_fr *gamma, size_t d, h2svd_fr *out);
 int h2svd_mat_vec_prefix_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, size_t rows,
                              size_t len, h2svd_fr *out_prefix);
+/* Same, additionally writing out_totals[i] = out_prefix[i*len + len-1] (the value field_mat_vec_mul
+ * returns for row i, :597); out_totals may be NULL. */
+int h2svd_mat_vec_prefix_totals_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, size_t rows,
+                                    size_t len, h2svd_fr *out_prefix, h2svd_fr *out_totals);
+/* Two matrices against the same vector in ONE launch (c_s . v and b . v of verify_mul, :335-336);
+ * rows1 may be 0. */
+int h2svd_mat_vec_prefix_pair_dev(h2svd_ctx *ctx, const h2svd_fr *a0, size_t rows0,
+                                  h2svd_fr *out_prefix0, h2svd_fr *out_totals0, const h2svd_fr *a1,
+                                  size_t rows1, h2svd_fr *out_prefix1, h2svd_fr *out_totals1,
+                                  const h2svd_fr *v, size_t len);
 /* out[i] = src[i*stride + offset]  (gathers the last running sum of every row) */
 int h2svd_gather_dev(h2svd_ctx *ctx, const h2svd_fr *src, size_t count, size_t stride,
                      size_t offset, h2svd_fr *out);

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "../../halo2-svd041_b200/csrc/fr_acc.cuh"
+#include "../../halo2-svd041_b200/csrc/fr_fast.cuh"
 
 using fr::Fr;
 
@@ -19,6 +20,13 @@ void hs_low_bits(const Fr* a, int bits, Fr* o, size_t n) { for (size_t i = 0; i 
 void hs_pow2(int s, Fr* o) { *o = fr::pow2(s); }
 int hs_is_canonical(const Fr* a) { return fr::is_canonical(*a) ? 1 : 0; }
 void hs_one(Fr* o) { *o = fr::one(); }
+// carry-chain primitives (host restatement of the PTX blocks in fr_fast.cuh)
+void hs_mont_mul_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::mont_mul_fast(a[i], b[i]); }
+void hs_mont_mul_small(const uint32_t* l, const Fr* c, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::mont_mul_small(l[i], c[i]); }
+void hs_add_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::add_fast(a[i], b[i]); }
+void hs_sub_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::sub_fast(a[i], b[i]); }
+void hs_to_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::to_mont_fast(a[i]); }
+void hs_from_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::from_mont_fast(a[i]); }
 // lazy dot product exactly as the mat-mul inner loop accumulates it (host fallback of chain4)
 void hs_lazy_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {
     fr::WideAcc w;

@@ -60,6 +60,38 @@ def test_field_ops_match_bigint(shim):
     assert shim.hs_is_canonical(P(raw_limbs([(1 << 256) - 1]))) == 0
 
 
+def test_carry_chain_primitives_match_bigint(shim):
+    """fr_fast.cuh: the two-limbs-per-step CIOS in even/odd 64-bit columns, the single-limb Montgomery
+    step and the modular add/sub, on edge values and 20k random pairs."""
+    rng = random.Random(11)
+    edge = [0, 1, 2, R - 1, R - 2, 1 << 253, (1 << 252) - 1, po.MONT_R, po.MONT_R2, (R - 1) // 2,
+            (1 << 32) - 1, (1 << 64) - 1, ((1 << 254) - 1) % R, R - (1 << 32), 0x30644e72 << 224]
+    xs = [x for x in edge for _ in edge] + [rng.randrange(R) for _ in range(20000)]
+    ys = [y for _ in edge for y in edge] + [rng.randrange(R) for _ in range(20000)]
+    n = len(xs)
+    a, b = raw_limbs(xs), raw_limbs(ys)
+    o = np.zeros_like(a)
+    shim.hs_mont_mul_fast(P(a), P(b), P(o), n)
+    assert unraw(o) == [x * y * po.MONT_RINV % R for x, y in zip(xs, ys)]
+    shim.hs_add_fast(P(a), P(b), P(o), n)
+    assert unraw(o) == [(x + y) % R for x, y in zip(xs, ys)]
+    shim.hs_sub_fast(P(a), P(b), P(o), n)
+    assert unraw(o) == [(x - y) % R for x, y in zip(xs, ys)]
+    shim.hs_to_mont_fast(P(a), P(o), n)
+    assert unraw(o) == [po.to_mont(x) for x in xs]
+    shim.hs_from_mont_fast(P(a), P(o), n)
+    assert unraw(o) == [po.from_mont(x) for x in xs]
+    ls = [0, 1, 2, (1 << 19) - 1, (1 << 31), (1 << 32) - 1] + [rng.randrange(1 << 32) for _ in range(5000)]
+    cs = [rng.randrange(R) for _ in ls]
+    cs[:6] = [R - 1, R - 1, 0, R - 1, R - 1, R - 1]
+    larr = np.array(ls, dtype=np.uint32)
+    c = raw_limbs(cs)
+    o = np.zeros_like(c)
+    shim.hs_mont_mul_small(P(larr), P(c), P(o), len(ls))
+    inv32 = pow(1 << 32, -1, R)
+    assert unraw(o) == [l * x * inv32 % R for l, x in zip(ls, cs)]
+
+
 def test_shift_and_mask_helpers(shim):
     vals = _vals()
     n = len(vals)

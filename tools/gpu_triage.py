@@ -89,6 +89,22 @@ def main():
     rs_bytes = N * N * 32 * (1 + W)
     out["rescale_N1024"] = dict(ms_best=best, ms_med=med, gbps=rs_bytes / (best * 1e-3) / 1e9, W=W)
     print("rescale N=1024:", out["rescale_N1024"], flush=True)
+    wit_ref, q_ref = torch.empty_like(wit), torch.empty_like(q)
+    pkg.set_rescale_generic(True)
+    best, med = timeit(lambda: h.rescale_witness_dev(cs, N * N, P, lb, q_ref, wit_ref), stream, reps=2, warm=1)
+    pkg.set_rescale_generic(False)
+    h.sync()
+    out["rescale_N1024_generic"] = dict(ms_best=best, same_as_staged=bool((wit_ref == wit).all() and (q_ref == q).all()))
+    print("rescale generic:", out["rescale_N1024_generic"], flush=True)
+    del wit_ref, q_ref
+    tot = torch.empty((N, 4), dtype=torch.int64, device="cuda")
+    best, med = timeit(lambda: h.mat_vec_prefix_dev(cs, bufs["powers"], bufs["pcv"], tot), stream)
+    out["mat_vec_prefix_N1024"] = dict(ms_best=best, ms_med=med, gbps=N * N * 64 / (best * 1e-3) / 1e9,
+                                       gmuladd_s=N * N / (best * 1e-3) / 1e9)
+    print("mat_vec_prefix N=1024:", out["mat_vec_prefix_N1024"], flush=True)
+    best, med = timeit(lambda: h.gamma_powers_dev(gamma, N, bufs["powers"]), stream)
+    out["gamma_powers_1024"] = dict(ms_best=best, ms_med=med)
+    print("gamma_powers 1024:", out["gamma_powers_1024"], flush=True)
     # zkvec config 1
     B_, L_ = 4096, 1024
     x, s = rand_fr(gen, B_, L_), rand_fr(gen, B_, L_)
