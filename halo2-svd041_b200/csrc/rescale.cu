@@ -101,34 +101,56 @@ constexpr size_t RS_SMEM = (size_t)RS_THREADS * 2 * RS_ROW_U4 * sizeof(uint4);
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// one lane of the (converged) warp; ptxas then knows the guarded region runs single-threaded and
+// feeds the uniform-operand bulk copies without a per-lane serialisation loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+    return is_leader != 0;
+}
 
 // Per-lane witness stream: values go to this lane's shared-memory row; every RS_CH values (and at the
-// end of the element) the row is shipped to its place in out_wit by one bulk copy.
+// end of the element) the warp ships its 32 rows to their places in out_wit.  cp.async.bulk takes
+// uniform operands, so ONE elected lane issues the 32 row copies of the warp (per-lane issue would be
+// serialised by the compiler into a 32-trip loop of ~14 instructions each -- measured: 44 % of all
+// executed instructions); the warp's 32 elements are consecutive, so row r goes to gbase + r*W.
 struct WitnessStream {
-    uint4* row0;  // two consecutive rows of RS_ROW_U4 16-byte units
-    Fr* gdst;
+    uint4* row0;      // this lane's two consecutive rows of RS_ROW_U4 16-byte units
+    uint4* warp_row0; // lane 0's rows (the elected lane walks all 32)
+    Fr* gwarp;        // out_wit position of lane 0's element, advanced by every flush
+    int W, valid;     // witnesses per element; lanes of this warp that hold a real element
     int buf, fill;
 
-    __device__ __forceinline__ uint4* row() const { return row0 + buf * RS_ROW_U4; }
     __device__ __forceinline__ void put(const Fr& v) {
-        uint4* s = row() + 2 * fill;
+        uint4* s = row0 + buf * RS_ROW_U4 + 2 * fill;
         s[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
         s[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
         if (++fill == RS_CH) flush();
     }
-    __device__ __forceinline__ void flush() {
+    __device__ __forceinline__ void flush() {  // warp-uniform: every lane has the same `fill`
         if (fill == 0) return;
-        // generic-proxy writes of this thread -> visible to the async proxy, then bulk store
+        // generic-proxy writes of every lane -> visible to the async proxy, then the elected lane ships
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                     "r"(smem_addr(row())), "r"((uint32_t)(fill * sizeof(Fr)))
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        gdst += fill;
+        __syncwarp();
+        if (elect_one()) {
+            const uint32_t bytes = (uint32_t)(fill * sizeof(Fr));
+            uint32_t src = smem_addr(warp_row0 + buf * RS_ROW_U4);
+            Fr* dst = gwarp;
+            for (int r = 0; r < valid; r++) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                             "r"(bytes)
+                             : "memory");
+                src += 2 * RS_ROW_U4 * sizeof(uint4);
+                dst += W;
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the rows we switch to were shipped one flush ago: wait until the engine has read them
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncwarp();
+        gwarp += fill;
         fill = 0;
         buf ^= 1;
-        // the row we switch to was shipped one flush ago: wait until the engine has read it
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     }
 };
 
@@ -174,13 +196,21 @@ __global__ void __launch_bounds__(RS_THREADS)
 rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
                const __grid_constant__ RescaleConsts k) {
     extern __shared__ __align__(16) uint4 rs_stage[];
+    const int lane = threadIdx.x & 31;
     WitnessStream ws;
     ws.row0 = rs_stage + (size_t)threadIdx.x * 2 * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * 2 * RS_ROW_U4;
+    ws.W = k.p.W;
     ws.buf = 0;
     ws.fill = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
-        ws.gdst = out_wit + e * (size_t)k.p.W;
+    // warp-uniform trip count: lanes past the end recompute the last element and ship nothing
+    for (size_t e0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < count; e0 += stride) {
+        const size_t left = count - e0;
+        ws.valid = left < 32 ? (int)left : 32;
+        ws.gwarp = out_wit + e0 * (size_t)k.p.W;
+        const bool live = lane < ws.valid;
+        const size_t e = live ? e0 + lane : count - 1;
         const Fr am = ldg_fr(cs + e);
         const Fr a = fr::from_mont_fast(am);                    // canonical integer
         const Fr ash = fr::add_fast(a, k.i_2S);                 // gate.add(a, Constant(2^S))
@@ -196,10 +226,10 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
         const Fr q = fr::sub_fast(m_div, k.m_2SP);              // gate.sub(div, Constant(2^(S-P)))
         ws.put(q);
         ws.flush();
-        st_fr(out_q + e, q);
+        if (live) st_fr(out_q + e, q);
     }
     // shared memory must outlive every bulk read, and the writes must be complete at kernel end
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace
