@@ -42,6 +42,12 @@ SIGNATURES = {
     "h2svd_mat_vec_prefix_dev": (_I, [_P, _P, _P, _Z, _Z, _P]),
     "h2svd_mat_vec_prefix_totals_dev": (_I, [_P, _P, _P, _Z, _Z, _P, _P]),
     "h2svd_mat_vec_prefix_pair_dev": (_I, [_P, _P, _Z, _P, _P, _P, _Z, _P, _P, _P, _Z]),
+    "h2svd_mat_vec_prefix": (_I, [_P, _P, _P, _Z, _Z, _P]),
+    "h2svd_host_fr_from_canonical": (_I, [_P, _P]),
+    "h2svd_host_fr_to_canonical": (None, [_P, _P]),
+    "h2svd_host_fr_add": (None, [_P, _P, _P]),
+    "h2svd_host_fr_sub": (None, [_P, _P, _P]),
+    "h2svd_host_fr_mul": (None, [_P, _P, _P]),
     "h2svd_gather_dev": (_I, [_P, _P, _Z, _Z, _Z, _P]),
     "h2svd_is_equal_witness_dev": (_I, [_P, _P, _P, _Z, _P, _P, _P]),
     "h2svd_rescale_witness_count": (_I, [_I, _I, _I, _I]),

@@ -330,6 +330,26 @@ int h2svd_freivalds_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b
     return check_flag(ctx, "freivalds_witness");
 }
 
+int h2svd_mat_vec_prefix(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* v, size_t rows, size_t len,
+                         h2svd_fr* out_prefix) {
+    REQUIRE(ctx && a && v && out_prefix, "mat_vec_prefix: null argument");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    const size_t cnt = rows * len, F = sizeof(Fr);
+    if (cnt == 0) return H2SVD_OK;
+    H2SVD_TRY(ws_reserve(ctx, 2 * Carver::need(cnt * F) + Carver::need(len * F)));
+    Carver cv(ctx->ws);
+    Fr* da = cv.take<Fr>(cnt);
+    Fr* dv = cv.take<Fr>(len);
+    Fr* dout = cv.take<Fr>(cnt);
+    H2SVD_TRY(h2d(ctx, da, a, cnt * F));
+    H2SVD_TRY(h2d(ctx, dv, v, len * F));
+    H2SVD_TRY(launch_check_canonical(ctx, da, cnt, ctx->d_flag));
+    H2SVD_TRY(launch_check_canonical(ctx, dv, len, ctx->d_flag));
+    H2SVD_TRY(launch_mat_vec_prefix(ctx, da, dv, rows, len, 0, dout, nullptr));
+    H2SVD_TRY(d2h(ctx, out_prefix, dout, cnt * F));
+    return check_flag(ctx, "mat_vec_prefix");
+}
+
 /* ---- K4 ---- */
 int h2svd_rescale_witness_count(int precision_bits, int lookup_bits, int shift_bits, int a_num_bits) {
     const int w = rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr);
@@ -481,6 +501,39 @@ int h2svd_check_canonical_dev(h2svd_ctx* ctx, const h2svd_fr* x, size_t count) {
     H2SVD_CUDA(cudaSetDevice(ctx->device));
     H2SVD_TRY(launch_check_canonical(ctx, as_fr(x), count, ctx->d_flag));
     return check_flag(ctx, "check_canonical");
+}
+
+/* ---- host-side scalar helpers (fr.cuh is host-callable) ---- */
+static Fr fr_from_u64(const uint64_t* x) {
+    Fr f;
+    for (int i = 0; i < 4; i++) {
+        f.l[2 * i] = (uint32_t)x[i];
+        f.l[2 * i + 1] = (uint32_t)(x[i] >> 32);
+    }
+    return f;
+}
+static void fr_to_u64(const Fr& f, uint64_t* x) {
+    for (int i = 0; i < 4; i++) x[i] = (uint64_t)f.l[2 * i] | ((uint64_t)f.l[2 * i + 1] << 32);
+}
+int h2svd_host_fr_from_canonical(const uint64_t x[4], h2svd_fr* out) {
+    REQUIRE(x && out, "host_fr_from_canonical: null argument");
+    const Fr v = fr_from_u64(x);
+    if (!fr::is_canonical(v)) {
+        set_error("host_fr_from_canonical: value >= r");
+        return H2SVD_ERANGE;
+    }
+    fr_to_u64(fr::to_mont(v), out->l);
+    return H2SVD_OK;
+}
+void h2svd_host_fr_to_canonical(const h2svd_fr* a, uint64_t out[4]) { fr_to_u64(fr::from_mont(fr_from_u64(a->l)), out); }
+void h2svd_host_fr_add(const h2svd_fr* a, const h2svd_fr* b, h2svd_fr* out) {
+    fr_to_u64(fr::add(fr_from_u64(a->l), fr_from_u64(b->l)), out->l);
+}
+void h2svd_host_fr_sub(const h2svd_fr* a, const h2svd_fr* b, h2svd_fr* out) {
+    fr_to_u64(fr::sub(fr_from_u64(a->l), fr_from_u64(b->l)), out->l);
+}
+void h2svd_host_fr_mul(const h2svd_fr* a, const h2svd_fr* b, h2svd_fr* out) {
+    fr_to_u64(fr::mont_mul(fr_from_u64(a->l), fr_from_u64(b->l)), out->l);
 }
 
 int h2svd_microbench_imad(h2svd_ctx* ctx, int kind, int iters, double* ops_per_s) {

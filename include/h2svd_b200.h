@@ -112,6 +112,11 @@ int h2svd_gather_dev(h2svd_ctx *ctx, const h2svd_fr *src, size_t count, size_t s
 int h2svd_is_equal_witness_dev(h2svd_ctx *ctx, const h2svd_fr *x, const h2svd_fr *y, size_t count,
                                h2svd_fr *diff, h2svd_fr *is_zero, h2svd_fr *inv);
 
+/* Host-pointer form of h2svd_mat_vec_prefix_dev: the value side of field_mat_vec_mul (:574-599) for callers outside
+ * verify_mul (e.g. ZkVector::mul, :169-182).  out_prefix[i*len + j] = sum_{t<=j} a[i][t] * v[t]. */
+int h2svd_mat_vec_prefix(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, size_t rows, size_t len,
+                         h2svd_fr *out_prefix);
+
 /* ---- K4: rescale witness -----------------------------------------------------------------------------
  * Replaces the value computation of ZkMatrix::rescale_matrix (src/matrix/mod.rs:354-375), i.e. one
  * FixedPointChip041::signed_div_scale per element (:369; also ZkVector::inner_product :104).
@@ -163,6 +168,15 @@ int h2svd_quantize_dev(h2svd_ctx *ctx, const double *x, size_t count, int precis
 /* ---- input validation ----------------------------------------------------------------------------------------
  * Returns H2SVD_OK if all `count` device-resident elements are canonical (< r), else H2SVD_ERANGE. */
 int h2svd_check_canonical_dev(h2svd_ctx *ctx, const h2svd_fr *x, size_t count);
+
+/* ---- host-side scalar field helpers (no GPU, no handle) --------------------------------------------------------------
+ * What a shim needs to build `Constant` cells (2^S, 2^(lb*i), -2^bits, ...) and to check gates a + b*c - d == 0
+ * on an advice stream; scalar utilities, not a compute path.  from_canonical returns H2SVD_ERANGE for x >= r. */
+int h2svd_host_fr_from_canonical(const uint64_t x[4], h2svd_fr *out);
+void h2svd_host_fr_to_canonical(const h2svd_fr *a, uint64_t out[4]);
+void h2svd_host_fr_add(const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *out);
+void h2svd_host_fr_sub(const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *out);
+void h2svd_host_fr_mul(const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *out);
 
 /* ---- measurement aids -------------------------------------------------------------------------------------------
  * Integer-pipe micro-benchmark used as the mat-mul roofline denominator.  kind: 0 = mad.lo.u32

@@ -490,6 +490,7 @@ class ZkMatrix:
         assert len(c_s[0]) >= 1
         d = len(c_s[0])
         one = ctx.load_witness(1)  # :318
+        ctx.constants.append((one.index, 1))  # :319 gate.assert_is_const(ctx, &one, &F::ONE): a constant equality, no new cell
         v = [one]
         for i in range(1, d):
             v.append(fp.gate.mul(ctx, E(v[i - 1]), E(init_rand)))  # :324

@@ -1,0 +1,151 @@
+// Test driver for include/h2svd_zk.hpp: runs the reference's usage scenarios through the C++ host
+// mirror and exports the recorded halo2-base contexts so pytest can diff them cell by cell against
+// the oracle's model (oracle/pyoracle.py).  Linked against libh2svd_b200.so for the GPU tests and
+// against tests/host/abi_over_oracle.c for the CPU-only tests of the bookkeeping.
+#include <cstring>
+#include <memory>
+
+#include "../../include/h2svd_zk.hpp"
+
+using namespace h2svd::zk;
+
+static std::vector<Context> g_ctx;
+static std::vector<std::string> g_fail;
+static std::string g_error;
+static std::vector<double> g_scalars;  // dequantized results a scenario wants to report
+
+template <uint32_t P>
+static void run_zkmatrix(int lb, const double* a, const double* b, size_t n, size_t k, size_t m, const Fr& gamma) {
+    // README.md:34-47 usage: phase 0 = honest_prover_mat_mul + rescale_matrix, phase 1 = verify_mul
+    FixedPointChip041<P> fpchip(lb);
+    g_ctx.emplace_back(0);
+    g_ctx.emplace_back(1);
+    Context& ctx = g_ctx[0];
+    std::vector<std::vector<double>> am(n, std::vector<double>(k)), bm(k, std::vector<double>(m));
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < k; j++) am[i][j] = a[i * k + j];
+    for (size_t i = 0; i < k; i++) for (size_t j = 0; j < m; j++) bm[i][j] = b[i * m + j];
+    const ZkMatrix<P> za = ZkMatrix<P>::create(ctx, fpchip, am);
+    const ZkMatrix<P> zb = ZkMatrix<P>::create(ctx, fpchip, bm);
+    const AssignedMatrix c_s = honest_prover_mat_mul(ctx, za.matrix, zb.matrix);
+    const ZkMatrix<P> c = ZkMatrix<P>::rescale_matrix(ctx, fpchip, c_s);
+    Context& ctx1 = g_ctx[1];
+    const AssignedValue init_rand = ctx1.load_witness(gamma);
+    ZkMatrix<P>::verify_mul(ctx1, fpchip, za, zb, c_s, init_rand);
+    for (const auto& row : c.dequantize(fpchip)) g_scalars.insert(g_scalars.end(), row.begin(), row.end());
+}
+
+// src/matrix/test_matrix.rs:39-198 (test_zkvector), same inputs and call order, P = 32
+static void run_zkvector(int lb) {
+    constexpr uint32_t P = 32;
+    FixedPointChip041<P> fpchip(lb);
+    g_ctx.emplace_back(0);
+    Context& ctx = g_ctx[0];
+    const size_t N = 5, M = 4;
+    std::vector<std::vector<double>> matrix(N, std::vector<double>(M));
+    for (size_t i = 0; i < N; i++) for (size_t j = 0; j < M; j++) matrix[i][j] = (double)i + (double)j / 10.0;
+    const ZkMatrix<P> zkmatrix = ZkMatrix<P>::create(ctx, fpchip, matrix);
+    std::vector<double> v1, v2;
+    for (size_t i = 0; i < M; i++) v1.push_back((i % 2 == 0 ? (double)i : -(double)i) + (double)(i * i + 1) / 10.0);
+    for (size_t i = 0; i < M; i++) v2.push_back((i % 2 == 0 ? 1.0 : -1.0) * (1.0 + (double)(i * i * i)) / 10.0);
+    const ZkVector<P> zkvec1 = ZkVector<P>::create(ctx, fpchip, v1);
+    const ZkVector<P> zkvec2 = ZkVector<P>::create(ctx, fpchip, v2);
+    auto dq = [&](const AssignedValue& x) { g_scalars.push_back(fpchip.dequantization(x.v)); };
+    dq(zkvec1.inner_product(ctx, fpchip, zkvec2.v));
+    dq(zkvec1.norm(ctx, fpchip));
+    dq(zkvec2.norm(ctx, fpchip));
+    dq(zkvec1.dist(ctx, fpchip, zkvec2.v));
+    dq(zkvec1._norm_square(ctx, fpchip));
+    dq(zkvec2._norm_square(ctx, fpchip));
+    dq(zkvec1._dist_square(ctx, fpchip, zkvec2.v));
+    for (double x : zkvec1.mul(ctx, fpchip, zkmatrix).dequantize(fpchip)) g_scalars.push_back(x);
+    for (double x : zkvec2.mul(ctx, fpchip, zkmatrix).dequantize(fpchip)) g_scalars.push_back(x);
+}
+
+// src/matrix/test_matrix.rs:201-265 (test_field_mat_times_vec) with caller-supplied inputs, P = 32
+static void run_mat_times_vec(int lb, const double* mat, const double* vec, size_t n, size_t m) {
+    constexpr uint32_t P = 32;
+    FixedPointChip041<P> fpchip(lb);
+    g_ctx.emplace_back(0);
+    Context& ctx = g_ctx[0];
+    std::vector<std::vector<double>> matrix(n, std::vector<double>(m));
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < m; j++) matrix[i][j] = mat[i * m + j];
+    const ZkMatrix<P> zkmatrix = ZkMatrix<P>::create(ctx, fpchip, matrix);
+    const ZkVector<P> zkvec1 = ZkVector<P>::create(ctx, fpchip, std::vector<double>(vec, vec + m));
+    const std::vector<AssignedValue> zku1_s = field_mat_vec_mul(ctx, fpchip.gate(), zkmatrix.matrix, zkvec1.v);
+    for (const AssignedValue& x : zku1_s) g_scalars.push_back(fpchip.dequantization(fpchip.signed_div_scale(ctx, x).first.v));
+}
+
+template <typename F>
+static int guarded(int lb, F&& f) {
+    g_ctx.clear();
+    g_fail.clear();
+    g_scalars.clear();
+    g_error.clear();
+    try {
+        f();
+        std::vector<const Context*> ptrs;
+        for (const Context& c : g_ctx) ptrs.push_back(&c);
+        g_fail = mock_verify(ptrs, lb);
+        return (int)g_fail.size();
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+extern "C" {
+int zkh_run_zkmatrix(int P, int lb, const double* a, const double* b, size_t n, size_t k, size_t m, const uint64_t* gamma) {
+    Fr g;
+    std::memcpy(g.l, gamma, 32);
+    return guarded(lb, [&] {
+        switch (P) {
+            case 32: run_zkmatrix<32>(lb, a, b, n, k, m, g); break;
+            case 42: run_zkmatrix<42>(lb, a, b, n, k, m, g); break;
+            case 63: run_zkmatrix<63>(lb, a, b, n, k, m, g); break;
+            default: throw std::logic_error("unsupported PRECISION_BITS in the test driver");
+        }
+    });
+}
+int zkh_run_zkvector(int lb) { return guarded(lb, [&] { run_zkvector(lb); }); }
+int zkh_run_mat_times_vec(int lb, const double* mat, const double* vec, size_t n, size_t m) {
+    return guarded(lb, [&] { run_mat_times_vec(lb, mat, vec, n, m); });
+}
+// shape-assert behaviour: verify_mul with mismatching shapes must throw (the reference panics, :307-310)
+int zkh_run_bad_shapes(int lb) {
+    return guarded(lb, [&] {
+        FixedPointChip041<32> fpchip(lb);
+        g_ctx.emplace_back(0);
+        Context& ctx = g_ctx[0];
+        const ZkMatrix<32> a = ZkMatrix<32>::create(ctx, fpchip, {{1.0, 2.0}, {3.0, 4.0}});
+        const ZkMatrix<32> b = ZkMatrix<32>::create(ctx, fpchip, {{1.0, 2.0, 3.0}});
+        honest_prover_mat_mul(ctx, a.matrix, b.matrix);
+    });
+}
+const char* zkh_error() { return g_error.c_str(); }
+const char* zkh_failure(int i) { return i < (int)g_fail.size() ? g_fail[i].c_str() : ""; }
+size_t zkh_ctx_count() { return g_ctx.size(); }
+size_t zkh_ctx_len(size_t c) { return g_ctx[c].advice.size(); }
+size_t zkh_ctx_ncopies(size_t c) { return g_ctx[c].copies.size(); }
+size_t zkh_ctx_nconstants(size_t c) { return g_ctx[c].constants.size(); }
+size_t zkh_ctx_nlookups(size_t c) { return g_ctx[c].lookups.size(); }
+size_t zkh_nscalars() { return g_scalars.size(); }
+void zkh_scalars(double* out) { std::memcpy(out, g_scalars.data(), g_scalars.size() * sizeof(double)); }
+void zkh_ctx_export(size_t c, uint64_t* advice, uint8_t* kind, uint8_t* selector, uint64_t* copies, uint64_t* const_idx,
+                    uint64_t* const_val, uint64_t* lookups) {
+    const Context& x = g_ctx[c];
+    std::memcpy(advice, x.advice.data(), x.advice.size() * sizeof(Fr));
+    std::memcpy(kind, x.kind.data(), x.kind.size());
+    std::memcpy(selector, x.selector.data(), x.selector.size());
+    for (size_t i = 0; i < x.copies.size(); i++) {
+        copies[4 * i] = x.copies[i].first.ctx_id;
+        copies[4 * i + 1] = x.copies[i].first.index;
+        copies[4 * i + 2] = x.copies[i].second.ctx_id;
+        copies[4 * i + 3] = x.copies[i].second.index;
+    }
+    for (size_t i = 0; i < x.constants.size(); i++) {
+        const_idx[i] = x.constants[i].first;
+        std::memcpy(const_val + 4 * i, x.constants[i].second.l, 32);
+    }
+    for (size_t i = 0; i < x.lookups.size(); i++) lookups[i] = x.lookups[i];
+}
+}
