@@ -69,6 +69,7 @@ DEBUG_SIGNATURES = {
     "h2svd_debug_fr_matmul_naive_dev": (_I, [_P, _P, _P, _P, _Z, _Z, _Z]),
     "h2svd_debug_set_matmul_variant": (_I, [_I]),
     "h2svd_debug_set_rescale_generic": (_I, [_I]),
+    "h2svd_debug_set_matmul_streamk": (_I, [_I]),
 }
 
 _LIB = None

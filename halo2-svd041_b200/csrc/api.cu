@@ -169,6 +169,7 @@ void h2svd_destroy(h2svd_ctx* ctx) {
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->sk_ws) cudaFree(ctx->sk_ws);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

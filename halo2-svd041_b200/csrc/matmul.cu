@@ -169,6 +169,205 @@ fr_matmul_kernel(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Stream-K variant for shapes whose tile count does not fill the resident CTA slots evenly (e.g. the
+// 128 x 1024 row slab of one of 8 GPUs at N=1024: 256 tiles on 296 slots = 86 % of a wave).
+// The (tile, k-chunk) iteration space is flattened into `total_units` and cut into gridDim.x equal
+// contiguous ranges, one per resident CTA, so every SM gets the same number of k-chunks (+-1).  The TMA
+// pipeline runs straight through tile boundaries.  A CTA that covers a whole tile writes C directly; a
+// partial tile goes, Montgomery-reduced, to this CTA's slot 0 (first segment) or slot 1 (last segment) of
+// `partial`, and fr_matmul_fixup_kernel adds the 2-3 partials of every split tile.  No CTA ever waits on
+// another one.  Exact: field addition of canonical partial sums is order-independent.
+// CTA-wide state of the stream-K kernel, kept in shared memory so that the segment routine below has the
+// same small register state as the one-CTA-per-tile kernel.
+template <int STAGES>
+struct SkShared {
+    uint64_t full_bar[STAGES];
+    uint64_t empty_bar[STAGES];
+    // per-stage unit descriptor written by the issuing warp: {klen, row0, col0, kc} (consumers use klen)
+    int4 meta[STAGES];
+    const Fr* A;
+    const Fr* B;
+    Fr* C;
+    Fr* partial;  // this CTA's two partial-tile slots
+    int n, k, m, tiles_x, nchunks, u0, nloc, tile0;
+};
+
+// The one SkShared object of the CTA (static shared memory has a compile-time address, so neither it nor
+// the dynamic-shared tile buffers cost a register in the segment routine).
+template <int STAGES>
+__device__ __forceinline__ SkShared<STAGES>* sk_shared() {
+    __shared__ __align__(16) SkShared<STAGES> sh;
+    return &sh;
+}
+extern __shared__ __align__(128) unsigned char sk_smem_raw[];
+
+// warp 0 only: stage unit i (in-range rows / columns / k only) and publish its descriptor
+template <int TM, int TN, int BK, int STAGES>
+__device__ __forceinline__ void sk_issue_unit(int i, int lane) {
+    using cfg = Cfg<TM, TN, BK, STAGES>;
+    SkShared<STAGES>* sh = sk_shared<STAGES>();
+    Fr* sA = reinterpret_cast<Fr*>(sk_smem_raw);
+    Fr* sB = sA + STAGES * cfg::A_STAGE;
+    const int n = sh->n, k = sh->k, m = sh->m, nchunks = sh->nchunks, tiles_x = sh->tiles_x, u0 = sh->u0;
+    const int u = u0 + i;
+    const int tile = u / nchunks, kc = u - tile * nchunks;
+    const int trow = tile / tiles_x;
+    const int row0 = trow * cfg::BM, col0 = (tile - trow * tiles_x) * cfg::BN;
+    const int rows_valid = min(cfg::BM, n - row0), cols_valid = min(cfg::BN, m - col0);
+    const int s = i % STAGES;
+    const int k0 = kc * BK;
+    const int klen = min(BK, k - k0);
+    if (lane == 0) {
+        sh->meta[s] = make_int4(klen, row0, col0, kc);
+        const uint32_t bytes = (uint32_t)((rows_valid * klen + klen * cols_valid) * sizeof(Fr));
+        mbar_arrive_expect_tx(&sh->full_bar[s], bytes);  // release: meta[s] is visible to whoever waits on it
+    }
+    __syncwarp();
+    Fr* dA = sA + s * cfg::A_STAGE;
+    Fr* dB = sB + s * cfg::B_STAGE;
+    const Fr* A = sh->A;
+    const Fr* B = sh->B;
+    for (int r = lane; r < rows_valid; r += 32)
+        tma_bulk_g2s(dA + r * BK, A + (size_t)(row0 + r) * k + k0, (uint32_t)(klen * sizeof(Fr)), &sh->full_bar[s]);
+    for (int r = lane; r < klen; r += 32)
+        tma_bulk_g2s(dB + r * cfg::BN, B + (size_t)(k0 + r) * m + col0, (uint32_t)(cols_valid * sizeof(Fr)),
+                     &sh->full_bar[s]);
+}
+
+// One segment = this CTA's share of one tile, starting at local unit i; returns the next local unit.
+// Deliberately NOT inlined, a COUNTED unit loop, and nothing but the accumulators live across the k loop
+// (the tile coordinates are recomputed after it): with any other shape ptxas stops keeping the 72 accumulator
+// registers in aligned pairs and shuffles them with IMAD.MOV / XOR swaps every k step -- up to +70 %
+// instructions on the very pipe the kernel is bound by (measured 98 vs 129 G mul-add/s).
+template <int TM, int TN, int BK, int STAGES>
+__device__ __noinline__ int sk_segment(int i) {
+    using cfg = Cfg<TM, TN, BK, STAGES>;
+    constexpr int PD = STAGES - 2;
+    SkShared<STAGES>* sh = sk_shared<STAGES>();
+    Fr* sA = reinterpret_cast<Fr*>(sk_smem_raw);
+    Fr* sB = sA + STAGES * cfg::A_STAGE;
+    fr::WideAcc acc[TM][TN];
+#pragma unroll
+    for (int ii = 0; ii < TM; ii++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) fr::acc_clear(acc[ii][j]);
+    // units of this segment: to the end of the tile or of this CTA's range, whichever comes first
+    const int kc0 = (sh->u0 + i) % sh->nchunks;
+    const int cnt = min(sh->nchunks - kc0, sh->nloc - i);
+    int s = 0;
+    for (int c = 0; c < cnt; c++, i++) {
+        if (threadIdx.x < 32 && i + PD < sh->nloc) {
+            if (i >= 2) mbar_wait(&sh->empty_bar[(i - 2) % STAGES], ((i - 2) / STAGES) & 1);
+            sk_issue_unit<TM, TN, BK, STAGES>(i + PD, (int)threadIdx.x);
+        }
+        s = i % STAGES;
+        mbar_wait(&sh->full_bar[s], (i / STAGES) & 1);
+        const Fr* pA = sA + s * cfg::A_STAGE + (threadIdx.x / TX) * BK;
+        const Fr* pB = sB + s * cfg::B_STAGE + (threadIdx.x % TX);
+        const int klen = sh->meta[s].x;
+#pragma unroll 1
+        for (int kk = 0; kk < klen; kk++) {
+            Fr a[TM], b[TN];
+#pragma unroll
+            for (int ii = 0; ii < TM; ii++) a[ii] = ld_fr(pA + ii * TY * BK + kk);
+#pragma unroll
+            for (int j = 0; j < TN; j++) b[j] = ld_fr(pB + kk * cfg::BN + j * TX);
+#pragma unroll
+            for (int ii = 0; ii < TM; ii++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) fr::mul_acc(acc[ii][j], a[ii].l, b[j].l);
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&sh->empty_bar[s]);
+    }
+    // where this segment lives (recomputed here rather than carried through the k loop in registers)
+    const int u_last = sh->u0 + i - 1;
+    const int tile = u_last / sh->nchunks, kc_last = u_last - tile * sh->nchunks;
+    const int trow = tile / sh->tiles_x;
+    const int row0 = trow * cfg::BM, col0 = (tile - trow * sh->tiles_x) * cfg::BN;
+    const int flags = ((kc_last == sh->nchunks - 1 && cnt == sh->nchunks) ? 2 : 0) | ((tile == sh->tile0 ? 0 : 1) << 2);
+
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const bool whole = (flags & 2) != 0;
+    const int n = sh->n, m = sh->m;
+    Fr* C = sh->C;
+    Fr* pdst = sh->partial + (size_t)(flags >> 2) * (cfg::BM * cfg::BN);
+#pragma unroll
+    for (int ii = 0; ii < TM; ii++) {
+        const int rl = ty + ii * TY;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            const int cl = tx + j * TX;
+            if (row0 + rl < n && col0 + cl < m) {
+                const Fr val = fr::acc_finalize(acc[ii][j]);
+                if (whole)
+                    st_fr(C + (size_t)(row0 + rl) * m + col0 + cl, val);
+                else
+                    st_fr(pdst + rl * cfg::BN + cl, val);
+            }
+        }
+    }
+    return i;
+}
+
+template <int TM, int TN, int BK, int STAGES, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+fr_matmul_streamk_kernel(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restrict__ C,
+                         Fr* __restrict__ partial, int n, int k, int m, int tiles_x, int nchunks,
+                         long long total_units) {
+    using cfg = Cfg<TM, TN, BK, STAGES>;
+    constexpr int PD = STAGES - 2;
+    SkShared<STAGES>* sh = sk_shared<STAGES>();
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        // total_units < 2^31 (checked by the launcher): per-unit index math stays 32-bit
+        const int u0 = (int)(((long long)blockIdx.x * total_units) / gridDim.x);
+        const int u1 = (int)(((long long)(blockIdx.x + 1) * total_units) / gridDim.x);
+        sh->A = A; sh->B = B; sh->C = C;
+        sh->partial = partial + (size_t)blockIdx.x * 2 * (cfg::BM * cfg::BN);
+        sh->n = n; sh->k = k; sh->m = m; sh->tiles_x = tiles_x; sh->nchunks = nchunks;
+        sh->u0 = u0; sh->nloc = u1 - u0; sh->tile0 = u0 / nchunks;
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&sh->full_bar[s], 1);
+            mbar_init(&sh->empty_bar[s], WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nloc = sh->nloc;
+    if (tid < 32) {
+        for (int i = 0; i < PD && i < nloc; i++) sk_issue_unit<TM, TN, BK, STAGES>(i, tid);
+    }
+    int i = 0;
+    while (i < nloc) i = sk_segment<TM, TN, BK, STAGES>(i);
+}
+
+// Adds the partial sums of every tile that stream-K split over several CTAs (see above).
+template <int BM, int BN>
+__global__ void fr_matmul_fixup_kernel(Fr* __restrict__ C, const Fr* __restrict__ partial, int n, int m, int tiles_x,
+                                       int nchunks, long long total_units, int G) {
+    const int tile = blockIdx.x;
+    const long long ub = (long long)tile * nchunks, ue = ub + nchunks - 1;
+    auto owner = [&](long long u) { return (int)(((u + 1) * G + total_units - 1) / total_units - 1); };
+    const int c_first = owner(ub), c_last = owner(ue);
+    if (c_first == c_last) return;  // written directly by its only CTA
+    const int row0 = (tile / tiles_x) * BM, col0 = (tile % tiles_x) * BN;
+    for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+        const int rl = e / BN, cl = e % BN;
+        if (row0 + rl >= n || col0 + cl >= m) continue;
+        Fr sum = fr::zero();
+        for (int c = c_first; c <= c_last; c++) {
+            const long long u0 = ((long long)c * total_units) / G;
+            const int slot = (u0 / nchunks == tile) ? 0 : 1;  // this tile is the CTA's first segment, else its last
+            sum = fr::add(sum, ldg_fr(partial + ((size_t)c * 2 + slot) * (BM * BN) + e));
+        }
+        st_fr(C + (size_t)(row0 + rl) * m + col0 + cl, sum);
+    }
+}
+
 // One thread per C element, fully reduced arithmetic.  Debug/triage only (not on any product path).
 __global__ void fr_matmul_naive_kernel(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restrict__ C,
                                        int n, int k, int m) {
@@ -204,17 +403,53 @@ __global__ void transpose_kernel(const Fr* __restrict__ src, Fr* __restrict__ ds
 }
 
 int g_variant = 0;
+int g_streamk = -1;  // -1 auto, 0 never, 1 always (triage hook)
 
 template <int TM, int TN, int BK, int STAGES, int MINBLOCKS>
 int launch_variant(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k, int m) {
     using cfg = Cfg<TM, TN, BK, STAGES>;
+    const int tiles_x = (m + cfg::BN - 1) / cfg::BN, tiles_y = (n + cfg::BM - 1) / cfg::BM;
+    const long long tiles = (long long)tiles_x * tiles_y;
+    const int nchunks = (k + BK - 1) / BK;
+    const int slots = ctx->sm_count * MINBLOCKS;
+    // Schedule choice (measured on B200, tools/matmul_bench.py): the one-CTA-per-tile launch runs at
+    // 129 G mul-add/s once there are >= ~3.5 waves of tiles (a partial last wave is softened because an SM
+    // holding one CTA instead of two runs it ~1.6x faster), but drops to 106-110 G/s at 0.9-1.7 waves (the
+    // 128- and 256-row slabs of the 8- and 4-GPU split of N=1024); stream-K holds ~118 G/s regardless.
+    const bool streamk = g_streamk < 0 ? (tiles * 2 < 5LL * slots && nchunks >= 4 && tiles * nchunks >= 2LL * slots)
+                                       : g_streamk != 0;
+    if (streamk && nchunks >= 1 && tiles * nchunks < (1LL << 31)) {
+        auto kern = fr_matmul_streamk_kernel<TM, TN, BK, STAGES, MINBLOCKS>;
+        static bool configured_sk = false;
+        if (!configured_sk) {
+            H2SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+            configured_sk = true;
+        }
+        const long long total_units = tiles * nchunks;
+        const int G = (int)(total_units < slots ? total_units : slots);
+        const size_t part_bytes = (size_t)G * 2 * cfg::BM * cfg::BN * sizeof(Fr);
+        if (ctx->sk_ws_bytes < part_bytes) {
+            H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ctx->sk_ws) H2SVD_CUDA(cudaFree(ctx->sk_ws));
+            ctx->sk_ws = nullptr;
+            ctx->sk_ws_bytes = 0;
+            H2SVD_CUDA(cudaMalloc(&ctx->sk_ws, part_bytes));
+            ctx->sk_ws_bytes = part_bytes;
+        }
+        kern<<<G, THREADS, cfg::SMEM, ctx->stream>>>(a, b, c, (Fr*)ctx->sk_ws, n, k, m, tiles_x, nchunks, total_units);
+        H2SVD_LAUNCH_CHECK(ctx);
+        fr_matmul_fixup_kernel<cfg::BM, cfg::BN><<<(unsigned)tiles, 256, 0, ctx->stream>>>(
+            c, (const Fr*)ctx->sk_ws, n, m, tiles_x, nchunks, total_units, G);
+        H2SVD_LAUNCH_CHECK(ctx);
+        return H2SVD_OK;
+    }
     auto kern = fr_matmul_kernel<TM, TN, BK, STAGES, MINBLOCKS>;
     static bool configured = false;  // per process; attribute is per function, device-wide
     if (!configured) {
         H2SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
         configured = true;
     }
-    dim3 grid((m + cfg::BN - 1) / cfg::BN, (n + cfg::BM - 1) / cfg::BM);
+    dim3 grid(tiles_x, tiles_y);
     kern<<<grid, THREADS, cfg::SMEM, ctx->stream>>>(a, b, c, n, k, m);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
@@ -256,5 +491,9 @@ int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t
 
 extern "C" int h2svd_debug_set_matmul_variant(int v) {
     h2svd::g_variant = v;
+    return 0;
+}
+extern "C" int h2svd_debug_set_matmul_streamk(int v) {
+    h2svd::g_streamk = v;
     return 0;
 }

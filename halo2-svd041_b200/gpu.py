@@ -254,6 +254,11 @@ def set_rescale_generic(v: bool) -> None:
     _ffi.load().h2svd_debug_set_rescale_generic(int(v))
 
 
+def set_matmul_streamk(v: int) -> None:
+    """Triage hook: -1 auto (default), 0 never, 1 always use the stream-K mat-mul schedule."""
+    _ffi.load().h2svd_debug_set_matmul_streamk(v)
+
+
 def set_matmul_variant(v: int) -> None:
     """Triage/tuning hook (not part of the public header)."""
     _ffi.load().h2svd_debug_set_matmul_variant(v)

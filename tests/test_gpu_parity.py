@@ -37,6 +37,27 @@ def test_fr_matmul_all_tile_variants(handle, pkg, variant):
     assert _eq(c, corac.field_mat_mul(a, b, threads=0))
 
 
+@pytest.mark.parametrize("n,k,m", [(8, 8, 8), (33, 100, 47), (128, 1024, 256), (5, 300, 3), (64, 17, 31)])
+def test_fr_matmul_streamk_schedule(handle, pkg, n, k, m):
+    """Stream-K schedule (flattened (tile, k-chunk) space cut evenly over the resident CTAs + partial-tile
+    fix-up) forced on: same bytes as the oracle and as the one-CTA-per-tile schedule."""
+    rng = np.random.default_rng(n * 7 + k)
+    a, b = random_fr(rng, n, k), random_fr(rng, k, m)
+    try:
+        pkg.set_matmul_streamk(1)
+        got = handle.fr_matmul(a, b)
+        pkg.set_matmul_streamk(0)
+        plain = handle.fr_matmul(a, b)
+    finally:
+        pkg.set_matmul_streamk(-1)
+    assert _eq(got, plain)
+    if n * k * m <= 1 << 22:
+        assert _eq(got, corac.field_mat_mul(a, b))
+    else:
+        rows = [0, n // 2, n - 1]
+        assert _eq(got[rows], corac.field_mat_mul(np.ascontiguousarray(a[rows]), b))
+
+
 def test_fr_matmul_adversarial_operands(handle):
     adv = adversarial_fr()  # 0, 1, r-1, R, R^2, 2^253, ...
     k = adv.shape[0]

@@ -1,0 +1,38 @@
+"""Times the field mat-mul on the shapes of the row-sharded N=1024 job (developer tool, run under gpurun):
+plain one-CTA-per-tile schedule vs stream-K."""
+import importlib, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("halo2-svd041_b200")
+torch.cuda.set_device(0)
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+h = pkg.Handle(0, stream.cuda_stream)
+gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+def rand_fr(*shape):
+    t = torch.randint(-(1 << 63), (1 << 63) - 1, shape + (4,), dtype=torch.int64, device="cuda", generator=gen)
+    t[..., 3] &= (1 << 60) - 1
+    return t
+shapes = [(1024, 1024, 1024), (512, 1024, 1024), (256, 1024, 1024), (128, 1024, 1024), (256, 256, 256), (512, 2048, 4096)]
+variants = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0]
+for (n, k, m) in shapes:
+    a, b = rand_fr(n, k), rand_fr(k, m)
+    c = torch.empty((n, m, 4), dtype=torch.int64, device="cuda")
+    ref = None
+    for variant in variants:
+        pkg.set_matmul_variant(variant)
+        for sk in (0, 1, -1):
+            pkg.set_matmul_streamk(sk)
+            ts = []
+            for i in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); h.fr_matmul_dev(a, b, c); e1.record(stream); e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            h.sync()
+            if ref is None:
+                ref = c.clone()
+            same = bool((ref == c).all())
+            t = min(ts[2:])
+            print(f"{n}x{k}x{m} variant {variant} streamk={sk:2d}: {t:.4f} ms  {n*k*m/t/1e6:.1f} G mul-add/s  same={same}", flush=True)
+pkg.set_matmul_streamk(-1); pkg.set_matmul_variant(0)
+h.close()
