@@ -182,6 +182,13 @@ def run_gpu(args) -> None:
     stream = torch.cuda.Stream(device=device)
     torch.cuda.set_stream(stream)
     h = pkg.Handle(local_rank, stream.cuda_stream)
+    # second handle on a second stream: the C-independent half of verify_mul overlaps the mat-mul
+    side_stream = torch.cuda.Stream(device=device)
+    h_side = pkg.Handle(local_rank, side_stream.cuda_stream)
+    side = wl.SideStream(torch, h_side, side_stream, stream)
+    # Measured: under a full-size mat-mul (2 CTAs/SM hold the whole register file) the side kernels only
+    # displace mat-mul CTAs (+0.13 ms at 1 GPU); under the small slabs of 4-8 GPUs they fill idle SM time.
+    overlap = (r1 - r0) * m < 512 * 1024
 
     n = k = m = args.n
     plan = wl.ShardPlan(n, k, m, world, rank)
@@ -199,12 +206,19 @@ def run_gpu(args) -> None:
     h.quantize_dev(b_dev_f, P_BITS, bufs.b)
     bufs.gamma.copy_(torch.from_numpy(gamma.view(np.int64).reshape(1, 4)))
     h.sync()
-    # pinned host copies of the Fr inputs / outputs for the end-to-end leg
-    host_in = {"a": bufs.a_slab.cpu().pin_memory(), "b_rows": bufs.b[b0:b1].cpu().pin_memory(),
-               "b_full": bufs.b.cpu().pin_memory(), "gamma": bufs.gamma.cpu().pin_memory()}
-    out_names = ["c_slab", "q_slab", "wit_slab", "powers", "prefix_cv", "prefix_bv", "prefix_abv", "diff",
-                 "is_zero", "inv"]
-    host_out = {nm: torch.empty(getattr(bufs, nm).shape, dtype=torch.int64).pin_memory() for nm in out_names}
+    # end-to-end leg: page-locked host buffers for the inputs and for every output of the fused C-ABI call
+    def pinned_like(t):
+        pb = pkg.PinnedBuffer(tuple(t.shape), np.uint64)
+        return pb
+
+    pin_in = {"a": pinned_like(bufs.a_slab), "b": pinned_like(bufs.b)}
+    pin_in["a"].array[...] = bufs.a_slab.cpu().numpy().view(np.uint64)
+    pin_in["b"].array[...] = bufs.b.cpu().numpy().view(np.uint64)
+    out_shapes = {"c_s": (r1 - r0, m), "q": (r1 - r0, m), "wit": ((r1 - r0) * m, W), "powers": (m,),
+                  "prefix_cv": (r1 - r0, m), "prefix_bv": (b1 - b0, m), "prefix_abv": (r1 - r0, k), "diff": (r1 - r0,),
+                  "is_zero": (r1 - r0,), "inv": (r1 - r0,)}
+    pin_out = {nm: pkg.PinnedBuffer(shp + (4,), np.uint64) for nm, shp in out_shapes.items()}
+    host_out = {nm: pb.array for nm, pb in pin_out.items()}
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
 
     def barrier():
@@ -216,40 +230,39 @@ def run_gpu(args) -> None:
         return torch.cuda.Event(enable_timing=True)
 
     def device_step(times=None):
+        # same schedule as wl.run_step(..., side=side), with phase events on the main stream
         e = [ev() for _ in range(4)] if times is not None else None
         if e: e[0].record(stream)
+        if overlap:
+            bv = side.run(lambda be: wl.step_freivalds_pre(be, plan, bufs, dist, comm))   # under the mat-mul
         wl.step_matmul(h, plan, bufs)
         if e: e[1].record(stream)
         wl.step_rescale(h, plan, bufs, P_BITS, LOOKUP_BITS)
         if e: e[2].record(stream)
-        wl.step_freivalds(h, plan, bufs, dist, comm)
+        if overlap:
+            side.join()
+        else:
+            bv = wl.step_freivalds_pre(h, plan, bufs, dist, comm)
+        wl.step_freivalds_post(h, plan, bufs, bv)
         if e:
             e[3].record(stream)
             times.append(e)
 
     def e2e_step():
-        # host -> device of this step's inputs (pinned), B row-slices all-gathered over NVLink
-        bufs.a_slab.copy_(host_in["a"], non_blocking=True)
-        bufs.gamma.copy_(host_in["gamma"], non_blocking=True)
-        if world > 1 and k % world == 0:
-            bufs.b[b0:b1].copy_(host_in["b_rows"], non_blocking=True)
-            dist.all_gather_into_tensor(bufs.b.view(-1, 4), bufs.b[b0:b1].reshape(-1, 4), group=comm)
-        else:
-            bufs.b.copy_(host_in["b_full"], non_blocking=True)
-        wl.run_step(h, plan, bufs, P_BITS, LOOKUP_BITS, dist, comm)
-        for nm in out_names:
-            host_out[nm].copy_(getattr(bufs, nm), non_blocking=True)
-        stream.synchronize()   # the step's result is on the host
+        # ONE call of the reference-facing C ABI on host buffers: H2D of A (this rank's rows), B, gamma; mat-mul,
+        # rescale and verify_mul witnesses in row slabs; D2H of every witness, overlapped slab by slab.  No
+        # collective: every rank derives the k row totals of B.v itself and returns its own share of prefix_bv.
+        h.zkmatrix_mul_witness(pin_in["a"].array, pin_in["b"].array, gamma, P_BITS, LOOKUP_BITS,
+                               bv_rows=(b0, b1), out=host_out)
 
-    launches0 = h.launch_count
     # ---- device-resident timing ----
+    sampler = ClockSampler(local_rank)   # runs through both timed regions (device-resident and end-to-end)
+    sampler.start()
     for _ in range(args.warmup):
         device_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     step_events = []
-    launches_before = h.launch_count
+    launches_before = h.launch_count + h_side.launch_count
     barrier()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -257,8 +270,7 @@ def run_gpu(args) -> None:
         device_step(step_events)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    gpu_launches = h.launch_count - launches_before
-    clocks = sampler.stop()
+    gpu_launches = h.launch_count + h_side.launch_count - launches_before
     tot = [e[0].elapsed_time(e[3]) for e in step_events]
     t_mm = [e[0].elapsed_time(e[1]) for e in step_events]
     t_rs = [e[1].elapsed_time(e[2]) for e in step_events]
@@ -275,29 +287,31 @@ def run_gpu(args) -> None:
     barrier()
     e2e_steps = args.steps
     t0 = time.perf_counter()
-    e0, e1 = ev(), ev()
-    e0.record(stream)
     for _ in range(e2e_steps):
-        e2e_step()
-    e1.record(stream)
+        e2e_step()             # synchronous: returns when the step's results are on the host
+    t_mine = (time.perf_counter() - t0) / e2e_steps
     barrier()
     e2e_wall = (time.perf_counter() - t0) / e2e_steps
-    e2e_ms_t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=device)
+    e2e_ms_t = torch.tensor([t_mine * 1e3], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(e2e_ms_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms_t.cpu()[0])
-    h2d = sum(int(host_in[x].numel()) * 8 for x in (("a", "gamma", "b_rows") if (world > 1 and k % world == 0)
-                                                    else ("a", "gamma", "b_full")))
-    d2h = sum(int(host_out[x].numel()) * 8 for x in out_names)
+    clocks = sampler.stop()
+    h2d = int(pin_in["a"].array.nbytes + pin_in["b"].array.nbytes + 32)
+    d2h = sum(int(host_out[x].nbytes) for x in host_out)
     bytes_t = torch.tensor([h2d, d2h], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
     h2d_all, d2h_all = [int(x) for x in bytes_t.cpu()]
 
     # ---- sanity: the timed buffers hold a correct witness (honest product => every diff is zero)
-    ok = bool((bufs.diff == 0).all().item()) and bool((host_out["diff"] == 0).all().item())
+    ok = bool((bufs.diff == 0).all().item()) and not host_out["diff"].any()
+    # both legs computed the same witness: the fused host call and the device-resident building blocks agree
+    for nm, dev_t in (("c_s", bufs.c_slab), ("q", bufs.q_slab), ("prefix_cv", bufs.prefix_cv), ("prefix_abv", bufs.prefix_abv),
+                      ("wit", bufs.wit_slab)):
+        ok = ok and bool((torch.from_numpy(host_out[nm].view(np.int64)).to(device) == dev_t).all().item())
     if not ok:
-        raise SystemExit("bench: Freivalds diff != 0 -- refusing to report a number for wrong results")
+        raise SystemExit("bench: witness check failed -- refusing to report a number for wrong results")
 
     units = plan.mul_adds()
     value = units / (ms_step * 1e-3)
@@ -312,7 +326,7 @@ def run_gpu(args) -> None:
         mm_imads = rows * k * m * 128.0
         achieved = mm_imads / (ms_mm * 1e-3)
         rs_bytes = rows * m * 32.0 * (1 + W)
-        fr_bytes = 2.0 * 32.0 * (rows * m + (b1 - b0) * m + rows * k)
+        fr_bytes = 2.0 * 32.0 * (rows * m + rows * k + (0 if overlap else (b1 - b0) * m))   # mat-vecs inside the timed phase
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -323,7 +337,7 @@ def run_gpu(args) -> None:
                                    f"Freivalds)", "n": n, "sharding": f"rows of A/C over {world} rank(s), B replicated, "
                                    "(B v) all-gathered", "l2": "256 MiB flush write between timed steps",
                        "inputs": "input-creator.py distribution, seeded, quantized on the GPU"},
-            "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds": ms_fr},
+            "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds_after_matmul": ms_fr, "freivalds_pre_overlapped_with_matmul": bool(overlap)},
             "roofline": {"bound": "imad", "kernel": "fr_matmul_kernel", "achieved": achieved / 1e12,
                          "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": achieved / imad_peak,
                          "peak_source": "measured live: mad.lo.u32 micro-benchmark, all SMs (h2svd_microbench_imad kind 0)",
@@ -340,15 +354,16 @@ def run_gpu(args) -> None:
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "wall_ms_per_step": e2e_wall * 1e3, "h2d_bytes_per_step": h2d_all,
                     "d2h_bytes_per_step": d2h_all,
-                    "api": "workload.run_step on pinned host buffers (H2D inputs, all witnesses D2H) per rank"},
+                    "api": "h2svd_zkmatrix_mul_witness (C ABI, pinned host buffers in/out, slab-pipelined D2H) per rank"},
             "gpu_launches": int(gpu_launches) * world, "clocks": clocks, "wall_s_timed_region": t_wall,
-            "verified": "Freivalds diff == 0 on the timed buffers",
+            "verified": "Freivalds diff == 0; fused host call and device building blocks byte-identical",
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_sample(n, 1, mm_rows=64, rs_elems=65536)
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": cb["sample"] + f" ({cb['t_sample_s']:.1f} s of CPU work, 1 thread: "
                                                              "the reference is single-threaded)"}
+    h_side.close()
     h.close()
     if world > 1:
         dist.barrier()

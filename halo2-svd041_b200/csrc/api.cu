@@ -406,6 +406,105 @@ int h2svd_rescale_witness(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count, int
     return check_flag(ctx, "rescale_witness");
 }
 
+/* ---- fused, slab-pipelined sequence ---- */
+int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t rows,
+                               size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
+                               size_t bv_row0, size_t bv_row1, h2svd_fr* c_s, h2svd_fr* q, h2svd_fr* wit,
+                               h2svd_fr* powers, h2svd_fr* prefix_cv, h2svd_fr* prefix_bv, h2svd_fr* prefix_abv,
+                               h2svd_fr* diff, h2svd_fr* is_zero, h2svd_fr* inv) {
+    REQUIRE(ctx && a && b && gamma && c_s && q && wit && powers && prefix_cv && prefix_abv && diff && is_zero && inv,
+            "zkmatrix_mul_witness: null argument");
+    REQUIRE(rows >= 1 && k >= 1 && m >= 1, "zkmatrix_mul_witness: empty matrix");
+    REQUIRE(bv_row0 <= bv_row1 && bv_row1 <= k, "zkmatrix_mul_witness: bad prefix_bv row range");
+    REQUIRE(bv_row0 == bv_row1 || prefix_bv, "zkmatrix_mul_witness: null prefix_bv");
+    const int W = rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr);
+    REQUIRE(W > 0, "zkmatrix_mul_witness: rescale parameters out of range");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    const size_t F = sizeof(Fr);
+    // slab height: ~96 MB of rescale witnesses per slab (two slab buffers are in flight)
+    size_t slab = ((size_t)96 << 20) / (m * (size_t)W * F);
+    if (slab < 1) slab = 1;
+    if (slab > rows) slab = rows;
+    const size_t need = Carver::need(rows * k * F) + Carver::need(k * m * F) + 3 * Carver::need(rows * m * F) +
+                        Carver::need(F) + Carver::need(m * F) + Carver::need(k * m * F) + Carver::need(rows * k * F) +
+                        Carver::need(k * F) + 5 * Carver::need(rows * F) + 2 * Carver::need(slab * m * (size_t)W * F);
+    H2SVD_TRY(ws_reserve(ctx, need));
+    Carver cv(ctx->ws);
+    Fr* da = cv.take<Fr>(rows * k);
+    Fr* db = cv.take<Fr>(k * m);
+    Fr* dc = cv.take<Fr>(rows * m);
+    Fr* dq = cv.take<Fr>(rows * m);
+    Fr* dpcv = cv.take<Fr>(rows * m);
+    Fr* dg = cv.take<Fr>(1);
+    Fr* dpow = cv.take<Fr>(m);
+    Fr* dpbv = cv.take<Fr>(k * m);
+    Fr* dpabv = cv.take<Fr>(rows * k);
+    Fr* dbv = cv.take<Fr>(k);
+    Fr* dcsv = cv.take<Fr>(rows);
+    Fr* dabv = cv.take<Fr>(rows);
+    Fr* ddiff = cv.take<Fr>(rows);
+    Fr* dz = cv.take<Fr>(rows);
+    Fr* dinv = cv.take<Fr>(rows);
+    Fr* dw[2] = {cv.take<Fr>(slab * m * (size_t)W), cv.take<Fr>(slab * m * (size_t)W)};
+    cudaStream_t cs = ctx->stream, xs = ctx->copy_stream;
+    auto to_host = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (bytes) H2SVD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, xs));
+        return H2SVD_OK;
+    };
+    // inputs: B and gamma first (the C-independent half of verify_mul starts at once), then A
+    H2SVD_TRY(h2d(ctx, db, b, k * m * F));
+    H2SVD_TRY(h2d(ctx, dg, gamma, F));
+    H2SVD_TRY(launch_check_canonical(ctx, db, k * m, ctx->d_flag));
+    H2SVD_TRY(launch_check_canonical(ctx, dg, 1, ctx->d_flag));
+    H2SVD_TRY(launch_gamma_powers(ctx, dg, m, dpow));                               // :316-326
+    H2SVD_TRY(launch_mat_vec_prefix(ctx, db, dpow, k, m, 0, dpbv, dbv));            // :336
+    H2SVD_CUDA(cudaEventRecord(ctx->ev[0], cs));
+    H2SVD_TRY(h2d(ctx, da, a, rows * k * F));
+    H2SVD_TRY(launch_check_canonical(ctx, da, rows * k, ctx->d_flag));
+    H2SVD_CUDA(cudaStreamWaitEvent(xs, ctx->ev[0], 0));
+    H2SVD_TRY(to_host(powers, dpow, m * F));
+    H2SVD_TRY(to_host(prefix_bv, dpbv + bv_row0 * m, (bv_row1 - bv_row0) * m * F));
+    // the copy stream must not start overwriting dw[] users... nothing pending yet; make the reuse events signalled
+    H2SVD_CUDA(cudaEventRecord(ctx->ev[2], xs));
+    H2SVD_CUDA(cudaEventRecord(ctx->ev[3], xs));
+    int buf = 0;
+    for (size_t r0 = 0; r0 < rows; r0 += slab, buf ^= 1) {
+        const size_t nr = rows - r0 < slab ? rows - r0 : slab;
+        H2SVD_TRY(launch_fr_matmul(ctx, da + r0 * k, db, dc + r0 * m, nr, k, m));                       // :546
+        H2SVD_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2 + buf], 0));  // slab buffer `buf` drained two slabs ago
+        H2SVD_TRY(launch_rescale(ctx, dc + r0 * m, nr * m, precision_bits, lookup_bits, shift_bits, a_num_bits,
+                                 dq + r0 * m, dw[buf]));                                                 // :354
+        H2SVD_TRY(launch_mat_vec_prefix(ctx, dc + r0 * m, dpow, nr, m, 0, dpcv + r0 * m, dcsv + r0));    // :335
+        H2SVD_TRY(launch_mat_vec_prefix(ctx, da + r0 * k, dbv, nr, k, 0, dpabv + r0 * k, dabv + r0));    // :337
+        H2SVD_TRY(launch_is_equal(ctx, dcsv + r0, dabv + r0, nr, ddiff + r0, dz + r0, dinv + r0));       // :339-341
+        H2SVD_CUDA(cudaEventRecord(ctx->ev[buf], cs));
+        H2SVD_CUDA(cudaStreamWaitEvent(xs, ctx->ev[buf], 0));
+        H2SVD_TRY(to_host(as_fr(wit) + r0 * m * (size_t)W, dw[buf], nr * m * (size_t)W * F));
+        H2SVD_CUDA(cudaEventRecord(ctx->ev[2 + buf], xs));
+        H2SVD_TRY(to_host(as_fr(c_s) + r0 * m, dc + r0 * m, nr * m * F));
+        H2SVD_TRY(to_host(as_fr(q) + r0 * m, dq + r0 * m, nr * m * F));
+        H2SVD_TRY(to_host(as_fr(prefix_cv) + r0 * m, dpcv + r0 * m, nr * m * F));
+        H2SVD_TRY(to_host(as_fr(prefix_abv) + r0 * k, dpabv + r0 * k, nr * k * F));
+    }
+    H2SVD_CUDA(cudaEventRecord(ctx->ev[0], cs));
+    H2SVD_CUDA(cudaStreamWaitEvent(xs, ctx->ev[0], 0));
+    H2SVD_TRY(to_host(diff, ddiff, rows * F));
+    H2SVD_TRY(to_host(is_zero, dz, rows * F));
+    H2SVD_TRY(to_host(inv, dinv, rows * F));
+    H2SVD_CUDA(cudaStreamSynchronize(xs));
+    return check_flag(ctx, "zkmatrix_mul_witness");
+}
+
+int h2svd_host_alloc(size_t bytes, void** out) {
+    REQUIRE(out != nullptr, "host_alloc: out is null");
+    *out = nullptr;
+    H2SVD_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return H2SVD_OK;
+}
+void h2svd_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 /* ---- K5/K6 ---- */
 int h2svd_zkvec_inner_prefix_dev(h2svd_ctx* ctx, const h2svd_fr* x, const h2svd_fr* self, size_t batch,
                                  size_t len, h2svd_fr* out_prefix) {

@@ -21,6 +21,28 @@ def _np_fr(*shape) -> np.ndarray:
     return np.empty(shape + (4,), dtype=np.uint64)
 
 
+class PinnedBuffer:
+    """Page-locked host memory from h2svd_host_alloc, viewed as a numpy array (freed with the object)."""
+
+    def __init__(self, shape, dtype=np.uint64) -> None:
+        self._lib = _ffi.load()
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = ct.c_void_p()
+        _ffi.check(self._lib.h2svd_host_alloc(nbytes, ct.byref(p)))
+        self._ptr = p
+        buf = (ct.c_ubyte * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            if self._ptr:
+                self.array = None
+                self._lib.h2svd_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
 def _np_ptr(a: np.ndarray) -> ct.c_void_p:
     if a.dtype != np.uint64 and a.dtype != np.float64:
         raise TypeError(f"expected uint64/float64 array, got {a.dtype}")
@@ -132,6 +154,32 @@ class Handle:
                                                   lookup_bits, shift_bits, a_num_bits, _np_ptr(q),
                                                   _np_ptr(wit)))
         return q.reshape(c_s.shape), wit
+
+    def zkmatrix_mul_witness(self, a: np.ndarray, b: np.ndarray, gamma: np.ndarray, precision_bits: int,
+                             lookup_bits: int, shift_bits: int = -1, a_num_bits: int = -1,
+                             bv_rows: Optional[tuple] = None, out: Optional[dict] = None) -> dict:
+        """honest_prover_mat_mul -> rescale_matrix -> verify_mul for the rows of `a` in ONE slab-pipelined call
+        (h2svd_zkmatrix_mul_witness).  `out` may hold preallocated (e.g. pinned) arrays under the result keys."""
+        rows, k = _fr_shape(a, 2)
+        k2, m = _fr_shape(b, 2)
+        if k != k2:
+            raise ValueError("zkmatrix_mul_witness: inner dimensions differ")
+        W = self.rescale_witness_count(precision_bits, lookup_bits, shift_bits, a_num_bits)
+        r0, r1 = bv_rows if bv_rows is not None else (0, k)
+        shapes = dict(c_s=(rows, m), q=(rows, m), wit=(rows * m, W), powers=(m,), prefix_cv=(rows, m),
+                      prefix_bv=(r1 - r0, m), prefix_abv=(rows, k), diff=(rows,), is_zero=(rows,), inv=(rows,))
+        res = {}
+        for key, shp in shapes.items():
+            arr = out[key] if out is not None and key in out else _np_fr(*shp)
+            if tuple(arr.shape) != shp + (4,):
+                raise ValueError(f"zkmatrix_mul_witness: out[{key!r}] has shape {arr.shape}, expected {shp + (4,)}")
+            res[key] = arr
+        g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
+        _ffi.check(self._lib.h2svd_zkmatrix_mul_witness(
+            self._h, _np_ptr(a), _np_ptr(b), _np_ptr(g), rows, k, m, precision_bits, lookup_bits, shift_bits,
+            a_num_bits, r0, r1, *[_np_ptr(res[key]) for key in ("c_s", "q", "wit", "powers", "prefix_cv", "prefix_bv",
+                                                                "prefix_abv", "diff", "is_zero", "inv")]))
+        return res
 
     def zkvec_inner_prefix(self, x: np.ndarray, self_: np.ndarray) -> np.ndarray:
         batch, ln = _fr_shape(x, 2)

@@ -134,6 +134,30 @@ int h2svd_rescale_witness_dev(h2svd_ctx *ctx, const h2svd_fr *c_s, size_t count,
                               int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
                               h2svd_fr *out_q, h2svd_fr *out_wit);
 
+/* ---- the whole README.md:34-47 sequence in one pipelined call -----------------------------------------------------
+ * honest_prover_mat_mul (src/matrix/mod.rs:546) -> rescale_matrix (:354) -> verify_mul (:299) for the caller's `rows`
+ * rows of A (all of A on one GPU; a row slab when the job is sharded over several handles/GPUs) against all of B.
+ * Host pointers in, host pointers out; internally the rows are processed in slabs so that the device-to-host copy of
+ * slab s (the rescale witnesses dominate: rows*m*W*32 bytes) overlaps the kernels of slab s+1 -- the call is bound by
+ * the PCIe transfer of its outputs, not by the sum of transfer and compute.  Use h2svd_host_alloc'ed (pinned) buffers
+ * for full bandwidth; pageable memory works but is staged by the driver.
+ *   c_s[rows*m]              the unscaled product (the Witness cells of honest_prover_mat_mul)
+ *   q[rows*m], wit[rows*m*W] as h2svd_rescale_witness
+ *   powers[m], prefix_cv[rows*m], prefix_abv[rows*k], diff/is_zero/inv[rows]   as h2svd_freivalds_witness
+ *   prefix_bv[(bv_row1-bv_row0)*m]  running sums of rows [bv_row0, bv_row1) of b . v (pass 0, k for all of them; a
+ *                                   sharded caller asks each handle for a different range -- no exchange needed,
+ *                                   every handle computes the k row totals of b . v itself) */
+int h2svd_zkmatrix_mul_witness(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, const h2svd_fr *gamma,
+                               size_t rows, size_t k, size_t m, int precision_bits, int lookup_bits,
+                               int shift_bits, int a_num_bits, size_t bv_row0, size_t bv_row1, h2svd_fr *c_s,
+                               h2svd_fr *q, h2svd_fr *wit, h2svd_fr *powers, h2svd_fr *prefix_cv,
+                               h2svd_fr *prefix_bv, h2svd_fr *prefix_abv, h2svd_fr *diff, h2svd_fr *is_zero,
+                               h2svd_fr *inv);
+
+/* Pinned (page-locked) host memory for the host-pointer entry points. */
+int h2svd_host_alloc(size_t bytes, void **out);
+void h2svd_host_free(void *p);
+
 /* ---- K5/K6: ZkVector witnesses -------------------------------------------------------------------------
  * h2svd_zkvec_inner_prefix: running sums of gate.inner_product(u = x, v = self) for `batch`
  *   independent vector pairs (ZkVector::inner_product, src/matrix/mod.rs:79-100; _norm_square :111

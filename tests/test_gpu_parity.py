@@ -300,3 +300,27 @@ def test_dev_entry_points_with_torch_tensors(handle):
     handle.fr_matmul_dev(ta, tb, tc)
     handle.sync()
     assert handle.launch_count == before + 1
+
+
+# ---------------------------------------------------------------- fused, slab-pipelined sequence
+@pytest.mark.parametrize("rows,k,m,P,bv", [(8, 8, 8, 42, None), (37, 20, 45, 63, (3, 11)), (300, 64, 700, 32, None)])
+def test_zkmatrix_mul_witness_fused_matches_oracle(handle, pkg, rows, k, m, P, bv):
+    """h2svd_zkmatrix_mul_witness (mat-mul -> rescale -> verify_mul, slabs pipelined against the D2H copies,
+    pinned output buffers) returns exactly what the three separate oracle functions return."""
+    lb = 19
+    rng = np.random.default_rng(rows + k)
+    a, b = quantized_matrix(rng, rows, k, P), quantized_matrix(rng, k, m, P)
+    gamma = random_fr(rng, 1)
+    W = handle.rescale_witness_count(P, lb)
+    pinned = pkg.PinnedBuffer((rows * m, W, 4))          # the big one in page-locked memory
+    res = handle.zkmatrix_mul_witness(a, b, gamma, P, lb, bv_rows=bv, out={"wit": pinned.array})
+    c = corac.field_mat_mul(a, b)
+    assert _eq(res["c_s"], c)
+    eq, _, ewit = corac.rescale_witness(c.reshape(-1, 4), P, lb)
+    assert _eq(res["q"].reshape(-1, 4), eq) and _eq(res["wit"], ewit)
+    fw = corac.freivalds_witness(a, b, c, gamma)
+    r0, r1 = bv if bv is not None else (0, k)
+    assert _eq(res["prefix_bv"], fw["prefix_bv"][r0:r1])
+    for key in ("powers", "prefix_cv", "prefix_abv", "diff", "is_zero", "inv"):
+        assert _eq(res[key], fw[key]), key
+    assert not res["diff"].any()

@@ -14,6 +14,8 @@ def rand_fr(*shape):
     t[..., 3] &= (1 << 60) - 1
     return t
 shapes = [(1024, 1024, 1024), (512, 1024, 1024), (256, 1024, 1024), (128, 1024, 1024), (256, 256, 256), (512, 2048, 4096)]
+if os.environ.get("SHAPES"):
+    shapes = [tuple(int(x) for x in sh.split("x")) for sh in os.environ["SHAPES"].split(",")]
 variants = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0]
 for (n, k, m) in shapes:
     a, b = rand_fr(n, k), rand_fr(k, m)
