@@ -89,6 +89,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def traffic_from_profile(kernel: str, n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (same command, same N)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)[kernel]
+        return t["dram_bytes_read"] + t["dram_bytes_write"] if t.get("n") == n else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peaks() -> dict:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -186,9 +196,6 @@ def run_gpu(args) -> None:
     side_stream = torch.cuda.Stream(device=device)
     h_side = pkg.Handle(local_rank, side_stream.cuda_stream)
     side = wl.SideStream(torch, h_side, side_stream, stream)
-    # Measured: under a full-size mat-mul (2 CTAs/SM hold the whole register file) the side kernels only
-    # displace mat-mul CTAs (+0.13 ms at 1 GPU); under the small slabs of 4-8 GPUs they fill idle SM time.
-    overlap = (r1 - r0) * m < 512 * 1024
 
     n = k = m = args.n
     plan = wl.ShardPlan(n, k, m, world, rank)
@@ -196,6 +203,9 @@ def run_gpu(args) -> None:
     bufs = wl.alloc_buffers(torch, plan, W, device)
     r0, r1 = plan.rows
     b0, b1 = plan.brows
+    # Measured: under a full-size mat-mul (2 CTAs/SM hold the whole register file) the side kernels only
+    # displace mat-mul CTAs (+0.13 ms at 1 GPU); under the small slabs of 4-8 GPUs they fill idle SM time.
+    overlap = (r1 - r0) * m < 512 * 1024
 
     # ---- synthetic inputs: f64 matrices -> pinned host -> GPU quantization kernel (product path)
     a_f, b_f, gamma = make_inputs(n, k, m)
@@ -344,7 +354,8 @@ def run_gpu(args) -> None:
                          "imad_wide_chain_peak": wide_peak / 1e12,
                          "frac_of_wide_chain_peak": (rows * k * m * 64.0 / (ms_mm * 1e-3)) / wide_peak,
                          "algorithmic": "128 IMAD slots per Fr mul-add = 64 IMAD.WIDE.U32 (half rate)",
-                         "traffic": None},
+                         "traffic": traffic_from_profile("fr_matmul_kernel", n) if world == 1 else None,
+                         "traffic_source": "profiles/traffic.json (ncu --set full capture of this command, bytes per launch)"},
             "roofline_hbm": {
                 "rescale": {"bound": "hbm", "achieved": rs_bytes / (ms_rs * 1e-3) / 1e9, "peak": hbm_peak,
                             "unit": "GB/s", "frac": rs_bytes / (ms_rs * 1e-3) / 1e9 / hbm_peak},
