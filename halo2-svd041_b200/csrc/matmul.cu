@@ -256,6 +256,8 @@ __device__ __noinline__ int sk_segment(int i) {
     const int kc0 = (sh->u0 + i) % sh->nchunks;
     const int cnt = min(sh->nchunks - kc0, sh->nloc - i);
     int s = 0;
+    const Fr* pA0 = sA + (threadIdx.x / TX) * BK;   // hoisted: fewer live temporaries in the unit loop
+    const Fr* pB0 = sB + (threadIdx.x % TX);
     for (int c = 0; c < cnt; c++, i++) {
         if (threadIdx.x < 32 && i + PD < sh->nloc) {
             if (i >= 2) mbar_wait(&sh->empty_bar[(i - 2) % STAGES], ((i - 2) / STAGES) & 1);
@@ -263,8 +265,8 @@ __device__ __noinline__ int sk_segment(int i) {
         }
         s = i % STAGES;
         mbar_wait(&sh->full_bar[s], (i / STAGES) & 1);
-        const Fr* pA = sA + s * cfg::A_STAGE + (threadIdx.x / TX) * BK;
-        const Fr* pB = sB + s * cfg::B_STAGE + (threadIdx.x % TX);
+        const Fr* pA = pA0 + s * cfg::A_STAGE;
+        const Fr* pB = pB0 + s * cfg::B_STAGE;
         const int klen = sh->meta[s].x;
 #pragma unroll 1
         for (int kk = 0; kk < klen; kk++) {
