@@ -25,7 +25,9 @@ namespace fr {
 FR_HD uint32_t lo32(uint64_t x) { return (uint32_t)x; }
 FR_HD uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
 
-// d[0..3] += {a0,a1,a2,a3} * b  (one carry chain over four 64-bit columns);  d[4] += carry out
+// d[0..3] += {a0,a1,a2,a3} * b  (one carry chain over four 64-bit columns);  d[4] += carry out.
+// PRECONDITION: d[4] < 2^32 - 1 (it only ever collects carries in the callers below), so the carry is added to
+// its low word alone.
 FR_HD void row4(uint64_t* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
 #if defined(__CUDA_ARCH__)
     asm("{\n\t"
@@ -43,8 +45,7 @@ FR_HD void row4(uint64_t* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
         "madc.hi.cc.u32  h2, %7, %9, h2;\n\t"
         "madc.lo.cc.u32  l3, %8, %9, l3;\n\t"
         "madc.hi.cc.u32  h3, %8, %9, h3;\n\t"
-        "addc.cc.u32     l4, l4, 0;\n\t"
-        "addc.u32        h4, h4, 0;\n\t"
+        "addc.u32        l4, l4, 0;\n\t"
         "mov.b64 %0, {l0, h0};\n\t"
         "mov.b64 %1, {l1, h1};\n\t"
         "mov.b64 %2, {l2, h2};\n\t"
@@ -91,8 +92,7 @@ FR_HD void row4_fold(uint64_t* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_
         "madc.hi.cc.u32  h2, %7, %9, h2;\n\t"
         "madc.lo.cc.u32  l3, %8, %9, l3;\n\t"
         "madc.hi.cc.u32  h3, %8, %9, h3;\n\t"
-        "addc.cc.u32     l4, l4, 0;\n\t"
-        "addc.u32        h4, h4, 0;\n\t"
+        "addc.u32        l4, l4, 0;\n\t"
         "mov.b64 %0, {l0, h0};\n\t"
         "mov.b64 %1, {l1, h1};\n\t"
         "mov.b64 %2, {l2, h2};\n\t"

@@ -152,6 +152,112 @@ mat_vec_prefix_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Consecutive-element version of the same computation for rows of >= 128 elements (the BASELINE shapes):
+// ONE WARP PER ROW, the row walked in 128-element tiles, each lane owning FOUR CONSECUTIVE elements of the tile.
+// The strided mapping of the kernel above needs a 5-level warp-shuffle scan per element (5 field adds + 40
+// shuffles); with consecutive elements the running sum is one field add per element, one shuffle scan covers
+// 128 elements, and a second, coalesced pass adds each lane's offset: ~300 instead of ~580 instructions per
+// element, leaving the 132 IMAD.WIDE of the Montgomery product (which every canonical running sum needs) as
+// the bound.  Warps never synchronise with each other (no __syncthreads, no flags): the 24 resident warps of an
+// SM sit in different phases (loading / multiplying / scanning / storing), which keeps the multiplier pipe fed.
+//  * each warp stages its a / v tiles with cp.async (16-byte LDGSTS, coalesced on the global side) into its
+//    own 128-byte-XOR-swizzled buffers (16-byte chunk q lives at q ^ ((q >> 3) & 7)): the lane-consecutive
+//    reads of pass 1, the stores of the un-offset sums and the coalesced reads of pass 2 are conflict-free.
+//  * the un-offset running sums overwrite the a tile; pass 2 adds the owner lane's offset and stores straight
+//    to global in element order.
+constexpr int MT_WARPS = 4;                      // warps per CTA (a container only: warps are independent)
+constexpr int MT_EPL = 4;                        // consecutive elements per lane
+constexpr int MT_SEG = 32 * MT_EPL;              // 128 elements (4 KB) per tile
+constexpr int MT_SEG_U4 = MT_SEG * 2;            // 16-byte chunks per tile buffer
+constexpr int MT_WARP_U4 = 2 * MT_SEG_U4 + 64;   // a tile + v tile + 32 lane offsets
+constexpr size_t MT_SMEM = (size_t)MT_WARPS * MT_WARP_U4 * sizeof(uint4);   // 36 KB -> 6 CTAs = 24 warps per SM
+
+__device__ __forceinline__ int mt_swz(int q) { return q ^ ((q >> 3) & 7); }
+__device__ __forceinline__ Fr mt_ld(const uint4* buf, int e) {
+    const uint4 lo = buf[mt_swz(2 * e)], hi = buf[mt_swz(2 * e + 1)];
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+__device__ __forceinline__ void mt_st(uint4* buf, int e, const Fr& v) {
+    buf[mt_swz(2 * e)] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    buf[mt_swz(2 * e + 1)] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// one warp stages `count` (<= MT_SEG) elements of src into a swizzled tile buffer
+__device__ __forceinline__ void mt_stage(uint4* buf, const Fr* src, int count, int lane) {
+    const uint4* g = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int r = 0; r < 2 * MT_EPL; r++) {
+        const int q = lane + 32 * r;
+        if (q < 2 * count) {
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(buf + mt_swz(q)));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + q) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MT_WARPS * 32, 6)
+mat_vec_prefix_tile_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len,
+                           size_t v_row_stride) {
+    extern __shared__ __align__(128) uint4 mt_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint4* sa = mt_smem + (size_t)w * MT_WARP_U4;
+    uint4* sv = sa + MT_SEG_U4;
+    Fr* soff = reinterpret_cast<Fr*>(sv + MT_SEG_U4);
+    size_t total_rows = 0;
+#pragma unroll
+    for (int q = 0; q < MV_MAX_JOBS; q++) total_rows += q < jobs.njobs ? jobs.job[q].rows : 0;
+    const size_t warps_total = (size_t)gridDim.x * MT_WARPS;
+
+    for (size_t grow = (size_t)blockIdx.x * MT_WARPS + w; grow < total_rows; grow += warps_total) {
+        size_t row = grow;
+        int jq = 0;
+        if (jobs.njobs > 1 && row >= jobs.job[0].rows) {
+            row -= jobs.job[0].rows;
+            jq = 1;
+        }
+        const Fr* a = jobs.job[jq].a + row * len;
+        Fr* out = jobs.job[jq].out + row * len;
+        const Fr* vr = v + row * v_row_stride;
+        Fr carry = fr::zero();  // sum of the complete tiles of this row
+        for (size_t t0 = 0; t0 < len; t0 += MT_SEG) {
+            const int nseg = (int)(len - t0 < (size_t)MT_SEG ? len - t0 : (size_t)MT_SEG);
+            mt_stage(sa, a + t0, nseg, lane);
+            mt_stage(sv, vr + t0, nseg, lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            // pass 1: products and un-offset running sums of this lane's four consecutive elements
+            Fr run = fr::zero();
+#pragma unroll
+            for (int i = 0; i < MT_EPL; i++) {
+                const int e = MT_EPL * lane + i;
+                if (e < nseg) {
+                    run = fr::add_fast(run, fr::mont_mul_fast(mt_ld(sa, e), mt_ld(sv, e)));
+                    mt_st(sa, e, run);
+                }
+            }
+            const Fr incl = warp_scan_fr<32>(run, lane);
+            Fr off = shfl_up_fr(incl, 1);  // exclusive over the lanes
+            if (lane == 0) off = fr::zero();
+            off = fr::add_fast(off, carry);
+            carry = fr::add_fast(carry, shfl_fr(incl, 31));
+            st_fr(&soff[lane], off);
+            __syncwarp();
+            // pass 2: coalesced -- element e gets the offset of its owner lane e / MT_EPL
+#pragma unroll
+            for (int r = 0; r < MT_EPL; r++) {
+                const int e = lane + 32 * r;
+                if (e < nseg) st_fr_cs(out + t0 + e, fr::add_fast(mt_ld(sa, e), ld_fr(&soff[e / MT_EPL])));
+            }
+            __syncwarp();  // the buffers are restaged by the next tile
+        }
+        if (lane == 0 && jobs.job[jq].totals) st_fr(jobs.job[jq].totals + row, carry);
+    }
+}
+
 __global__ void gather_kernel(const Fr* __restrict__ src, Fr* __restrict__ out, size_t count, size_t stride,
                               size_t offset) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,6 +311,8 @@ int launch_gamma_powers(h2svd_ctx* ctx, const Fr* gamma, size_t d, Fr* out) {
     return H2SVD_OK;
 }
 
+static int g_mv_force_warp = 0;  // triage hook: 1 = always use the warp-per-segment kernel
+
 template <int WPR>
 static int launch_mv(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, const Fr* v, size_t len, size_t vs) {
     constexpr int RPC = MV_WARPS / WPR;
@@ -220,6 +328,22 @@ static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_
     size_t total_rows = 0;
     for (int q = 0; q < jobs.njobs; q++) total_rows += jobs.job[q].rows;
     if (total_rows == 0 || len == 0) return H2SVD_OK;
+    if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && g_mv_force_warp == 0) {
+        // one warp per row, consecutive elements per lane (mat_vec_prefix_tile_kernel); needs enough rows to
+        // give every SM a few warps, otherwise the row-splitting kernel below is the better fit
+        static bool configured = false;
+        if (!configured) {
+            H2SVD_CUDA(cudaFuncSetAttribute(mat_vec_prefix_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)MT_SMEM));
+            configured = true;
+        }
+        size_t blocks = (total_rows + MT_WARPS - 1) / MT_WARPS;
+        const size_t cap = (size_t)ctx->sm_count * 6;  // 6 CTAs of 4 independent warps per SM, grid-stride beyond
+        if (blocks > cap) blocks = cap;
+        mat_vec_prefix_tile_kernel<<<(unsigned)blocks, MT_WARPS * 32, MT_SMEM, ctx->stream>>>(jobs, v, len, vs);
+        H2SVD_LAUNCH_CHECK(ctx);
+        return H2SVD_OK;
+    }
     // warps per row: enough to cover the row with 128-element segments, and enough to fill the GPU
     int wpr = 1;
     while (wpr < MV_WARPS && (size_t)wpr * 128 < len) wpr <<= 1;
@@ -264,3 +388,8 @@ int launch_is_equal(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, Fr* 
 }
 
 }  // namespace h2svd
+
+extern "C" int h2svd_debug_set_matvec_warp_kernel(int v) {
+    h2svd::g_mv_force_warp = v;
+    return 0;
+}

@@ -302,6 +302,11 @@ def set_rescale_generic(v: bool) -> None:
     _ffi.load().h2svd_debug_set_rescale_generic(int(v))
 
 
+def set_matvec_warp_kernel(v: bool) -> None:
+    """Triage hook: force the warp-per-segment mat-vec prefix kernel instead of the tile kernel."""
+    _ffi.load().h2svd_debug_set_matvec_warp_kernel(int(v))
+
+
 def set_matmul_streamk(v: int) -> None:
     """Triage hook: -1 auto (default), 0 never, 1 always use the stream-K mat-mul schedule."""
     _ffi.load().h2svd_debug_set_matmul_streamk(v)
