@@ -50,6 +50,14 @@ SIGNATURES = {
     "h2svd_host_fr_mul": (None, [_P, _P, _P]),
     "h2svd_gather_dev": (_I, [_P, _P, _Z, _Z, _Z, _P]),
     "h2svd_is_equal_witness_dev": (_I, [_P, _P, _P, _Z, _P, _P, _P]),
+    "h2svd_abs_less_than_witness_count": (_I, [_P, _I, _I]),
+    "h2svd_abs_less_than_witness": (_I, [_P, _P, _P, _Z, _P, _I, _P]),
+    "h2svd_abs_less_than_witness_dev": (_I, [_P, _P, _P, _Z, _P, _I, _P]),
+    "h2svd_range_check_witness_count": (_I, [_I, _I]),
+    "h2svd_range_check_witness": (_I, [_P, _P, _Z, _I, _I, _P]),
+    "h2svd_range_check_witness_dev": (_I, [_P, _P, _Z, _I, _I, _P]),
+    "h2svd_mat_times_diag": (_I, [_P, _P, _P, _Z, _Z, _Z, _P]),
+    "h2svd_mat_times_diag_dev": (_I, [_P, _P, _P, _Z, _Z, _Z, _P]),
     "h2svd_zkmatrix_mul_witness": (_I, [_P, _P, _P, _P, _Z, _Z, _Z, _I, _I, _I, _I, _Z, _Z] + [_P] * 10),
     "h2svd_host_alloc": (_I, [_Z, ct.POINTER(_P)]),
     "h2svd_host_free": (None, [_P]),

@@ -406,6 +406,107 @@ int h2svd_rescale_witness(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count, int
     return check_flag(ctx, "rescale_witness");
 }
 
+/* ---- range-check witnesses of the SVD verifier's helpers ---- */
+static Fr fr_from_u64(const uint64_t* x) {
+    Fr f;
+    for (int i = 0; i < 4; i++) {
+        f.l[2 * i] = (uint32_t)x[i];
+        f.l[2 * i + 1] = (uint32_t)(x[i] >> 32);
+    }
+    return f;
+}
+int h2svd_abs_less_than_witness_count(const uint64_t bnd[4], int lookup_bits, int with_diff) {
+    REQUIRE(bnd != nullptr, "abs_less_than_witness_count: null bound");
+    const int w = abs_less_than_params(fr_from_u64(bnd), lookup_bits, with_diff, nullptr, nullptr);
+    REQUIRE(w > 0, "abs_less_than_witness_count: parameters out of range");
+    return w;
+}
+int h2svd_abs_less_than_witness_dev(h2svd_ctx* ctx, const h2svd_fr* x, const h2svd_fr* y, size_t count,
+                                    const uint64_t bnd[4], int lookup_bits, h2svd_fr* out_wit) {
+    REQUIRE(ctx && x && bnd && out_wit, "abs_less_than_witness: null argument");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_abs_less_than(ctx, as_fr(x), y ? as_fr(y) : nullptr, count, fr_from_u64(bnd), lookup_bits, as_fr(out_wit));
+}
+int h2svd_abs_less_than_witness(h2svd_ctx* ctx, const h2svd_fr* x, const h2svd_fr* y, size_t count,
+                                const uint64_t bnd[4], int lookup_bits, h2svd_fr* out_wit) {
+    REQUIRE(ctx && x && bnd && out_wit, "abs_less_than_witness: null argument");
+    const int W = abs_less_than_params(fr_from_u64(bnd), lookup_bits, y != nullptr, nullptr, nullptr);
+    REQUIRE(W > 0, "abs_less_than_witness: parameters out of range");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    if (count == 0) return H2SVD_OK;
+    const size_t F = sizeof(Fr);
+    H2SVD_TRY(ws_reserve(ctx, 2 * Carver::need(count * F) + Carver::need(count * (size_t)W * F)));
+    Carver cv(ctx->ws);
+    Fr* dx = cv.take<Fr>(count);
+    Fr* dy = cv.take<Fr>(count);
+    Fr* dw = cv.take<Fr>(count * (size_t)W);
+    H2SVD_TRY(h2d(ctx, dx, x, count * F));
+    H2SVD_TRY(launch_check_canonical(ctx, dx, count, ctx->d_flag));
+    if (y) {
+        H2SVD_TRY(h2d(ctx, dy, y, count * F));
+        H2SVD_TRY(launch_check_canonical(ctx, dy, count, ctx->d_flag));
+    }
+    H2SVD_TRY(launch_abs_less_than(ctx, dx, y ? dy : nullptr, count, fr_from_u64(bnd), lookup_bits, dw));
+    H2SVD_TRY(d2h(ctx, out_wit, dw, count * (size_t)W * F));
+    return check_flag(ctx, "abs_less_than_witness");
+}
+int h2svd_range_check_witness_count(int range_bits, int lookup_bits) {
+    const int w = range_check_params(range_bits, lookup_bits, nullptr, nullptr);
+    REQUIRE(w >= 0, "range_check_witness_count: parameters out of range");
+    return w;
+}
+int h2svd_range_check_witness_dev(h2svd_ctx* ctx, const h2svd_fr* x, size_t count, int range_bits, int lookup_bits,
+                                  h2svd_fr* out_wit) {
+    REQUIRE(ctx && x && out_wit, "range_check_witness: null argument");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_range_check(ctx, as_fr(x), count, range_bits, lookup_bits, as_fr(out_wit));
+}
+int h2svd_range_check_witness(h2svd_ctx* ctx, const h2svd_fr* x, size_t count, int range_bits, int lookup_bits,
+                              h2svd_fr* out_wit) {
+    REQUIRE(ctx && x && out_wit, "range_check_witness: null argument");
+    const int W = range_check_params(range_bits, lookup_bits, nullptr, nullptr);
+    REQUIRE(W >= 0, "range_check_witness: parameters out of range");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    if (count == 0 || W == 0) return H2SVD_OK;
+    const size_t F = sizeof(Fr);
+    H2SVD_TRY(ws_reserve(ctx, Carver::need(count * F) + Carver::need(count * (size_t)W * F)));
+    Carver cv(ctx->ws);
+    Fr* dx = cv.take<Fr>(count);
+    Fr* dw = cv.take<Fr>(count * (size_t)W);
+    H2SVD_TRY(h2d(ctx, dx, x, count * F));
+    H2SVD_TRY(launch_check_canonical(ctx, dx, count, ctx->d_flag));
+    H2SVD_TRY(launch_range_check(ctx, dx, count, range_bits, lookup_bits, dw));
+    H2SVD_TRY(d2h(ctx, out_wit, dw, count * (size_t)W * F));
+    return check_flag(ctx, "range_check_witness");
+}
+int h2svd_mat_times_diag_dev(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* v, size_t rows, size_t lda,
+                             size_t cols_v, h2svd_fr* out) {
+    REQUIRE(ctx && a && v && out, "mat_times_diag: null argument");
+    REQUIRE(cols_v <= lda, "mat_times_diag: v.len() <= a[0].len()");  // reference :616
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_mat_times_diag(ctx, as_fr(a), as_fr(v), rows, lda, cols_v, as_fr(out));
+}
+int h2svd_mat_times_diag(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* v, size_t rows, size_t lda, size_t cols_v,
+                         h2svd_fr* out) {
+    REQUIRE(ctx && a && v && out, "mat_times_diag: null argument");
+    REQUIRE(cols_v <= lda, "mat_times_diag: v.len() <= a[0].len()");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    if (rows == 0 || cols_v == 0) return H2SVD_OK;
+    const size_t F = sizeof(Fr);
+    H2SVD_TRY(ws_reserve(ctx, Carver::need(rows * lda * F) + Carver::need(cols_v * F) + Carver::need(rows * cols_v * F)));
+    Carver cv(ctx->ws);
+    Fr* da = cv.take<Fr>(rows * lda);
+    Fr* dv = cv.take<Fr>(cols_v);
+    Fr* dout = cv.take<Fr>(rows * cols_v);
+    H2SVD_TRY(h2d(ctx, da, a, rows * lda * F));
+    H2SVD_TRY(h2d(ctx, dv, v, cols_v * F));
+    H2SVD_TRY(launch_check_canonical(ctx, da, rows * lda, ctx->d_flag));
+    H2SVD_TRY(launch_check_canonical(ctx, dv, cols_v, ctx->d_flag));
+    H2SVD_TRY(launch_mat_times_diag(ctx, da, dv, rows, lda, cols_v, dout));
+    H2SVD_TRY(d2h(ctx, out, dout, rows * cols_v * F));
+    return check_flag(ctx, "mat_times_diag");
+}
+
 /* ---- fused, slab-pipelined sequence ---- */
 int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t rows,
                                size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
@@ -604,14 +705,6 @@ int h2svd_check_canonical_dev(h2svd_ctx* ctx, const h2svd_fr* x, size_t count) {
 }
 
 /* ---- host-side scalar helpers (fr.cuh is host-callable) ---- */
-static Fr fr_from_u64(const uint64_t* x) {
-    Fr f;
-    for (int i = 0; i < 4; i++) {
-        f.l[2 * i] = (uint32_t)x[i];
-        f.l[2 * i + 1] = (uint32_t)(x[i] >> 32);
-    }
-    return f;
-}
 static void fr_to_u64(const Fr& f, uint64_t* x) {
     for (int i = 0; i < 4; i++) x[i] = (uint64_t)f.l[2 * i] | ((uint64_t)f.l[2 * i + 1] << 32);
 }

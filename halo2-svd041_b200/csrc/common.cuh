@@ -102,6 +102,11 @@ int launch_is_equal(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, Fr* 
                     Fr* inv);
 int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, int S, int A, Fr* out_q,
                    Fr* out_wit);
+int abs_less_than_params(const Fr& bnd, int lb, int with_diff, int* n_out, Fr* bound_out);
+int launch_abs_less_than(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, const Fr& bnd, int lb, Fr* out_wit);
+int range_check_params(int range_bits, int lb, int* n_out, int* rem_out);
+int launch_range_check(h2svd_ctx* ctx, const Fr* x, size_t count, int range_bits, int lb, Fr* out_wit);
+int launch_mat_times_diag(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t lda, size_t cols_v, Fr* out);
 int launch_sub(h2svd_ctx* ctx, const Fr* a, const Fr* b, size_t count, Fr* out);
 int launch_isqrt(h2svd_ctx* ctx, const Fr* a, size_t count, int P, Fr* out);
 int launch_quantize(h2svd_ctx* ctx, const double* x, size_t count, int P, Fr* out);

@@ -198,7 +198,7 @@ __device__ __forceinline__ void mt_stage(uint4* buf, const Fr* src, int count, i
     }
 }
 
-__global__ void __launch_bounds__(MT_WARPS * 32, 6)
+__global__ void __launch_bounds__(MT_WARPS * 32)
 mat_vec_prefix_tile_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len,
                            size_t v_row_stride) {
     extern __shared__ __align__(128) uint4 mt_smem[];
@@ -338,7 +338,7 @@ static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_
             configured = true;
         }
         size_t blocks = (total_rows + MT_WARPS - 1) / MT_WARPS;
-        const size_t cap = (size_t)ctx->sm_count * 6;  // 6 CTAs of 4 independent warps per SM, grid-stride beyond
+        const size_t cap = (size_t)ctx->sm_count * 5;  // 5 CTAs (96 regs) of 4 independent warps per SM, grid-stride beyond
         if (blocks > cap) blocks = cap;
         mat_vec_prefix_tile_kernel<<<(unsigned)blocks, MT_WARPS * 32, MT_SMEM, ctx->stream>>>(jobs, v, len, vs);
         H2SVD_LAUNCH_CHECK(ctx);

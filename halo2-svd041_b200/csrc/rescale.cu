@@ -38,12 +38,31 @@ struct RescaleParams {
 };
 
 // Host-precomputed constants of one (P, lb, S, A) configuration, passed by value (constant bank).
+// limb-decomposition constants shared by every range-check style kernel
+struct LimbConsts {
+    int lb;
+    uint32_t lb_mask;
+    Fr c[MAX_POS];  // c[i] = 2^(lb*i) * 2^288 mod r
+};
 struct RescaleConsts {
     RescaleParams p;
-    uint32_t lb_mask;
     Fr i_2S, i_pow_d, i_bound_d, i_pow_r, i_bound_r;   // canonical integers
     Fr m_2S, m_2SP, m_pow_d, m_bound_d, m_pow_r, m_bound_r;  // Montgomery forms
-    Fr c[MAX_POS];  // c[i] = 2^(lb*i) * 2^288 mod r
+    LimbConsts lc;
+};
+// check_abs_less_than / check_mat_diff (reference src/matrix/mod.rs:425-459)
+struct AbsLtConsts {
+    int n, W, with_diff;
+    Fr m_add;                                // M(bnd - 1)
+    Fr i_pow, i_bound, m_pow, m_bound;       // 2^(n*lb), 2*bnd - 1
+    LimbConsts lc;
+};
+// RangeChip::range_check(x, range_bits)
+struct RangeConsts {
+    int n, rem, W;
+    Fr c_shift;                              // 2^(lb - rem) * 2^288 mod r (rem > 1)
+    Fr m_shift;                              // M(2^(lb - rem))
+    LimbConsts lc;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -163,12 +182,12 @@ __device__ __forceinline__ Fr shr_small(const Fr& y, int s) {  // 1 <= s <= 32
 }
 
 // RangeChip::range_check(x, n*lb): limbs l_i and running sums s_i = x mod 2^(lb*(i+1)), Montgomery form
-__device__ __forceinline__ void stream_range_check(WitnessStream& ws, const RescaleConsts& k, Fr y, int n) {
+__device__ __forceinline__ void stream_range_check(WitnessStream& ws, const LimbConsts& k, Fr y, int n) {
     if (n == 1) return;
     Fr sum;
     for (int i = 0; i < n; i++) {
         const uint32_t l = y.l[0] & k.lb_mask;
-        y = shr_small(y, k.p.lb);
+        y = shr_small(y, k.lb);
         const Fr ml = fr::mont_mul_small(l, k.c[0]);
         ws.put(ml);
         if (i == 0) {
@@ -181,7 +200,7 @@ __device__ __forceinline__ void stream_range_check(WitnessStream& ws, const Resc
 }
 
 // RangeChip::check_big_less_than_safe(x, B)
-__device__ __forceinline__ void stream_cbls(WitnessStream& ws, const RescaleConsts& k, const Fr& x_int,
+__device__ __forceinline__ void stream_cbls(WitnessStream& ws, const LimbConsts& k, const Fr& x_int,
                                             const Fr& x_mont, int n, const Fr& i_pow, const Fr& i_bound,
                                             const Fr& m_pow, const Fr& m_bound) {
     stream_range_check(ws, k, x_int, n);
@@ -221,8 +240,8 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
         ws.put(fr::add_fast(am, k.m_2S));
         ws.put(m_rem);
         ws.put(m_div);
-        stream_cbls(ws, k, div, m_div, k.p.n_d, k.i_pow_d, k.i_bound_d, k.m_pow_d, k.m_bound_d);
-        stream_cbls(ws, k, rem, m_rem, k.p.n_r, k.i_pow_r, k.i_bound_r, k.m_pow_r, k.m_bound_r);
+        stream_cbls(ws, k.lc, div, m_div, k.p.n_d, k.i_pow_d, k.i_bound_d, k.m_pow_d, k.m_bound_d);
+        stream_cbls(ws, k.lc, rem, m_rem, k.p.n_r, k.i_pow_r, k.i_bound_r, k.m_pow_r, k.m_bound_r);
         const Fr q = fr::sub_fast(m_div, k.m_2SP);              // gate.sub(div, Constant(2^(S-P)))
         ws.put(q);
         ws.flush();
@@ -230,6 +249,84 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
     }
     // shared memory must outlive every bulk read, and the writes must be complete at kernel end
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// check_abs_less_than(x, bnd) (reference src/matrix/mod.rs:425-437), optionally of a difference x - y
+// (check_mat_diff :441-459): witnesses [x - y]?, t = d + (bnd - 1), check_big_less_than_safe(t, 2*bnd - 1).
+__global__ void __launch_bounds__(RS_THREADS)
+abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __restrict__ out_wit, size_t count,
+                     const __grid_constant__ AbsLtConsts k) {
+    extern __shared__ __align__(16) uint4 rs_stage[];
+    const int lane = threadIdx.x & 31;
+    WitnessStream ws;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * 2 * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * 2 * RS_ROW_U4;
+    ws.W = k.W;
+    ws.buf = 0;
+    ws.fill = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < count; e0 += stride) {
+        const size_t left = count - e0;
+        ws.valid = left < 32 ? (int)left : 32;
+        ws.gwarp = out_wit + e0 * (size_t)k.W;
+        const size_t e = lane < ws.valid ? e0 + lane : count - 1;
+        Fr dm = ldg_fr(x + e);
+        if (k.with_diff) {
+            dm = fr::sub_fast(dm, ldg_fr(y + e));   // gate.sub(a, b) -> Witness(a - b)
+            ws.put(dm);
+        }
+        const Fr tm = fr::add_fast(dm, k.m_add);     // gate.add(x, Constant(bnd - 1))
+        ws.put(tm);
+        stream_cbls(ws, k.lc, fr::from_mont_fast(tm), tm, k.n, k.i_pow, k.i_bound, k.m_pow, k.m_bound);
+        ws.flush();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// RangeChip::range_check(x, range_bits) with n = ceil(range_bits / lb) limbs: limbs + running sums (none when
+// n == 1), plus last_limb * 2^(lb - rem) when range_bits % lb = rem > 1 (ZkVector::entries_less_than, :185-197).
+__global__ void __launch_bounds__(RS_THREADS)
+range_check_kernel(const Fr* __restrict__ x, Fr* __restrict__ out_wit, size_t count, const __grid_constant__ RangeConsts k) {
+    extern __shared__ __align__(16) uint4 rs_stage[];
+    const int lane = threadIdx.x & 31;
+    WitnessStream ws;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * 2 * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * 2 * RS_ROW_U4;
+    ws.W = k.W;
+    ws.buf = 0;
+    ws.fill = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < count; e0 += stride) {
+        const size_t left = count - e0;
+        ws.valid = left < 32 ? (int)left : 32;
+        ws.gwarp = out_wit + e0 * (size_t)k.W;
+        const size_t e = lane < ws.valid ? e0 + lane : count - 1;
+        const Fr xm = ldg_fr(x + e);
+        const Fr xi = fr::from_mont_fast(xm);
+        stream_range_check(ws, k.lc, xi, k.n);
+        if (k.rem > 1) {
+            if (k.n == 1) {
+                ws.put(fr::mont_mul_fast(xm, k.m_shift));   // gate.mul(x, 2^(lb-rem)): x is the only "limb", at full width
+            } else {
+                Fr t = xi;                                   // last limb: bits [lb*(n-1), lb*n) of x
+                for (int i = 0; i < k.n - 1; i++) t = shr_small(t, k.lc.lb);
+                ws.put(fr::mont_mul_small(t.l[0] & k.lc.lb_mask, k.c_shift));
+            }
+        }
+        ws.flush();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// mat_times_diag_mat (reference :610-627): out[i][j] = a[i][j] * v[j], j < cols_v <= lda
+__global__ void mat_times_diag_kernel(const Fr* __restrict__ a, const Fr* __restrict__ v, Fr* __restrict__ out, size_t rows,
+                                      size_t lda, size_t cols_v) {
+    const size_t total = rows * cols_v;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const size_t i = idx / cols_v, j = idx - i * cols_v;
+        st_fr(out + idx, fr::mont_mul_fast(ldg_fr(a + i * lda + j), ldg_fr(v + j)));
+    }
 }
 
 }  // namespace
@@ -248,6 +345,19 @@ int rescale_params(int P, int lb, int S, int A, int* n_d, int* n_r) {
 }
 
 static int g_force_generic = 0;
+
+static void fill_limb_consts(LimbConsts& lc, int lb, int npos) {
+    lc.lb = lb;
+    lc.lb_mask = lb == 32 ? 0xffffffffu : ((1u << lb) - 1u);
+    const Fr m_2_32 = fr::to_mont(fr::pow2(32));
+    for (int i = 0; i < MAX_POS; i++)
+        lc.c[i] = i < npos ? fr::mont_mul(fr::to_mont(fr::pow2(lb * i)), m_2_32) : fr::zero();
+}
+static int bit_length(const Fr& x) {
+    for (int i = 7; i >= 0; i--)
+        if (x.l[i]) return 32 * i + (32 - __builtin_clz(x.l[i]));
+    return 0;
+}
 
 int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, int S, int A, Fr* out_q,
                    Fr* out_wit) {
@@ -269,7 +379,7 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     // constants of this configuration (fr.cuh is host-callable)
     RescaleConsts k;
     k.p = p;
-    k.lb_mask = lb == 32 ? 0xffffffffu : ((1u << lb) - 1u);
+    fill_limb_consts(k.lc, lb, p.n_d > p.n_r ? p.n_d : p.n_r);
     k.i_2S = fr::pow2(S);
     k.i_pow_d = fr::pow2(p.n_d * lb);
     k.i_bound_d = fr::pow2(A - P);
@@ -282,11 +392,6 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     k.m_bound_d = fr::to_mont(k.i_bound_d);
     k.m_pow_r = fr::to_mont(k.i_pow_r);
     k.m_bound_r = fr::to_mont(k.i_bound_r);
-    const Fr m_2_32 = fr::to_mont(fr::pow2(32));
-    const int npos = p.n_d > p.n_r ? p.n_d : p.n_r;
-    for (int i = 0; i < MAX_POS; i++)
-        k.c[i] = i < npos ? fr::mont_mul(fr::to_mont(fr::pow2(lb * i)), m_2_32) : fr::zero();
-
     static bool configured = false;
     if (!configured) {
         H2SVD_CUDA(cudaFuncSetAttribute(rescale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
@@ -296,6 +401,98 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     const size_t cap = (size_t)ctx->sm_count * 3;  // 3 CTAs (69.6 KB of staging each) per SM, grid-stride beyond
     if (blocks > cap) blocks = cap;
     rescale_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
+    H2SVD_LAUNCH_CHECK(ctx);
+    return H2SVD_OK;
+}
+
+// W of check_abs_less_than for bound `bnd` (canonical integer): [diff] + t + cbls(2*bnd - 1)
+int abs_less_than_params(const Fr& bnd, int lb, int with_diff, int* n_out, Fr* bound_out) {
+    if (lb < 1 || lb > 32 || fr::is_zero(bnd) || bit_length(bnd) > 250) return -1;
+    Fr two_bnd, one = fr::zero();
+    one.l[0] = 1u;
+    fr::add_n<8>(two_bnd.l, bnd.l, bnd.l);
+    Fr bound;
+    fr::sub_n<8>(bound.l, two_bnd.l, one.l);  // 2*bnd - 1
+    const int n = ceil_div(bit_length(bound), lb);
+    if (n * lb > 253 || n > MAX_POS) return -1;
+    if (n_out) *n_out = n;
+    if (bound_out) *bound_out = bound;
+    return (with_diff ? 1 : 0) + 1 + 2 + (n >= 2 ? 2 * (2 * n - 1) : 0);
+}
+
+int launch_abs_less_than(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, const Fr& bnd, int lb, Fr* out_wit) {
+    AbsLtConsts k;
+    Fr bound;
+    k.with_diff = y != nullptr;
+    k.W = abs_less_than_params(bnd, lb, k.with_diff, &k.n, &bound);
+    if (k.W < 0) {
+        set_error("abs_less_than: parameters out of range");
+        return H2SVD_EINVAL;
+    }
+    if (count == 0) return H2SVD_OK;
+    fill_limb_consts(k.lc, lb, k.n);
+    Fr one = fr::zero();
+    one.l[0] = 1u;
+    Fr bm1;
+    fr::sub_n<8>(bm1.l, bnd.l, one.l);
+    k.m_add = fr::to_mont(bm1);
+    k.i_pow = fr::pow2(k.n * lb);
+    k.i_bound = bound;
+    k.m_pow = fr::to_mont(k.i_pow);
+    k.m_bound = fr::to_mont(bound);
+    static bool configured = false;
+    if (!configured) {
+        H2SVD_CUDA(cudaFuncSetAttribute(abs_less_than_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+        configured = true;
+    }
+    size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
+    const size_t cap = (size_t)ctx->sm_count * 3;
+    if (blocks > cap) blocks = cap;
+    abs_less_than_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, y, out_wit, count, k);
+    H2SVD_LAUNCH_CHECK(ctx);
+    return H2SVD_OK;
+}
+
+int range_check_params(int range_bits, int lb, int* n_out, int* rem_out) {
+    if (lb < 1 || lb > 32 || range_bits < 1 || range_bits > 253) return -1;
+    const int n = ceil_div(range_bits, lb), rem = range_bits % lb;
+    if (n > MAX_POS) return -1;
+    if (n_out) *n_out = n;
+    if (rem_out) *rem_out = rem;
+    return (n >= 2 ? 2 * n - 1 : 0) + (rem > 1 ? 1 : 0);
+}
+
+int launch_range_check(h2svd_ctx* ctx, const Fr* x, size_t count, int range_bits, int lb, Fr* out_wit) {
+    RangeConsts k;
+    k.W = range_check_params(range_bits, lb, &k.n, &k.rem);
+    if (k.W < 0) {
+        set_error("range_check: parameters out of range");
+        return H2SVD_EINVAL;
+    }
+    if (count == 0 || k.W == 0) return H2SVD_OK;
+    fill_limb_consts(k.lc, lb, k.n);
+    k.m_shift = k.rem > 1 ? fr::to_mont(fr::pow2(lb - k.rem)) : fr::zero();
+    k.c_shift = k.rem > 1 ? fr::mont_mul(k.m_shift, fr::to_mont(fr::pow2(32))) : fr::zero();
+    static bool configured = false;
+    if (!configured) {
+        H2SVD_CUDA(cudaFuncSetAttribute(range_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+        configured = true;
+    }
+    size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
+    const size_t cap = (size_t)ctx->sm_count * 3;
+    if (blocks > cap) blocks = cap;
+    range_check_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, out_wit, count, k);
+    H2SVD_LAUNCH_CHECK(ctx);
+    return H2SVD_OK;
+}
+
+int launch_mat_times_diag(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t lda, size_t cols_v, Fr* out) {
+    if (rows == 0 || cols_v == 0) return H2SVD_OK;
+    const size_t total = rows * cols_v;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    mat_times_diag_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, v, out, rows, lda, cols_v);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }

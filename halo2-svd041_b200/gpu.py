@@ -155,6 +155,44 @@ class Handle:
                                                   _np_ptr(wit)))
         return q.reshape(c_s.shape), wit
 
+    @staticmethod
+    def _bnd_limbs(bnd: int) -> np.ndarray:
+        return np.array([(bnd >> (64 * i)) & ((1 << 64) - 1) for i in range(4)], dtype=np.uint64)
+
+    def abs_less_than_witness(self, x: np.ndarray, bnd: int, lookup_bits: int,
+                              y: Optional[np.ndarray] = None) -> np.ndarray:
+        """check_abs_less_than(x [- y], bnd) witnesses (reference src/matrix/mod.rs:425-459)."""
+        xf = np.ascontiguousarray(x).reshape(-1, 4)
+        yf = np.ascontiguousarray(y).reshape(-1, 4) if y is not None else None
+        if yf is not None and yf.shape != xf.shape:
+            raise ValueError("abs_less_than_witness: shape mismatch")   # reference :448-449
+        b = self._bnd_limbs(bnd)
+        W = self._lib.h2svd_abs_less_than_witness_count(_np_ptr(b), lookup_bits, int(y is not None))
+        if W < 0:
+            _ffi.check(W)
+        out = _np_fr(xf.shape[0], W)
+        _ffi.check(self._lib.h2svd_abs_less_than_witness(self._h, _np_ptr(xf), _np_ptr(yf) if yf is not None else
+                                                        ct.c_void_p(0), xf.shape[0], _np_ptr(b), lookup_bits, _np_ptr(out)))
+        return out
+
+    def range_check_witness(self, x: np.ndarray, range_bits: int, lookup_bits: int) -> np.ndarray:
+        xf = np.ascontiguousarray(x).reshape(-1, 4)
+        W = self._lib.h2svd_range_check_witness_count(range_bits, lookup_bits)
+        if W < 0:
+            _ffi.check(W)
+        out = _np_fr(xf.shape[0], W)
+        if W:
+            _ffi.check(self._lib.h2svd_range_check_witness(self._h, _np_ptr(xf), xf.shape[0], range_bits, lookup_bits,
+                                                          _np_ptr(out)))
+        return out
+
+    def mat_times_diag(self, a: np.ndarray, v: np.ndarray) -> np.ndarray:
+        rows, lda = _fr_shape(a, 2)
+        (cols_v,) = _fr_shape(v, 1)
+        out = _np_fr(rows, cols_v)
+        _ffi.check(self._lib.h2svd_mat_times_diag(self._h, _np_ptr(a), _np_ptr(v), rows, lda, cols_v, _np_ptr(out)))
+        return out
+
     def zkmatrix_mul_witness(self, a: np.ndarray, b: np.ndarray, gamma: np.ndarray, precision_bits: int,
                              lookup_bits: int, shift_bits: int = -1, a_num_bits: int = -1,
                              bv_rows: Optional[tuple] = None, out: Optional[dict] = None) -> dict:

@@ -134,6 +134,32 @@ int h2svd_rescale_witness_dev(h2svd_ctx *ctx, const h2svd_fr *c_s, size_t count,
                               int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
                               h2svd_fr *out_q, h2svd_fr *out_wit);
 
+/* ---- range-check witnesses of the SVD verifier's helpers ---------------------------------------------
+ * h2svd_abs_less_than_witness: check_abs_less_than (src/matrix/mod.rs:425-437) for `count` elements, optionally of a
+ *   difference (check_mat_diff :441-459, check_mat_id :461-483; pass y = NULL for check_mat_entries_bounded :490-501):
+ *     d = x - y                                  gate.sub, 1 Witness            (only when y != NULL)
+ *     t = d + (bnd - 1)                          gate.add, 1 Witness
+ *     check_big_less_than_safe(t, 2*bnd - 1)     range_check(t) | chk, xp | range_check(chk)   
+ *   `bnd` is the canonical integer bound, 4 x u64 little-endian.  out_wit[count * W], W from the _count function.
+ * h2svd_range_check_witness: RangeChip::range_check(x, range_bits) (ZkVector::entries_less_than :185-197,
+ *   entries_in_desc_order :199-216): n = ceil(range_bits/lookup_bits) limbs and n-1 running sums (l0, l1, s1, l2, s2, ...;
+ *   none when n == 1), then last_limb * 2^(lookup_bits - rem) when range_bits % lookup_bits = rem > 1.  W may be 0.
+ * h2svd_mat_times_diag: mat_times_diag_mat (:610-627): out[i*cols_v + j] = a[i*lda + j] * v[j] (the gate.mul Witness). */
+int h2svd_abs_less_than_witness_count(const uint64_t bnd[4], int lookup_bits, int with_diff);
+int h2svd_abs_less_than_witness(h2svd_ctx *ctx, const h2svd_fr *x, const h2svd_fr *y, size_t count,
+                                const uint64_t bnd[4], int lookup_bits, h2svd_fr *out_wit);
+int h2svd_abs_less_than_witness_dev(h2svd_ctx *ctx, const h2svd_fr *x, const h2svd_fr *y, size_t count,
+                                    const uint64_t bnd[4], int lookup_bits, h2svd_fr *out_wit);
+int h2svd_range_check_witness_count(int range_bits, int lookup_bits);
+int h2svd_range_check_witness(h2svd_ctx *ctx, const h2svd_fr *x, size_t count, int range_bits, int lookup_bits,
+                              h2svd_fr *out_wit);
+int h2svd_range_check_witness_dev(h2svd_ctx *ctx, const h2svd_fr *x, size_t count, int range_bits,
+                                  int lookup_bits, h2svd_fr *out_wit);
+int h2svd_mat_times_diag(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, size_t rows, size_t lda,
+                         size_t cols_v, h2svd_fr *out);
+int h2svd_mat_times_diag_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, size_t rows, size_t lda,
+                             size_t cols_v, h2svd_fr *out);
+
 /* ---- the whole README.md:34-47 sequence in one pipelined call -----------------------------------------------------
  * honest_prover_mat_mul (src/matrix/mod.rs:546) -> rescale_matrix (:354) -> verify_mul (:299) for the caller's `rows`
  * rows of A (all of A on one GPU; a row slab when the job is sharded over several handles/GPUs) against all of B.

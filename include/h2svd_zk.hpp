@@ -259,6 +259,32 @@ class RangeChip {
         for (int i = 0; i < n - 1; i++) ctx.lookups.push_back(row + 1 + 3 * i);
         return 2 * n - 1;
     }
+    // range_check(a, range_bits) for any width (halo2-base RangeChip::range_check): n = ceil(range_bits/lb) limbs;
+    // when range_bits % lb = rem: rem == 1 -> assert_bit-style gate on the last limb, rem > 1 -> the last limb
+    // times 2^(lb-rem) (one more witness) is looked up too.  Returns the number of witness values consumed.
+    int range_check_bits(Context& ctx, const AssignedValue& a, int range_bits, const Fr* wit) const {
+        const int n = (range_bits + lookup_bits - 1) / lookup_bits, rem = range_bits % lookup_bits;
+        int used = 0;
+        AssignedValue last = a;
+        if (n == 1) {
+            ctx.lookups.push_back(a.index);
+        } else {
+            const size_t row = gate.limb_inner_product(ctx, wit, n, lookup_bits);
+            ctx.constrain_equal(a, ctx.get(-1));
+            ctx.lookups.push_back(row);
+            for (int i = 0; i < n - 1; i++) ctx.lookups.push_back(row + 1 + 3 * i);
+            last = ctx.get((ptrdiff_t)(row + 1 + 3 * (n - 2)));
+            used = 2 * n - 1;
+        }
+        if (rem == 1) {
+            ctx.assign_region({Constant(field::zero()), Existing(last), Existing(last), Existing(last)}, {0});
+        } else if (rem > 1) {
+            const AssignedValue chk = gate.mul(ctx, Existing(last), Constant(field::pow2(lookup_bits - rem)), wit[used]);
+            ctx.lookups.push_back(chk.index);
+            used++;
+        }
+        return used;
+    }
     // check_big_less_than_safe(a, bound) with n = ceil(bound.bits()/lb):
     //   wit = range_check(a) | chk, xp | range_check(chk)        (4n values, 4 when n == 1 -> just chk, xp)
     int check_big_less_than_safe(Context& ctx, const AssignedValue& a, const Fr& bound, int n, const Fr* wit) const {
@@ -469,6 +495,37 @@ class ZkVector {
     // mul (:169-182): y_i = inner_product(row_i) for every row of a -- two bulk calls for all rows,
     // cells emitted per row in the reference's order (inner product, then its signed_div_scale)
     ZkVector mul(Context& ctx, const Chip& fpchip, const ZkMatrix<PRECISION_BITS>& a) const;
+    // entries_less_than (:185-197): range_check(elem, max_bits) for every entry (one bulk call)
+    void entries_less_than(Context& ctx, const Chip& fpchip, size_t max_bits) const {
+        range_check_all(ctx, fpchip, v, max_bits);
+    }
+    // entries_in_desc_order (:199-216): all the qsub differences first, then their range checks
+    void entries_in_desc_order(Context& ctx, const Chip& fpchip, size_t max_bits) const {
+        if (v.size() < 2) return;
+        const size_t n = v.size() - 1;
+        const std::vector<Fr> fs = gather_values(v);
+        std::vector<Fr> d(n);
+        check(h2svd_zkvec_sub(fpchip.gpu().raw(), fs.data(), fs.data() + 1, n, d.data()), "entries_in_desc_order");
+        std::vector<AssignedValue> vec_diff;
+        for (size_t i = 0; i < n; i++) vec_diff.push_back(fpchip.gate().sub(ctx, Existing(v[i]), Existing(v[i + 1]), d[i]));
+        range_check_all(ctx, fpchip, vec_diff, max_bits);
+    }
+
+  private:
+    static void range_check_all(Context& ctx, const Chip& fpchip, const std::vector<AssignedValue>& xs, size_t max_bits) {
+        const int W = h2svd_range_check_witness_count((int)max_bits, fpchip.lookup_bits);
+        if (W < 0) throw std::logic_error(std::string("range_check: ") + h2svd_last_error());
+        const std::vector<Fr> fx = gather_values(xs);
+        std::vector<Fr> w(xs.size() * (size_t)W + 1);
+        if (W > 0 && !xs.empty())
+            check(h2svd_range_check_witness(fpchip.gpu().raw(), fx.data(), xs.size(), (int)max_bits, fpchip.lookup_bits,
+                                            w.data()),
+                  "range_check");
+        for (size_t i = 0; i < xs.size(); i++)
+            fpchip.range_gate().range_check_bits(ctx, xs[i], (int)max_bits, w.data() + i * (size_t)W);
+    }
+
+  public:
 };
 
 // ---- ZkMatrix (:219-420) ---------------------------------------------------------------------------------
@@ -583,6 +640,173 @@ ZkVector<PRECISION_BITS> ZkVector<PRECISION_BITS>::mul(Context& ctx, const Chip&
     }
     return y;
 }
+
+// ---- range-check helpers of src/matrix/mod.rs (:425-501, :610-627) ----------------------------------------------
+using BigUint = std::array<uint64_t, 4>;  // canonical integer, little-endian limbs (the reference passes &BigUint)
+inline BigUint biguint(unsigned __int128 x) { return BigUint{(uint64_t)x, (uint64_t)(x >> 64), 0, 0}; }
+inline Fr biguint_to_fe(const BigUint& x) {
+    Fr o;
+    check(h2svd_host_fr_from_canonical(x.data(), &o), "biguint_to_fe");
+    return o;
+}
+inline BigUint biguint_sub1(const BigUint& x) {
+    BigUint o = x;
+    for (int i = 0; i < 4; i++)
+        if (o[i]-- != 0) break;
+    return o;
+}
+inline BigUint biguint_2x_minus1(const BigUint& x) {
+    BigUint o;
+    uint64_t c = 0;
+    for (int i = 0; i < 4; i++) {
+        o[i] = (x[i] << 1) | c;
+        c = x[i] >> 63;
+    }
+    return biguint_sub1(o);
+}
+inline int biguint_bits(const BigUint& x) {
+    for (int i = 3; i >= 0; i--)
+        if (x[i]) return 64 * i + (64 - __builtin_clzll(x[i]));
+    return 0;
+}
+
+// Cells of ONE check_abs_less_than(x, bnd) (:425-437) given its GPU-produced witnesses w = t | cbls(t, 2*bnd-1).
+inline void assign_check_abs_less_than(Context& ctx, const RangeChip& range, const AssignedValue& x, const BigUint& bnd,
+                                       const Fr* w) {
+    const BigUint new_bnd = biguint_2x_minus1(bnd);
+    const int n = (biguint_bits(new_bnd) + range.lookup_bits - 1) / range.lookup_bits;
+    const AssignedValue translated_x = range.gate.add(ctx, Existing(x), Constant(biguint_to_fe(biguint_sub1(bnd))), w[0]);
+    range.check_big_less_than_safe(ctx, translated_x, biguint_to_fe(new_bnd), n, w + 1);
+}
+inline void check_abs_less_than(Context& ctx, const RangeChip& range, const AssignedValue& x, const BigUint& bnd) {
+    const int W = h2svd_abs_less_than_witness_count(bnd.data(), range.lookup_bits, 0);
+    if (W < 0) throw std::logic_error(std::string("check_abs_less_than: ") + h2svd_last_error());
+    std::vector<Fr> w((size_t)W);
+    check(h2svd_abs_less_than_witness(Gpu::current().raw(), &x.v, nullptr, 1, bnd.data(), range.lookup_bits, w.data()),
+          "check_abs_less_than");
+    assign_check_abs_less_than(ctx, range, x, bnd, w.data());
+}
+// check_mat_diff (:441-459): |a[i][j] - b[i][j]| < tol for every entry -- one bulk call, cells per entry in order
+inline void check_mat_diff(Context& ctx, const RangeChip& range, const AssignedMatrix& a, const AssignedMatrix& b,
+                           const BigUint& tol) {
+    require(a.size() == b.size(), "a.len() == b.len()");                             // :448
+    require(!a.empty() && a[0].size() == b[0].size(), "a[0].len() == b[0].len()");  // :449
+    const size_t rows = a.size(), cols = a[0].size();
+    const int W = h2svd_abs_less_than_witness_count(tol.data(), range.lookup_bits, 1);
+    if (W < 0) throw std::logic_error(std::string("check_mat_diff: ") + h2svd_last_error());
+    const std::vector<Fr> fa = gather_values(a), fb = gather_values(b);
+    std::vector<Fr> w(rows * cols * (size_t)W);
+    check(h2svd_abs_less_than_witness(Gpu::current().raw(), fa.data(), fb.data(), rows * cols, tol.data(),
+                                      range.lookup_bits, w.data()),
+          "check_mat_diff");
+    for (size_t i = 0; i < rows; i++)
+        for (size_t j = 0; j < cols; j++) {
+            const Fr* we = w.data() + (i * cols + j) * (size_t)W;
+            const AssignedValue diff = range.gate.sub(ctx, Existing(a[i][j]), Existing(b[i][j]), we[0]);  // :453
+            assign_check_abs_less_than(ctx, range, diff, tol, we + 1);                                    // :454
+        }
+}
+// check_mat_id (:461-483)
+inline void check_mat_id(Context& ctx, const RangeChip& range, const AssignedMatrix& a, const AssignedValue& scalar_id,
+                         const BigUint& tol) {
+    const AssignedValue zero = ctx.load_constant(field::zero());
+    AssignedMatrix b(a.size());
+    for (size_t i = 0; i < a.size(); i++)
+        for (size_t j = 0; j < a[0].size(); j++) b[i].push_back(i == j ? scalar_id : zero);
+    check_mat_diff(ctx, range, a, b, tol);
+}
+// check_mat_entries_bounded (:490-501)
+inline void check_mat_entries_bounded(Context& ctx, const RangeChip& range, const AssignedMatrix& a, const BigUint& bnd) {
+    if (a.empty()) return;
+    const size_t rows = a.size(), cols = a[0].size();
+    const int W = h2svd_abs_less_than_witness_count(bnd.data(), range.lookup_bits, 0);
+    if (W < 0) throw std::logic_error(std::string("check_mat_entries_bounded: ") + h2svd_last_error());
+    const std::vector<Fr> fa = gather_values(a);
+    std::vector<Fr> w(rows * cols * (size_t)W);
+    check(h2svd_abs_less_than_witness(Gpu::current().raw(), fa.data(), nullptr, rows * cols, bnd.data(),
+                                      range.lookup_bits, w.data()),
+          "check_mat_entries_bounded");
+    for (size_t i = 0; i < rows; i++)
+        for (size_t j = 0; j < cols; j++)
+            assign_check_abs_less_than(ctx, range, a[i][j], bnd, w.data() + (i * cols + j) * (size_t)W);
+}
+// mat_times_diag_mat (:610-627): a * [Diag(v) 0]^T, one gate.mul per entry
+inline AssignedMatrix mat_times_diag_mat(Context& ctx, const GateChip& gate, const AssignedMatrix& a,
+                                         const std::vector<AssignedValue>& v) {
+    require(!a.empty() && v.size() <= a[0].size(), "v.len() <= a[0].len()");  // :616
+    const size_t rows = a.size(), lda = a[0].size(), cols = v.size();
+    const std::vector<Fr> fa = gather_values(a), fv = gather_values(v);
+    std::vector<Fr> prod(rows * cols);
+    check(h2svd_mat_times_diag(Gpu::current().raw(), fa.data(), fv.data(), rows, lda, cols, prod.data()), "mat_times_diag_mat");
+    AssignedMatrix m(rows);
+    for (size_t i = 0; i < rows; i++)
+        for (size_t j = 0; j < cols; j++) m[i].push_back(gate.mul(ctx, Existing(a[i][j]), Existing(v[j]), prod[i * cols + j]));
+    return m;
+}
+
+// ---- the caller of the path: src/svd/mod.rs (check_svd_phase0 :32-116, check_svd_phase1 :127-144, err_calc :155-163) ----
+namespace svd {
+inline std::pair<double, double> err_calc(uint32_t p, size_t size, double max_norm, double eps_svd, double eps_u) {
+    const double precision = std::pow(2.0, -1.0 * ((double)p + 1.0));
+    const double err_svd = precision * (double)size * (1.0 + max_norm + eps_svd + precision) +
+                           (double)size * max_norm * precision + std::pow(1.0 + eps_u, 0.5) * (max_norm + eps_svd) * eps_u +
+                           std::pow(1.0 + eps_u, 0.5) * eps_svd;
+    const double err_u = eps_u + precision * (double)size * (2.0 * (1.0 + eps_u) + precision);
+    return {err_svd, err_u};
+}
+template <uint32_t P>
+struct Phase0Out {
+    ZkMatrix<P> u_t, v_t;
+    AssignedMatrix m_times_vt, u_times_ut, v_times_vt;
+};
+template <uint32_t P>
+Phase0Out<P> check_svd_phase0(Context& ctx, const FixedPointChip041<P>& fpchip, const ZkMatrix<P>& m, const ZkMatrix<P>& u,
+                              const ZkMatrix<P>& v, const ZkVector<P>& d, double err_svd, double err_u, uint32_t max_bits_d) {
+    require(m.num_rows == u.num_rows, "m.num_rows == u.num_rows");
+    require(m.num_col == v.num_rows, "m.num_col == v.num_rows");
+    const size_t N = m.num_rows, M = m.num_col, minNM = N < M ? N : M;
+    require(u.num_rows == u.num_col && v.num_rows == v.num_col, "unitaries are square");
+    require(minNM == d.v.size(), "min(N, M) == d.len()");
+    const RangeChip& range = fpchip.range_gate();
+    const GateChip& gate = fpchip.gate();
+    const size_t max_bits = (size_t)max_bits_d + P;
+    d.entries_less_than(ctx, fpchip, max_bits);
+    d.entries_in_desc_order(ctx, fpchip, max_bits);
+    const BigUint unit_bnd_q = biguint(((unsigned __int128)1 << P) + 1);
+    check_mat_entries_bounded(ctx, range, u.matrix, unit_bnd_q);
+    check_mat_entries_bounded(ctx, range, v.matrix, unit_bnd_q);
+    Phase0Out<P> out;
+    out.u_t = ZkMatrix<P>::transpose_matrix(u);
+    out.v_t = ZkMatrix<P>::transpose_matrix(v);
+    AssignedMatrix u_times_d;
+    if (minNM == M) {
+        u_times_d = mat_times_diag_mat(ctx, gate, u.matrix, d.v);
+    } else {
+        const AssignedValue zero = ctx.load_constant(field::zero());
+        u_times_d = mat_times_diag_mat(ctx, gate, u.matrix, d.v);
+        for (auto& row : u_times_d)
+            for (size_t j = N; j < M; j++) row.push_back(zero);
+    }
+    out.m_times_vt = honest_prover_mat_mul(ctx, m.matrix, out.v_t.matrix);
+    const double scale = std::ldexp(1.0, 2 * (int)P);
+    const BigUint err_svd_scale = biguint((unsigned __int128)std::round(err_svd * scale));
+    const BigUint err_u_scale = biguint((unsigned __int128)std::round(err_u * scale));
+    check_mat_diff(ctx, range, u_times_d, out.m_times_vt, err_svd_scale);
+    const AssignedValue quant_square = ctx.load_constant(field::pow2(2 * (int)P));
+    out.u_times_ut = honest_prover_mat_mul(ctx, u.matrix, out.u_t.matrix);
+    check_mat_id(ctx, range, out.u_times_ut, quant_square, err_u_scale);
+    out.v_times_vt = honest_prover_mat_mul(ctx, v.matrix, out.v_t.matrix);
+    check_mat_id(ctx, range, out.v_times_vt, quant_square, err_u_scale);
+    return out;
+}
+template <uint32_t P>
+void check_svd_phase1(Context& ctx, const FixedPointChip041<P>& fpchip, const ZkMatrix<P>& m, const ZkMatrix<P>& u,
+                      const ZkMatrix<P>& v, const Phase0Out<P>& p0, const AssignedValue& init_rand) {
+    ZkMatrix<P>::verify_mul(ctx, fpchip, m, p0.v_t, p0.m_times_vt, init_rand);
+    ZkMatrix<P>::verify_mul(ctx, fpchip, u, p0.u_t, p0.u_times_ut, init_rand);
+    ZkMatrix<P>::verify_mul(ctx, fpchip, v, p0.v_t, p0.v_times_vt, init_rand);
+}
+}  // namespace svd
 
 // ---- MockProver-style check of recorded contexts ------------------------------------------------------------
 // Gates a + b*c - d == 0 at every selected row, copy constraints, constants, lookups (< 2^lookup_bits).

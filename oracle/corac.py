@@ -40,6 +40,11 @@ def lib():
         L.orc_quantize.argtypes = [P, Z, I, P]
         L.orc_isqrt_fixed.argtypes = [P, Z, I, P]
         L.orc_freivalds_witness.argtypes = [P, P, P, P, Z, Z, Z, P, P, P, P, P, P, P, I]
+        L.orc_abs_less_than_witness_count.argtypes = [P, I, I]
+        L.orc_abs_less_than_witness.argtypes = [P, P, Z, P, I, P]
+        L.orc_range_check_witness_count.argtypes = [I, I]
+        L.orc_range_check_witness.argtypes = [P, Z, I, I, P]
+        L.orc_mat_times_diag.argtypes = [P, P, Z, Z, Z, P]
     return _LIB
 
 
@@ -133,4 +138,39 @@ def freivalds_witness(a: np.ndarray, b: np.ndarray, cs: np.ndarray, gamma: np.nd
                                      _p(out["prefix_cv"]), _p(out["prefix_bv"]),
                                      _p(out["prefix_abv"]), _p(out["diff"]), _p(out["is_zero"]),
                                      _p(out["inv"]), threads), "freivalds")
+    return out
+
+
+def _bnd(bnd: int) -> np.ndarray:
+    return np.array([(bnd >> (64 * i)) & ((1 << 64) - 1) for i in range(4)], dtype=np.uint64)
+
+
+def abs_less_than_witness(x: np.ndarray, bnd: int, lb: int, y: np.ndarray | None = None) -> np.ndarray:
+    xf = np.ascontiguousarray(x).reshape(-1, 4)
+    b = _bnd(bnd)
+    W = lib().orc_abs_less_than_witness_count(_p(b), lb, int(y is not None))
+    if W < 0:
+        raise ValueError("abs_less_than: parameters out of range")
+    out = _fr(xf.shape[0], W)
+    yf = np.ascontiguousarray(y).reshape(-1, 4) if y is not None else None
+    _chk(lib().orc_abs_less_than_witness(_p(xf), _p(yf) if yf is not None else None, xf.shape[0], _p(b), lb, _p(out)),
+         "abs_less_than_witness")
+    return out
+
+
+def range_check_witness(x: np.ndarray, range_bits: int, lb: int) -> np.ndarray:
+    xf = np.ascontiguousarray(x).reshape(-1, 4)
+    W = lib().orc_range_check_witness_count(range_bits, lb)
+    if W < 0:
+        raise ValueError("range_check: parameters out of range")
+    out = _fr(xf.shape[0], W)
+    if W:
+        _chk(lib().orc_range_check_witness(_p(xf), xf.shape[0], range_bits, lb, _p(out)), "range_check_witness")
+    return out
+
+
+def mat_times_diag(a: np.ndarray, v: np.ndarray) -> np.ndarray:
+    rows, lda = a.shape[0], a.shape[1]
+    out = _fr(rows, v.shape[0])
+    _chk(lib().orc_mat_times_diag(_p(a), _p(v), rows, lda, v.shape[0], _p(out)), "mat_times_diag")
     return out

@@ -339,6 +339,87 @@ int orc_rescale_witness(const orc_fr *cs, size_t count, int P, int lb, int S, in
     return 0;
 }
 
+/* ---- range-check witnesses of the SVD verifier's helpers (reference src/matrix/mod.rs:425-501, :185-216, :610-627) ---- */
+static int u256_bits(const uint64_t a[4]) {
+    for (int i = 3; i >= 0; i--)
+        if (a[i]) return 64 * i + (64 - __builtin_clzll(a[i]));
+    return 0;
+}
+int orc_abs_less_than_witness_count(const uint64_t bnd[4], int lb, int with_diff) {
+    uint64_t two[4], bound[4], one[4] = {1, 0, 0, 0};
+    if (lb < 1 || lb > 32 || u256_bits(bnd) == 0 || u256_bits(bnd) > 250) return -1;
+    u256_add(two, bnd, bnd);
+    u256_sub(bound, two, one);
+    int n = ceil_div(u256_bits(bound), lb);
+    if (n * lb > 253) return -1;
+    return (with_diff ? 1 : 0) + 1 + 2 + (n >= 2 ? 2 * (2 * n - 1) : 0);
+}
+/* check_abs_less_than(x [- y], bnd): [x - y]?, t = d + (bnd - 1), check_big_less_than_safe(t, 2*bnd - 1) */
+int orc_abs_less_than_witness(const orc_fr *x, const orc_fr *y, size_t count, const uint64_t bnd[4], int lb,
+                              orc_fr *out_wit) {
+    int W = orc_abs_less_than_witness_count(bnd, lb, y != NULL);
+    if (W < 0) return -1;
+    uint64_t two[4], bound[4], bm1[4], one[4] = {1, 0, 0, 0};
+    u256_add(two, bnd, bnd);
+    u256_sub(bound, two, one);
+    u256_sub(bm1, bnd, one);
+    for (size_t e = 0; e < count; e++) {
+        orc_fr *w = out_wit + e * (size_t)W;
+        uint64_t d[4], t[4];
+        orc_fr_to_canonical(d, &x[e]);
+        if (y) {
+            uint64_t yy[4];
+            orc_fr_to_canonical(yy, &y[e]);
+            int_sub_mod(d, d, yy);      /* gate.sub(a, b) */
+            w = emit(w, d);
+        }
+        int_add_mod(t, d, bm1);         /* gate.add(x, bnd - 1) */
+        w = emit(w, t);
+        w = emit_cbls(w, t, bound, u256_bits(bound), lb);
+    }
+    return 0;
+}
+int orc_range_check_witness_count(int range_bits, int lb) {
+    if (lb < 1 || lb > 32 || range_bits < 1 || range_bits > 253) return -1;
+    int n = ceil_div(range_bits, lb), rem = range_bits % lb;
+    return (n >= 2 ? 2 * n - 1 : 0) + (rem > 1 ? 1 : 0);
+}
+/* RangeChip::range_check(x, range_bits): limbs + running sums, then last_limb * 2^(lb - rem) when rem > 1 */
+int orc_range_check_witness(const orc_fr *x, size_t count, int range_bits, int lb, orc_fr *out_wit) {
+    int W = orc_range_check_witness_count(range_bits, lb);
+    if (W < 0) return -1;
+    int n = ceil_div(range_bits, lb), rem = range_bits % lb;
+    for (size_t e = 0; e < count; e++) {
+        orc_fr *w = out_wit + e * (size_t)W;
+        uint64_t v[4];
+        orc_fr_to_canonical(v, &x[e]);
+        w = emit_range_check(w, v, n, lb);
+        if (rem > 1) {
+            uint64_t last[4], p2[4];
+            orc_fr a, b;
+            if (n == 1) {
+                memcpy(last, v, sizeof last);
+            } else {
+                uint64_t t[4];
+                u256_shr(t, v, (unsigned)(lb * (n - 1)));
+                u256_low_bits(last, t, (unsigned)lb);
+            }
+            u256_pow2(p2, (unsigned)(lb - rem));
+            orc_fr_from_canonical(&a, last);
+            orc_fr_from_canonical(&b, p2);
+            orc_fr_mul(w, &a, &b);      /* gate.mul(last, 2^(lb - rem)) */
+        }
+    }
+    return 0;
+}
+/* mat_times_diag_mat: out[i*cols_v + j] = a[i*lda + j] * v[j] */
+int orc_mat_times_diag(const orc_fr *a, const orc_fr *v, size_t rows, size_t lda, size_t cols_v, orc_fr *out) {
+    if (cols_v > lda) return -1;
+    for (size_t i = 0; i < rows; i++)
+        for (size_t j = 0; j < cols_v; j++) orc_fr_mul(&out[i * cols_v + j], &a[i * lda + j], &v[j]);
+    return 0;
+}
+
 /* FixedPointChip041::quantization (SURVEY A.5 / PDF Eq. 11) */
 int orc_quantize(const double *x, size_t count, int P, orc_fr *out) {
     if (P < 1 || P > 63) return -1;

@@ -66,6 +66,19 @@ int orc_zkvec_inner_prefix(const orc_fr *x, const orc_fr *self, size_t batch, si
 /* reference src/matrix/mod.rs:143-146: diff[i] = self[i] - x[i] (qsub = gate.sub) */
 int orc_zkvec_sub(const orc_fr *self, const orc_fr *x, size_t count, orc_fr *out);
 
+/* reference src/matrix/mod.rs:425-459 check_abs_less_than / check_mat_diff witnesses:
+ * [x - y]? , t = d + (bnd - 1), check_big_less_than_safe(t, 2*bnd - 1); bnd = canonical integer */
+int orc_abs_less_than_witness_count(const uint64_t bnd[4], int lookup_bits, int with_diff);
+int orc_abs_less_than_witness(const orc_fr *x, const orc_fr *y, size_t count, const uint64_t bnd[4],
+                              int lookup_bits, orc_fr *out_wit);
+/* RangeChip::range_check(x, range_bits) witnesses (reference :185-216 callers) */
+int orc_range_check_witness_count(int range_bits, int lookup_bits);
+int orc_range_check_witness(const orc_fr *x, size_t count, int range_bits, int lookup_bits,
+                            orc_fr *out_wit);
+/* reference :610-627 mat_times_diag_mat values */
+int orc_mat_times_diag(const orc_fr *a, const orc_fr *v, size_t rows, size_t lda, size_t cols_v,
+                       orc_fr *out);
+
 /* FixedPointChip041::quantization: sign-magnitude round-half-up */
 int orc_quantize(const double *x, size_t count, int precision_bits, orc_fr *out);
 

@@ -46,6 +46,17 @@ int h2svd_isqrt_fixed(h2svd_ctx *c, const h2svd_fr *a, size_t count, int P, h2sv
 int h2svd_quantize(h2svd_ctx *c, const double *x, size_t count, int P, h2svd_fr *out) {
     (void)c; return rc(orc_quantize(x, count, P, O(out)), "quantize");
 }
+int h2svd_abs_less_than_witness_count(const uint64_t bnd[4], int lb, int with_diff) { return orc_abs_less_than_witness_count(bnd, lb, with_diff); }
+int h2svd_abs_less_than_witness(h2svd_ctx *c, const h2svd_fr *x, const h2svd_fr *y, size_t count, const uint64_t bnd[4], int lb, h2svd_fr *w) {
+    (void)c; return rc(orc_abs_less_than_witness(OC(x), y ? OC(y) : NULL, count, bnd, lb, O(w)), "abs_less_than");
+}
+int h2svd_range_check_witness_count(int bits, int lb) { return orc_range_check_witness_count(bits, lb); }
+int h2svd_range_check_witness(h2svd_ctx *c, const h2svd_fr *x, size_t count, int bits, int lb, h2svd_fr *w) {
+    (void)c; return rc(orc_range_check_witness(OC(x), count, bits, lb, O(w)), "range_check");
+}
+int h2svd_mat_times_diag(h2svd_ctx *c, const h2svd_fr *a, const h2svd_fr *v, size_t rows, size_t lda, size_t cols_v, h2svd_fr *out) {
+    (void)c; return rc(orc_mat_times_diag(OC(a), OC(v), rows, lda, cols_v, O(out)), "mat_times_diag");
+}
 int h2svd_host_fr_from_canonical(const uint64_t x[4], h2svd_fr *out) { orc_fr_from_canonical(O(out), x); return H2SVD_OK; }
 void h2svd_host_fr_to_canonical(const h2svd_fr *a, uint64_t out[4]) { orc_fr_to_canonical(out, OC(a)); }
 void h2svd_host_fr_add(const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *o) { orc_fr_add(O(o), OC(a), OC(b)); }

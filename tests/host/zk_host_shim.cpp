@@ -75,6 +75,30 @@ static void run_mat_times_vec(int lb, const double* mat, const double* vec, size
     for (const AssignedValue& x : zku1_s) g_scalars.push_back(fpchip.dequantization(fpchip.signed_div_scale(ctx, x).first.v));
 }
 
+// do_zk_svd's circuit (examples/svd_example.rs:98-201 -> src/svd/mod.rs): phase 0 on ctx 0, phase 1 on ctx 1
+template <uint32_t P>
+static void run_svd(int lb, const double* m, const double* u, const double* v, const double* d, size_t n, size_t mm,
+                    size_t err_size, const Fr& gamma) {
+    FixedPointChip041<P> fpchip(lb);
+    g_ctx.emplace_back(0);
+    g_ctx.emplace_back(1);
+    Context& ctx = g_ctx[0];
+    auto mat = [](const double* p, size_t r, size_t c) {
+        std::vector<std::vector<double>> o(r, std::vector<double>(c));
+        for (size_t i = 0; i < r; i++) for (size_t j = 0; j < c; j++) o[i][j] = p[i * c + j];
+        return o;
+    };
+    const ZkMatrix<P> zm = ZkMatrix<P>::create(ctx, fpchip, mat(m, n, mm));
+    const ZkMatrix<P> zu = ZkMatrix<P>::create(ctx, fpchip, mat(u, n, n));
+    const ZkMatrix<P> zv = ZkMatrix<P>::create(ctx, fpchip, mat(v, mm, mm));
+    const ZkVector<P> zd = ZkVector<P>::create(ctx, fpchip, std::vector<double>(d, d + (n < mm ? n : mm)));
+    const auto errs = svd::err_calc(P, err_size, 100.0, 1e-10, 1e-10);
+    const auto p0 = svd::check_svd_phase0(ctx, fpchip, zm, zu, zv, zd, errs.first, errs.second, 30);
+    Context& ctx1 = g_ctx[1];
+    const AssignedValue init_rand = ctx1.load_witness(gamma);
+    svd::check_svd_phase1(ctx1, fpchip, zm, zu, zv, p0, init_rand);
+}
+
 template <typename F>
 static int guarded(int lb, F&& f) {
     g_ctx.clear();
@@ -102,6 +126,19 @@ int zkh_run_zkmatrix(int P, int lb, const double* a, const double* b, size_t n, 
             case 32: run_zkmatrix<32>(lb, a, b, n, k, m, g); break;
             case 42: run_zkmatrix<42>(lb, a, b, n, k, m, g); break;
             case 63: run_zkmatrix<63>(lb, a, b, n, k, m, g); break;
+            default: throw std::logic_error("unsupported PRECISION_BITS in the test driver");
+        }
+    });
+}
+int zkh_run_svd(int P, int lb, const double* m, const double* u, const double* v, const double* d, size_t n, size_t mm,
+                size_t err_size, const uint64_t* gamma) {
+    Fr g;
+    std::memcpy(g.l, gamma, 32);
+    return guarded(lb, [&] {
+        switch (P) {
+            case 32: run_svd<32>(lb, m, u, v, d, n, mm, err_size, g); break;
+            case 42: run_svd<42>(lb, m, u, v, d, n, mm, err_size, g); break;
+            case 63: run_svd<63>(lb, m, u, v, d, n, mm, err_size, g); break;
             default: throw std::logic_error("unsupported PRECISION_BITS in the test driver");
         }
     });

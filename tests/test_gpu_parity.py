@@ -324,3 +324,39 @@ def test_zkmatrix_mul_witness_fused_matches_oracle(handle, pkg, rows, k, m, P, b
     for key in ("powers", "prefix_cv", "prefix_abv", "diff", "is_zero", "inv"):
         assert _eq(res[key], fw[key]), key
     assert not res["diff"].any()
+
+
+# ---------------------------------------------------------------- SVD-verifier range-check witnesses
+@pytest.mark.parametrize("bnd,lb", [((1 << 42) + 1, 19), (12345678901234567890123, 19), (5, 19), ((1 << 63) + 1, 12), (1 << 100, 8)])
+def test_abs_less_than_witness_matches_oracle(handle, bnd, lb):
+    rng = np.random.default_rng(lb)
+    import random as _r
+    r = _r.Random(bnd % 997)
+    n = 3000
+    xs = [r.randrange(-(bnd - 1), bnd) % po.R_MOD for _ in range(n - 3)] + [0, bnd - 1, (-(bnd - 1)) % po.R_MOD]
+    x = po.pack_mont(xs)
+    y = random_fr(rng, n)
+    assert _eq(handle.abs_less_than_witness(x, bnd, lb), corac.abs_less_than_witness(x, bnd, lb))
+    xy = corac.zkvec_sub(x, corac.zkvec_sub(np.zeros_like(y), y))   # x + y, so that (x + y) - y is in range
+    assert _eq(handle.abs_less_than_witness(xy, bnd, lb, y=y), corac.abs_less_than_witness(xy, bnd, lb, y=y))
+    # out-of-range inputs (a dishonest prover) still produce the model's cells
+    bad = random_fr(rng, 200)
+    assert _eq(handle.abs_less_than_witness(bad, bnd, lb), corac.abs_less_than_witness(bad, bnd, lb))
+
+
+@pytest.mark.parametrize("bits,lb", [(72, 19), (93, 19), (19, 19), (20, 19), (57, 19), (5, 19), (38, 19), (64, 8), (33, 32)])
+def test_range_check_witness_matches_oracle(handle, bits, lb):
+    import random as _r
+    r = _r.Random(bits)
+    x = po.pack_mont([r.randrange(1 << bits) for _ in range(1500)] + [0, (1 << bits) - 1])
+    assert _eq(handle.range_check_witness(x, bits, lb), corac.range_check_witness(x, bits, lb))
+    bad = random_fr(np.random.default_rng(bits), 100)
+    assert _eq(handle.range_check_witness(bad, bits, lb), corac.range_check_witness(bad, bits, lb))
+
+
+def test_mat_times_diag_matches_oracle(handle):
+    rng = np.random.default_rng(3)
+    a, v = random_fr(rng, 37, 50), random_fr(rng, 41)
+    assert _eq(handle.mat_times_diag(a, v), corac.mat_times_diag(a, v))
+    with pytest.raises(Exception):
+        handle.mat_times_diag(random_fr(rng, 3, 4), random_fr(rng, 5))     # reference :616 assert

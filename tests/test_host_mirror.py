@@ -45,6 +45,7 @@ def _build(tmp, gpu: bool) -> ct.CDLL:
     lib.zkh_failure.argtypes = [ct.c_int]
     lib.zkh_run_zkmatrix.argtypes = [ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_size_t, ct.c_size_t, ct.c_void_p]
     lib.zkh_run_zkvector.argtypes = [ct.c_int]
+    lib.zkh_run_svd.argtypes = [ct.c_int, ct.c_int] + [ct.c_void_p] * 4 + [ct.c_size_t] * 3 + [ct.c_void_p]
     lib.zkh_run_mat_times_vec.argtypes = [ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_size_t]
     lib.zkh_run_bad_shapes.argtypes = [ct.c_int]
     lib.zkh_ctx_export.argtypes = [ct.c_size_t] + [ct.c_void_p] * 7
@@ -180,7 +181,57 @@ def _check_mat_times_vec(lib, lb):
     assert np.array_equal(_scalars(lib), np.array([fp.dequantization(o.value) for o in out]))
 
 
+def _oracle_svd(inputs, P, lb, err_size):
+    fp = po.FixedPointChip(P, lb)
+    ctx = po.Context(0)
+    m, u, v = (po.ZkMatrix.new(ctx, fp, inputs[k]) for k in ("m", "u", "v"))
+    d = po.ZkVector.new(ctx, fp, inputs["d"])
+    err_svd, err_u = po.err_calc(P, err_size, 100.0, 1e-10, 1e-10)
+    out = po.check_svd_phase0(ctx, fp, m, u, v, d, err_svd, err_u, 30)
+    ctx1 = po.Context(1)
+    po.check_svd_phase1(ctx1, fp, m, u, v, *out, ctx1.load_witness(GAMMA))
+    return ctx, ctx1
+
+
+def _run_svd(lib, inputs, P, lb, err_size):
+    arrs = [np.ascontiguousarray(np.array(inputs[k], dtype=np.float64)) for k in ("m", "u", "v", "d")]
+    n, mm = arrs[0].shape
+    g = po.pack_mont([GAMMA])
+    return lib.zkh_run_svd(P, lb, *[_p(a) for a in arrs], n, mm, err_size, _p(g))
+
+
+def _check_svd(lib, n, mm, P, lb):
+    """BASELINE configs[0]: the SVD circuit (phase 0 + phase 1) on an input-creator.py style matrix: every cell of
+    both contexts identical to the oracle's model, `matrix` satisfied, `matrix-wrong` rejected by a phase-0 check."""
+    good, wrong = po.make_svd_inputs(n, mm, 2024 + n)
+    good = {k: np.asarray(v).tolist() for k, v in good.items()}
+    wrong = {k: np.asarray(v).tolist() for k, v in wrong.items()}
+    rc = _run_svd(lib, good, P, lb, max(n, mm))
+    assert rc == 0, (lib.zkh_error(), lib.zkh_failure(0))
+    ctx, ctx1 = _oracle_svd(good, P, lb, max(n, mm))
+    got = _export(lib)
+    _assert_same_context(got[0], ctx)
+    _assert_same_context(got[1], ctx1)
+    assert po.mock_prove([ctx, ctx1], lb) == []
+    rc = _run_svd(lib, wrong, P, lb, max(n, mm))
+    assert rc >= 0, lib.zkh_error()
+    if P >= 42:   # the +1e-7 of input-creator.py:50 is above the tolerance only at the example's precision (P=42) and up
+        assert rc > 0, "matrix-wrong must violate the circuit"
+    ctxw, ctxw1 = _oracle_svd(wrong, P, lb, max(n, mm))
+    gotw = _export(lib)
+    _assert_same_context(gotw[0], ctxw)
+    _assert_same_context(gotw[1], ctxw1)
+    fails = [lib.zkh_failure(i).decode() for i in range(min(rc, 16))]
+    assert all(f.startswith("ctx 0:") for f in fails), fails     # rejected in phase 0 (check_mat_diff), never in phase 1
+    assert len(po.mock_prove([ctxw, ctxw1], lb)) == rc
+
+
 # ------------------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize("n,mm,P", [(8, 8, 42), (4, 6, 32), (6, 4, 63)])
+def test_host_mirror_svd_circuit_cpu(cpu_lib, n, mm, P):
+    _check_svd(cpu_lib, n, mm, P, 19)
+
+
 @pytest.mark.parametrize("P,lb,n,k,m", [(42, 19, 8, 8, 8), (32, 19, 3, 5, 4), (63, 19, 4, 4, 4), (32, 12, 2, 3, 2)])
 def test_host_mirror_zkmatrix_cpu(cpu_lib, P, lb, n, k, m):
     _check_zkmatrix(cpu_lib, P, lb, n, k, m, seed=100 + P + n)
@@ -205,6 +256,13 @@ def test_host_mirror_shape_asserts_cpu(cpu_lib):
 def test_host_mirror_zkmatrix_gpu(gpu_lib, P, lb, n, k, m):
     """BASELINE configs[0] shape (8x8, P=42, lb=19) and friends through the CUDA library."""
     _check_zkmatrix(gpu_lib, P, lb, n, k, m, seed=100 + P + n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,mm,P", [(8, 8, 42), (4, 6, 32), (6, 4, 63), (16, 16, 42)])
+def test_host_mirror_svd_circuit_gpu(gpu_lib, n, mm, P):
+    """configs[0] through the CUDA library: `matrix` passes, `matrix-wrong` fails, every cell as in the oracle."""
+    _check_svd(gpu_lib, n, mm, P, 19)
 
 
 @pytest.mark.gpu

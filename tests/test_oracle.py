@@ -143,3 +143,54 @@ def test_freivalds_oracle_detects_wrong_product():
     fw2 = corac.freivalds_witness(a, b, cs2, g)
     d, iv, z = (po.unpack_mont(fw2[x]) for x in ("diff", "inv", "is_zero"))
     assert d[2] != 0 and d[2] * iv[2] % po.R_MOD == 1 and z[2] == 0 and z[0] == 1
+
+
+def _witness_values(ctx, start):
+    return [v for v, k in zip(ctx.advice[start:], ctx.kind[start:]) if k == "W"]
+
+
+@pytest.mark.parametrize("bnd,lb", [((1 << 42) + 1, 19), (12345678901234567890123, 19), (5, 19), ((1 << 63) + 1, 12), (1 << 100, 8)])
+def test_c_oracle_abs_less_than_matches_layout_model(bnd, lb):
+    """orc_abs_less_than_witness == the Witness cells of check_abs_less_than / check_mat_diff in the layout model."""
+    rng = random.Random(bnd % 1000)
+    rg = po.RangeChip(lb)
+    xs = [rng.randrange(-(bnd - 1), bnd) % po.R_MOD for _ in range(20)] + [0, bnd - 1, (-(bnd - 1)) % po.R_MOD, bnd % po.R_MOD]
+    ys = [rng.randrange(po.R_MOD) for _ in xs]
+    want, want_diff = [], []
+    for x, y in zip(xs, ys):
+        ctx = po.Context()
+        cx = ctx.load_witness(x)
+        po.check_abs_less_than(ctx, rg, cx, bnd)
+        want.append(_witness_values(ctx, 1))
+        ctx = po.Context()
+        ca, cb = ctx.load_witness((x + y) % po.R_MOD), ctx.load_witness(y)
+        po.check_mat_diff(ctx, rg, [[ca]], [[cb]], bnd)
+        want_diff.append(_witness_values(ctx, 2))
+    got = corac.abs_less_than_witness(po.pack_mont(xs), bnd, lb)
+    assert [po.unpack_mont(r) for r in got] == want
+    got = corac.abs_less_than_witness(po.pack_mont([(x + y) % po.R_MOD for x, y in zip(xs, ys)]), bnd, lb, y=po.pack_mont(ys))
+    assert [po.unpack_mont(r) for r in got] == want_diff
+
+
+@pytest.mark.parametrize("bits,lb", [(72, 19), (93, 19), (19, 19), (20, 19), (57, 19), (5, 19), (38, 19), (64, 8), (33, 32)])
+def test_c_oracle_range_check_matches_layout_model(bits, lb):
+    rng = random.Random(bits)
+    rg = po.RangeChip(lb)
+    xs = [rng.randrange(1 << bits) for _ in range(20)] + [0, (1 << bits) - 1]
+    want = []
+    for x in xs:
+        ctx = po.Context()
+        cx = ctx.load_witness(x)
+        rg.range_check(ctx, cx, bits)
+        want.append(_witness_values(ctx, 1))
+        assert po.mock_prove(ctx, lb) == []
+    got = corac.range_check_witness(po.pack_mont(xs), bits, lb)
+    assert [po.unpack_mont(r) for r in got] == want
+
+
+def test_c_oracle_mat_times_diag():
+    rng = random.Random(9)
+    a = [[rng.randrange(po.R_MOD) for _ in range(5)] for _ in range(3)]
+    v = [rng.randrange(po.R_MOD) for _ in range(4)]
+    got = corac.mat_times_diag(po.pack_mont(sum(a, [])).reshape(3, 5, 4), po.pack_mont(v))
+    assert po.unpack_mont(got) == [a[i][j] * v[j] % po.R_MOD for i in range(3) for j in range(4)]
