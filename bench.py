@@ -146,7 +146,7 @@ def run_reference(args) -> None:
     n = args.n
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
-        r = cpu_sample(n, threads, mm_rows=max(16, 2 * threads), rs_elems=16384)
+        r = cpu_sample(n, threads, mm_rows=min(n, max(64, 8 * threads)), rs_elems=min(n * n, 65536 * max(1, threads // 4)))
         if i >= args.warmup:
             vals.append(r)
             secs.append(r["seconds_full_job_extrapolated"])
@@ -370,7 +370,7 @@ def run_gpu(args) -> None:
             "verified": "Freivalds diff == 0; fused host call and device building blocks byte-identical",
         }
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_sample(n, 1, mm_rows=64, rs_elems=65536)
+            cb = cpu_sample(n, 1, mm_rows=256, rs_elems=262144)   # ~15 s of single-thread CPU work
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": cb["sample"] + f" ({cb['t_sample_s']:.1f} s of CPU work, 1 thread: "
                                                              "the reference is single-threaded)"}

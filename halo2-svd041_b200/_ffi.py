@@ -81,6 +81,7 @@ DEBUG_SIGNATURES = {
     "h2svd_debug_set_matmul_variant": (_I, [_I]),
     "h2svd_debug_set_rescale_generic": (_I, [_I]),
     "h2svd_debug_set_matmul_streamk": (_I, [_I]),
+    "h2svd_debug_set_matmul_karatsuba": (_I, [_I]),
     "h2svd_debug_set_matvec_warp_kernel": (_I, [_I]),
 }
 

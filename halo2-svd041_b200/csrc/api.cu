@@ -170,6 +170,7 @@ void h2svd_destroy(h2svd_ctx* ctx) {
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->sk_ws) cudaFree(ctx->sk_ws);
+    if (ctx->kara_ws) cudaFree(ctx->kara_ws);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -18,6 +18,8 @@ struct h2svd_ctx {
     // second stream + events for copy/compute overlap in the host-pointer entry points
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* kara_ws = nullptr;  // pre-split (Karatsuba) operands of the mat-mul
+    size_t kara_ws_bytes = 0;
     void* sk_ws = nullptr;  // stream-K partial-tile workspace of the mat-mul
     size_t sk_ws_bytes = 0;
     int* d_flag = nullptr;  // device flag for validation kernels

@@ -345,6 +345,11 @@ def set_matvec_warp_kernel(v: bool) -> None:
     _ffi.load().h2svd_debug_set_matvec_warp_kernel(int(v))
 
 
+def set_matmul_karatsuba(v: int) -> None:
+    """Triage hook: 0 schoolbook kernels, 1..3 Karatsuba kernel variants."""
+    _ffi.load().h2svd_debug_set_matmul_karatsuba(v)
+
+
 def set_matmul_streamk(v: int) -> None:
     """Triage hook: -1 auto (default), 0 never, 1 always use the stream-K mat-mul schedule."""
     _ffi.load().h2svd_debug_set_matmul_streamk(v)

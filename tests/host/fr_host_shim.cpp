@@ -6,6 +6,7 @@
 
 #include "../../halo2-svd041_b200/csrc/fr_acc.cuh"
 #include "../../halo2-svd041_b200/csrc/fr_fast.cuh"
+#include "../../halo2-svd041_b200/csrc/fr_kara.cuh"
 
 using fr::Fr;
 
@@ -27,6 +28,29 @@ void hs_add_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0;
 void hs_sub_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::sub_fast(a[i], b[i]); }
 void hs_to_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::to_mont_fast(a[i]); }
 void hs_from_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::from_mont_fast(a[i]); }
+// Karatsuba lazy dot product exactly as the Karatsuba mat-mul accumulates it (fr_kara.cuh)
+void hs_kara_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {
+    fr::KAcc p0, p1, p2;
+    fr::kacc_clear(p0); fr::kacc_clear(p1); fr::kacc_clear(p2);
+    for (size_t i = 0; i < k; i++) {
+        const fr::KOp x = fr::ksplit(a[i]), y = fr::ksplit(b[i]);
+        fr::kmul_acc(p0, x.lo, y.lo);
+        fr::kmul_acc(p2, x.hi, y.hi);
+        fr::kmul_acc(p1, x.s, y.s);
+    }
+    *o = fr::kara_finalize(p0, p1, p2);
+}
+void hs_kara_repeat(const Fr* a, const Fr* b, size_t k, Fr* o) {
+    fr::KAcc p0, p1, p2;
+    fr::kacc_clear(p0); fr::kacc_clear(p1); fr::kacc_clear(p2);
+    const fr::KOp x = fr::ksplit(*a), y = fr::ksplit(*b);
+    for (size_t i = 0; i < k; i++) {
+        fr::kmul_acc(p0, x.lo, y.lo);
+        fr::kmul_acc(p2, x.hi, y.hi);
+        fr::kmul_acc(p1, x.s, y.s);
+    }
+    *o = fr::kara_finalize(p0, p1, p2);
+}
 // lazy dot product exactly as the mat-mul inner loop accumulates it (host fallback of chain4)
 void hs_lazy_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {
     fr::WideAcc w;

@@ -140,3 +140,25 @@ def test_lazy_matmul_ragged(shim):
     exp = [sum(A[i * k + t] * B[t * m + j] for t in range(k)) * po.MONT_RINV % R
            for i in range(n) for j in range(m)]
     assert unraw(C) == exp
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 17, 64, 1000])
+def test_karatsuba_lazy_dot_product(shim, k):
+    """fr_kara.cuh: split at bit 127, three lazy 4x4-limb product sums, recombination + reduction in the epilogue."""
+    rng = random.Random(100 + k)
+    edge = [0, 1, R - 1, (1 << 127) - 1, 1 << 127, (1 << 253), ((1 << 254) - 1) % R, (1 << 128) - 1]
+    xs = ([rng.choice(edge) for _ in range(k // 2)] + [rng.randrange(R) for _ in range(k)])[:k]
+    ys = ([rng.choice(edge) for _ in range(k // 3)] + [rng.randrange(R) for _ in range(k)])[:k]
+    a, b = raw_limbs(xs), raw_limbs(ys)
+    o = np.zeros((1, 4), dtype=np.uint64)
+    shim.hs_kara_dot(P(a), P(b), k, P(o))
+    assert unraw(o) == [sum(x * y for x, y in zip(xs, ys)) * po.MONT_RINV % R]
+
+
+def test_karatsuba_accumulator_headroom(shim):
+    """worst-case operands (r - 1) repeated: the 4x4 accumulators and their carry counters must not wrap"""
+    a = raw_limbs([R - 1])
+    o = np.zeros((1, 4), dtype=np.uint64)
+    for k in (1, 4096, 100000):
+        shim.hs_kara_repeat(P(a), P(a), k, P(o))
+        assert unraw(o) == [k * (R - 1) * (R - 1) * po.MONT_RINV % R]

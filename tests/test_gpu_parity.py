@@ -30,10 +30,12 @@ def test_fr_matmul_all_tile_variants(handle, pkg, variant):
     rng = np.random.default_rng(variant)
     a, b = random_fr(rng, 70, 50, ), random_fr(rng, 50, 45)
     try:
+        pkg.set_matmul_karatsuba(0)      # tile variants of the schoolbook engine
         pkg.set_matmul_variant(variant)
         c = handle.fr_matmul(a, b)
     finally:
         pkg.set_matmul_variant(0)
+        pkg.set_matmul_karatsuba(-1)
     assert _eq(c, corac.field_mat_mul(a, b, threads=0))
 
 
@@ -44,18 +46,41 @@ def test_fr_matmul_streamk_schedule(handle, pkg, n, k, m):
     rng = np.random.default_rng(n * 7 + k)
     a, b = random_fr(rng, n, k), random_fr(rng, k, m)
     try:
+        pkg.set_matmul_karatsuba(0)      # schoolbook engine: this test is about the schedule
         pkg.set_matmul_streamk(1)
         got = handle.fr_matmul(a, b)
         pkg.set_matmul_streamk(0)
         plain = handle.fr_matmul(a, b)
     finally:
         pkg.set_matmul_streamk(-1)
+        pkg.set_matmul_karatsuba(-1)
     assert _eq(got, plain)
     if n * k * m <= 1 << 22:
         assert _eq(got, corac.field_mat_mul(a, b))
     else:
         rows = [0, n // 2, n - 1]
         assert _eq(got[rows], corac.field_mat_mul(np.ascontiguousarray(a[rows]), b))
+
+
+@pytest.mark.parametrize("kara", [1, 2, 3])
+@pytest.mark.parametrize("streamk", [0, 1])
+@pytest.mark.parametrize("n,k,m", [(8, 8, 8), (33, 100, 47), (5, 300, 3), (64, 17, 31), (128, 256, 100)])
+def test_fr_matmul_karatsuba_engine(handle, pkg, kara, streamk, n, k, m):
+    """Karatsuba engine (operands pre-split at bit 127, three lazy 4x4-limb accumulators, recombination in the
+    epilogue), one-CTA-per-tile and stream-K schedules: same bytes as the oracle, incl. adversarial operands."""
+    rng = np.random.default_rng(n * 11 + k)
+    a, b = random_fr(rng, n, k), random_fr(rng, k, m)
+    adv = adversarial_fr()
+    a.reshape(-1, 4)[: min(len(adv), n * k)] = adv[: n * k]
+    b.reshape(-1, 4)[-min(len(adv), k * m):] = adv[: min(len(adv), k * m)]
+    try:
+        pkg.set_matmul_karatsuba(kara)
+        pkg.set_matmul_streamk(streamk)
+        got = handle.fr_matmul(a, b)
+    finally:
+        pkg.set_matmul_karatsuba(-1)
+        pkg.set_matmul_streamk(-1)
+    assert _eq(got, corac.field_mat_mul(a, b))
 
 
 def test_fr_matmul_adversarial_operands(handle):

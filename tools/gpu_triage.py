@@ -53,6 +53,7 @@ def main():
         a, b = rand_fr(gen, N, N), rand_fr(gen, N, N)
         c = torch.empty_like(a)
         ref = None
+        pkg.set_matmul_karatsuba(0)          # tile variants of the schoolbook engine
         for variant in (0, 1, 2, 3):
             pkg.set_matmul_variant(variant)
             best, med = timeit(lambda: h.fr_matmul_dev(a, b, c), stream)
@@ -65,6 +66,11 @@ def main():
             print(f"matmul N={N} variant {variant}: best {best:.3f} ms med {med:.3f} ms -> {rate/1e9:.1f} G mul-add/s"
                   f" same={same}", flush=True)
         pkg.set_matmul_variant(0)
+        pkg.set_matmul_karatsuba(-1)
+        best, med = timeit(lambda: h.fr_matmul_dev(a, b, c), stream)
+        h.sync()
+        out[f"matmul_N{N}_default"] = dict(ms_best=best, ms_med=med, gmuladd_s=N ** 3 / (best * 1e-3) / 1e9, same_as_v0=bool((ref == c).all()))
+        print(f"matmul N={N} default (Karatsuba engine): best {best:.3f} ms -> {N**3/(best*1e-3)/1e9:.1f} G mul-add/s same={bool((ref == c).all())}", flush=True)
     # Freivalds + rescale at N=1024
     N, P, lb = 1024, 63, 19
     a, b = rand_fr(gen, N, N), rand_fr(gen, N, N)

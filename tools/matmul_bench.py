@@ -17,14 +17,17 @@ shapes = [(1024, 1024, 1024), (512, 1024, 1024), (256, 1024, 1024), (128, 1024, 
 if os.environ.get("SHAPES"):
     shapes = [tuple(int(x) for x in sh.split("x")) for sh in os.environ["SHAPES"].split(",")]
 variants = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0]
+kara_modes = [int(x) for x in os.environ.get("KARA", "1,2,3").split(",") if x]
 for (n, k, m) in shapes:
     a, b = rand_fr(n, k), rand_fr(k, m)
     c = torch.empty((n, m, 4), dtype=torch.int64, device="cuda")
     ref = None
     for variant in variants:
         pkg.set_matmul_variant(variant)
-        for sk in (0, 1, -1):
-            pkg.set_matmul_streamk(sk)
+        modes = [("sk", 0), ("sk", 1), ("sk", -1)] + [("kara", x) for x in kara_modes]
+        for kind, sk in modes:
+            pkg.set_matmul_karatsuba(sk if kind == "kara" else 0)
+            pkg.set_matmul_streamk(sk if kind == "sk" else -1)
             ts = []
             for i in range(7):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,6 +38,6 @@ for (n, k, m) in shapes:
                 ref = c.clone()
             same = bool((ref == c).all())
             t = min(ts[2:])
-            print(f"{n}x{k}x{m} variant {variant} streamk={sk:2d}: {t:.4f} ms  {n*k*m/t/1e6:.1f} G mul-add/s  same={same}", flush=True)
-pkg.set_matmul_streamk(-1); pkg.set_matmul_variant(0)
+            print(f"{n}x{k}x{m} variant {variant} {kind}={sk:2d}: {t:.4f} ms  {n*k*m/t/1e6:.1f} G mul-add/s  same={same}", flush=True)
+pkg.set_matmul_streamk(-1); pkg.set_matmul_variant(0); pkg.set_matmul_karatsuba(-1)
 h.close()
