@@ -24,8 +24,8 @@ struct alignas(16) KOp {   // 48 bytes: the three 128-bit pieces of one field el
 struct KAcc {              // lazy sum of 4x4-limb products (< 2^(256 + 32) for < 2^30 terms)
     uint64_t e[4];         // columns at limbs (0,1) (2,3) (4,5) (6,7)
     uint64_t o[3];         // columns at limbs (1,2) (3,4) (5,6)
-    uint32_t ce[3];        // carries out of even chains, weight 2^(32*(4+2q))  (limbs 4, 6, 8)
-    uint32_t co[2];        // carries out of odd chains,  weight 2^(32*(5+2q))  (limbs 5, 7)
+    uint32_t ce3, ce4;     // carries out of even chains, weights 2^(32*6), 2^(32*8)
+    uint32_t co2, co3;     // carries out of odd chains,  weights 2^(32*5), 2^(32*7)
 };
 
 FR_HD void kacc_clear(KAcc& w) {
@@ -33,10 +33,7 @@ FR_HD void kacc_clear(KAcc& w) {
     for (int i = 0; i < 4; i++) w.e[i] = 0;
 #pragma unroll
     for (int i = 0; i < 3; i++) w.o[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) w.ce[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 2; i++) w.co[i] = 0;
+    w.ce3 = w.ce4 = w.co2 = w.co3 = 0;
 }
 
 FR_HD KOp ksplit(const Fr& x) {
@@ -58,28 +55,85 @@ FR_HD KOp ksplit(const Fr& x) {
     return k;  // c == 0: lo + hi < 2^128
 }
 
-// d[0..2) (two 64-bit columns) += {a0, a1} * b with one carry chain; cnt += carry out.
-FR_HD void chain2(uint64_t* d, uint32_t& cnt, uint32_t a0, uint32_t a1, uint32_t b) {
+// d[0..N) (N consecutive 64-bit columns) += a_t * b_t for t < N, one carry chain; cnt += carry out.
+// Every product may have its own (a, b): a chain only needs its products to sit on consecutive columns.
+template <int N>
+FR_HD void kchain(uint64_t* d, uint32_t& cnt, const uint32_t* a, const uint32_t* b) {
 #if defined(__CUDA_ARCH__)
-    asm("{\n\t"
-        ".reg .u32 l0, h0, l1, h1;\n\t"
-        "mov.b64 {l0, h0}, %0;\n\t"
-        "mov.b64 {l1, h1}, %1;\n\t"
-        "mad.lo.cc.u32   l0, %3, %5, l0;\n\t"
-        "madc.hi.cc.u32  h0, %3, %5, h0;\n\t"
-        "madc.lo.cc.u32  l1, %4, %5, l1;\n\t"
-        "madc.hi.cc.u32  h1, %4, %5, h1;\n\t"
-        "addc.u32        %2, %2, 0;\n\t"
-        "mov.b64 %0, {l0, h0};\n\t"
-        "mov.b64 %1, {l1, h1};\n\t"
-        "}"
-        : "+l"(d[0]), "+l"(d[1]), "+r"(cnt)
-        : "r"(a0), "r"(a1), "r"(b));
+    static_assert(N >= 1 && N <= 4, "chain length");
+    if (N == 1) {
+        asm("{\n\t"
+            ".reg .u32 l0, h0;\n\t"
+            "mov.b64 {l0, h0}, %0;\n\t"
+            "mad.lo.cc.u32   l0, %2, %3, l0;\n\t"
+            "madc.hi.cc.u32  h0, %2, %3, h0;\n\t"
+            "addc.u32        %1, %1, 0;\n\t"
+            "mov.b64 %0, {l0, h0};\n\t"
+            "}"
+            : "+l"(d[0]), "+r"(cnt)
+            : "r"(a[0]), "r"(b[0]));
+    } else if (N == 2) {
+        asm("{\n\t"
+            ".reg .u32 l0, h0, l1, h1;\n\t"
+            "mov.b64 {l0, h0}, %0;\n\t"
+            "mov.b64 {l1, h1}, %1;\n\t"
+            "mad.lo.cc.u32   l0, %3, %5, l0;\n\t"
+            "madc.hi.cc.u32  h0, %3, %5, h0;\n\t"
+            "madc.lo.cc.u32  l1, %4, %6, l1;\n\t"
+            "madc.hi.cc.u32  h1, %4, %6, h1;\n\t"
+            "addc.u32        %2, %2, 0;\n\t"
+            "mov.b64 %0, {l0, h0};\n\t"
+            "mov.b64 %1, {l1, h1};\n\t"
+            "}"
+            : "+l"(d[0]), "+l"(d[1]), "+r"(cnt)
+            : "r"(a[0]), "r"(a[1]), "r"(b[0]), "r"(b[1]));
+    } else if (N == 3) {
+        asm("{\n\t"
+            ".reg .u32 l0, h0, l1, h1, l2, h2;\n\t"
+            "mov.b64 {l0, h0}, %0;\n\t"
+            "mov.b64 {l1, h1}, %1;\n\t"
+            "mov.b64 {l2, h2}, %2;\n\t"
+            "mad.lo.cc.u32   l0, %4, %7, l0;\n\t"
+            "madc.hi.cc.u32  h0, %4, %7, h0;\n\t"
+            "madc.lo.cc.u32  l1, %5, %8, l1;\n\t"
+            "madc.hi.cc.u32  h1, %5, %8, h1;\n\t"
+            "madc.lo.cc.u32  l2, %6, %9, l2;\n\t"
+            "madc.hi.cc.u32  h2, %6, %9, h2;\n\t"
+            "addc.u32        %3, %3, 0;\n\t"
+            "mov.b64 %0, {l0, h0};\n\t"
+            "mov.b64 %1, {l1, h1};\n\t"
+            "mov.b64 %2, {l2, h2};\n\t"
+            "}"
+            : "+l"(d[0]), "+l"(d[1]), "+l"(d[2]), "+r"(cnt)
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b[0]), "r"(b[1]), "r"(b[2]));
+    } else {
+        asm("{\n\t"
+            ".reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+            "mov.b64 {l0, h0}, %0;\n\t"
+            "mov.b64 {l1, h1}, %1;\n\t"
+            "mov.b64 {l2, h2}, %2;\n\t"
+            "mov.b64 {l3, h3}, %3;\n\t"
+            "mad.lo.cc.u32   l0, %5, %9,  l0;\n\t"
+            "madc.hi.cc.u32  h0, %5, %9,  h0;\n\t"
+            "madc.lo.cc.u32  l1, %6, %10, l1;\n\t"
+            "madc.hi.cc.u32  h1, %6, %10, h1;\n\t"
+            "madc.lo.cc.u32  l2, %7, %11, l2;\n\t"
+            "madc.hi.cc.u32  h2, %7, %11, h2;\n\t"
+            "madc.lo.cc.u32  l3, %8, %12, l3;\n\t"
+            "madc.hi.cc.u32  h3, %8, %12, h3;\n\t"
+            "addc.u32        %4, %4, 0;\n\t"
+            "mov.b64 %0, {l0, h0};\n\t"
+            "mov.b64 %1, {l1, h1};\n\t"
+            "mov.b64 %2, {l2, h2};\n\t"
+            "mov.b64 %3, {l3, h3};\n\t"
+            "}"
+            : "+l"(d[0]), "+l"(d[1]), "+l"(d[2]), "+l"(d[3]), "+r"(cnt)
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    }
 #else
-    const uint32_t a[2] = {a0, a1};
     uint32_t carry = 0;
-    for (int i = 0; i < 2; i++) {
-        unsigned __int128 t = (unsigned __int128)((uint64_t)a[i] * b) + d[i] + carry;
+    for (int i = 0; i < N; i++) {
+        unsigned __int128 t = (unsigned __int128)((uint64_t)a[i] * b[i]) + d[i] + carry;
         d[i] = (uint64_t)t;
         carry = (uint32_t)(t >> 64);
     }
@@ -87,16 +141,33 @@ FR_HD void chain2(uint64_t* d, uint32_t& cnt, uint32_t a0, uint32_t a1, uint32_t
 #endif
 }
 
-// w += a * b   (a, b: 4 x u32 limbs each): 16 IMAD.WIDE + 8 IADD3.X
+// w += a * b   (a, b: 4 x u32 limbs each): 16 IMAD.WIDE in 7 carry chains.  Product a_i*b_j sits at limb i+j: even
+// sums on the e columns, odd sums on the o columns.  The chains are chosen so that the carry-outs land on only
+// four counters, three of which receive two carries each (ptxas folds those into one IADD3.X with two carry
+// predicates): the diagonal a_i*b_i is one 4-chain, the rest are 2- and 3-chains plus two single products.
 FR_HD void kmul_acc(KAcc& w, const uint32_t* a, const uint32_t* b) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int i0 = j & 1;          // a-limbs with i+j even: i0, i0+2 -> even columns pe, pe+1
-        const int pe = (i0 + j) >> 1;  // 0, 1, 1, 2
-        chain2(&w.e[pe], w.ce[pe], a[i0], a[i0 + 2], b[j]);
-        const int i1 = 1 - i0;         // a-limbs with i+j odd: i1, i1+2 -> odd columns po, po+1
-        const int po = j >> 1;         // 0, 0, 1, 1
-        chain2(&w.o[po], w.co[po], a[i1], a[i1 + 2], b[j]);
+    {   // even: (0,0) (1,1) (2,2) (3,3) on columns 0..3 -> limb 8
+        kchain<4>(&w.e[0], w.ce4, a, b);
+    }
+    {   // even: (2,0) (3,1) on columns 1, 2 -> limb 6
+        const uint32_t x[2] = {a[2], a[3]}, y[2] = {b[0], b[1]};
+        kchain<2>(&w.e[1], w.ce3, x, y);
+    }
+    {   // even: (0,2) (1,3) on columns 1, 2 -> limb 6
+        const uint32_t x[2] = {a[0], a[1]}, y[2] = {b[2], b[3]};
+        kchain<2>(&w.e[1], w.ce3, x, y);
+    }
+    {   // odd: (1,0) (3,0) (3,2) on columns 0, 1, 2 -> limb 7
+        const uint32_t x[3] = {a[1], a[3], a[3]}, y[3] = {b[0], b[0], b[2]};
+        kchain<3>(&w.o[0], w.co3, x, y);
+    }
+    {   // odd: (0,1) (2,1) (2,3) on columns 0, 1, 2 -> limb 7
+        const uint32_t x[3] = {a[0], a[2], a[2]}, y[3] = {b[1], b[1], b[3]};
+        kchain<3>(&w.o[0], w.co3, x, y);
+    }
+    {   // odd: (1,2) and (0,3) on column 1 -> limb 5
+        kchain<1>(&w.o[1], w.co2, &a[1], &b[2]);
+        kchain<1>(&w.o[1], w.co2, &a[0], &b[3]);
     }
 }
 
@@ -115,10 +186,10 @@ FR_HD void kacc_collapse(const KAcc& w, uint32_t* T) {
         col[2 * p + 1] += (uint32_t)w.o[p];
         col[2 * p + 2] += (uint32_t)(w.o[p] >> 32);
     }
-#pragma unroll
-    for (int q = 0; q < 3; q++) col[4 + 2 * q] += w.ce[q];
-#pragma unroll
-    for (int q = 0; q < 2; q++) col[5 + 2 * q] += w.co[q];
+    col[6] += w.ce3;
+    col[8] += w.ce4;
+    col[5] += w.co2;
+    col[7] += w.co3;
     uint64_t c = 0;
 #pragma unroll
     for (int i = 0; i < 10; i++) {
