@@ -348,13 +348,16 @@ def run_gpu(args) -> None:
                                    "(B v) all-gathered", "l2": "256 MiB flush write between timed steps",
                        "inputs": "input-creator.py distribution, seeded, quantized on the GPU"},
             "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds_after_matmul": ms_fr, "freivalds_pre_overlapped_with_matmul": bool(overlap)},
-            "roofline": {"bound": "imad", "kernel": "fr_matmul_kernel", "achieved": achieved / 1e12,
-                         "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": achieved / imad_peak,
+            "roofline": {"bound": "imad", "kernel": "fr_matmul_kara_kernel (stream-K variant on row slabs)",
+                         "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": achieved / imad_peak,
                          "peak_source": "measured live: mad.lo.u32 micro-benchmark, all SMs (h2svd_microbench_imad kind 0)",
+                         "algorithmic": "SURVEY 8(d): 128 IMAD-pipe slots per Fr mul-add (8x8-limb schoolbook, 64 IMAD.WIDE at half "
+                                        "rate); frac can exceed 1 because the kernel is one-level Karatsuba (48 IMAD.WIDE)",
+                         "executed_imad_slots_per_muladd": 108.2,
+                         "imad_pipe_utilization": (rows * k * m * 108.2 / (ms_mm * 1e-3)) / imad_peak,
+                         "executed_source": "profiles/r01c_ncu_full_summary.md: 48 IMAD.WIDE (2 slots) + 6 IMAD.MOV + 6 IMAD.X per mul-add",
                          "imad_wide_chain_peak": wide_peak / 1e12,
-                         "frac_of_wide_chain_peak": (rows * k * m * 64.0 / (ms_mm * 1e-3)) / wide_peak,
-                         "algorithmic": "128 IMAD slots per Fr mul-add = 64 IMAD.WIDE.U32 (half rate)",
-                         "traffic": traffic_from_profile("fr_matmul_kernel", n) if world == 1 else None,
+                         "traffic": traffic_from_profile("fr_matmul_kara_kernel", n) if world == 1 else None,
                          "traffic_source": "profiles/traffic.json (ncu --set full capture of this command, bytes per launch)"},
             "roofline_hbm": {
                 "rescale": {"bound": "hbm", "achieved": rs_bytes / (ms_rs * 1e-3) / 1e9, "peak": hbm_peak,
