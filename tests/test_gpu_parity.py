@@ -385,3 +385,49 @@ def test_mat_times_diag_matches_oracle(handle):
     assert _eq(handle.mat_times_diag(a, v), corac.mat_times_diag(a, v))
     with pytest.raises(Exception):
         handle.mat_times_diag(random_fr(rng, 3, 4), random_fr(rng, 5))     # reference :616 assert
+
+
+# ---------------------------------------------------------------- BASELINE configs[4], one rank's share
+def test_config4_one_rank_share(handle):
+    """configs[4] (4096x2048 . 2048x4096, P=63, lb=19, 8 GPUs): the 512-row slab one of the 8 ranks owns, at full size
+    on this GPU through the device-pointer entry points.  Checked by (1) the Freivalds identity on every row (diff == 0,
+    computed by kernels independent of the mat-mul), (2) sampled rows of C and (3) sampled rescale witness stripes,
+    bit-exact against the oracle."""
+    import torch
+    P, lb = 63, 19
+    rows, k, m = 512, 2048, 4096
+    dev = torch.device("cuda", handle.device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4)
+    af = (torch.rand((rows, k), dtype=torch.float64, device=dev, generator=gen) - 0.5) * 4
+    bf = (torch.rand((k, m), dtype=torch.float64, device=dev, generator=gen) - 0.5) * 4
+
+    def fr(*shape):
+        return torch.empty(shape + (4,), dtype=torch.int64, device=dev)
+
+    a, b, c = fr(rows, k), fr(k, m), fr(rows, m)
+    handle.quantize_dev(af, P, a)
+    handle.quantize_dev(bf, P, b)
+    handle.fr_matmul_dev(a, b, c)
+    gamma = torch.tensor([[0x1234567, 0x89ABCDEF, 0x13579BDF, 0x2468ACE]], dtype=torch.int64, device=dev)
+    powers, pcv, pbv, pabv = fr(m), fr(rows, m), fr(k, m), fr(rows, k)
+    diff, isz, inv = fr(rows), fr(rows), fr(rows)
+    handle.freivalds_witness_dev(a, b, c, gamma, powers, pcv, pbv, pabv, diff, isz, inv)
+    W = handle.rescale_witness_count(P, lb)
+    q, wit = fr(rows, m), fr(rows * m, W)
+    handle.rescale_witness_dev(c, rows * m, P, lb, q, wit)
+    handle.sync()
+    assert not bool(diff.any().item()), "Freivalds identity violated"
+    one = po.pack_mont([1]).view(np.int64)
+    assert bool((isz.cpu().numpy() == one).all())
+    # sampled rows of C against the oracle
+    sel = [0, 255, 511]
+    a_h = a[sel].cpu().numpy().view(np.uint64)
+    b_h = b.cpu().numpy().view(np.uint64)
+    assert _eq(c[sel].cpu().numpy().view(np.uint64), corac.field_mat_mul(np.ascontiguousarray(a_h), b_h, threads=0))
+    # sampled witness stripes against the oracle
+    idx = torch.tensor([0, 1, 4095, 4096, 1000003, rows * m - 1], device=dev)
+    c_s = c.reshape(-1, 4)[idx].cpu().numpy().view(np.uint64)
+    eq, _, ewit = corac.rescale_witness(np.ascontiguousarray(c_s), P, lb)
+    assert _eq(wit[idx].cpu().numpy().view(np.uint64), ewit)
+    assert _eq(q.reshape(-1, 4)[idx].cpu().numpy().view(np.uint64), eq)
