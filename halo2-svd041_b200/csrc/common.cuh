@@ -45,6 +45,18 @@ int ws_reserve(h2svd_ctx* ctx, size_t bytes);
         H2SVD_CUDA(cudaGetLastError());         \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per function AND per device: remember it per device so that
+// several handles on different GPUs in one process each configure their own copy of the kernel.
+#define H2SVD_SET_SMEM(ctx, kern, bytes)                                                                   \
+    do {                                                                                                   \
+        static uint64_t _done_mask = 0; /* bit d: configured on device d (devices >= 64 are always reconfigured) */ \
+        const int _d = (ctx)->device;                                                                      \
+        if (_d >= 64 || !((_done_mask >> _d) & 1ull)) {                                                    \
+            H2SVD_CUDA(cudaFuncSetAttribute((kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (_d < 64) _done_mask |= 1ull << _d;                                                         \
+        }                                                                                                  \
+    } while (0)
+
 #define H2SVD_TRY(expr)                 \
     do {                                \
         int _rc = (expr);               \

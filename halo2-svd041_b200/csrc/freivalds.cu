@@ -331,12 +331,7 @@ static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_
     if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && g_mv_force_warp == 0) {
         // one warp per row, consecutive elements per lane (mat_vec_prefix_tile_kernel); needs enough rows to
         // give every SM a few warps, otherwise the row-splitting kernel below is the better fit
-        static bool configured = false;
-        if (!configured) {
-            H2SVD_CUDA(cudaFuncSetAttribute(mat_vec_prefix_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)MT_SMEM));
-            configured = true;
-        }
+        H2SVD_SET_SMEM(ctx, mat_vec_prefix_tile_kernel, MT_SMEM);
         size_t blocks = (total_rows + MT_WARPS - 1) / MT_WARPS;
         const size_t cap = (size_t)ctx->sm_count * 5;  // 5 CTAs (96 regs) of 4 independent warps per SM, grid-stride beyond
         if (blocks > cap) blocks = cap;

@@ -713,11 +713,7 @@ int launch_variant(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k
                                        : g_streamk != 0;
     if (streamk && nchunks >= 1 && tiles * nchunks < (1LL << 31)) {
         auto kern = fr_matmul_streamk_kernel<TM, TN, BK, STAGES, MINBLOCKS>;
-        static bool configured_sk = false;
-        if (!configured_sk) {
-            H2SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
-            configured_sk = true;
-        }
+        H2SVD_SET_SMEM(ctx, kern, cfg::SMEM);
         const long long total_units = tiles * nchunks;
         const int G = (int)(total_units < slots ? total_units : slots);
         const size_t part_bytes = (size_t)G * 2 * cfg::BM * cfg::BN * sizeof(Fr);
@@ -737,11 +733,7 @@ int launch_variant(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k
         return H2SVD_OK;
     }
     auto kern = fr_matmul_kernel<TM, TN, BK, STAGES, MINBLOCKS>;
-    static bool configured = false;  // per process; attribute is per function, device-wide
-    if (!configured) {
-        H2SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
-        configured = true;
-    }
+    H2SVD_SET_SMEM(ctx, kern, cfg::SMEM);
     dim3 grid(tiles_x, tiles_y);
     kern<<<grid, THREADS, cfg::SMEM, ctx->stream>>>(a, b, c, n, k, m);
     H2SVD_LAUNCH_CHECK(ctx);
@@ -756,11 +748,7 @@ template <int BK, int STAGES, int MINBLOCKS>
 static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k, int m) {
     using cfg = KCfg<BK, STAGES>;
     auto kern = fr_matmul_kara_kernel<BK, STAGES, MINBLOCKS>;
-    static bool configured = false;
-    if (!configured) {
-        H2SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
-        configured = true;
-    }
+    H2SVD_SET_SMEM(ctx, kern, cfg::SMEM);
     // pre-split operands (48 bytes per element) in a dedicated workspace
     const size_t na = (size_t)n * k, nb = (size_t)k * m;
     const size_t bytes = (na + nb) * sizeof(KOp);
@@ -788,11 +776,7 @@ static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, i
                                        : g_streamk != 0;
     if (streamk && tiles * nchunks < (1LL << 31)) {
         auto skern = fr_matmul_streamk_kara_kernel<BK, STAGES, MINBLOCKS>;
-        static bool configured_sk = false;
-        if (!configured_sk) {
-            H2SVD_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
-            configured_sk = true;
-        }
+        H2SVD_SET_SMEM(ctx, skern, cfg::SMEM);
         const long long total_units = tiles * nchunks;
         const int G = (int)(total_units < slots ? total_units : slots);
         const size_t part_bytes = (size_t)G * 2 * cfg::BM * cfg::BN * sizeof(Fr);

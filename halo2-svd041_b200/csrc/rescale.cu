@@ -392,11 +392,7 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     k.m_bound_d = fr::to_mont(k.i_bound_d);
     k.m_pow_r = fr::to_mont(k.i_pow_r);
     k.m_bound_r = fr::to_mont(k.i_bound_r);
-    static bool configured = false;
-    if (!configured) {
-        H2SVD_CUDA(cudaFuncSetAttribute(rescale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
-        configured = true;
-    }
+    H2SVD_SET_SMEM(ctx, rescale_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
     const size_t cap = (size_t)ctx->sm_count * 3;  // 3 CTAs (69.6 KB of staging each) per SM, grid-stride beyond
     if (blocks > cap) blocks = cap;
@@ -440,11 +436,7 @@ int launch_abs_less_than(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count,
     k.i_bound = bound;
     k.m_pow = fr::to_mont(k.i_pow);
     k.m_bound = fr::to_mont(bound);
-    static bool configured = false;
-    if (!configured) {
-        H2SVD_CUDA(cudaFuncSetAttribute(abs_less_than_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
-        configured = true;
-    }
+    H2SVD_SET_SMEM(ctx, abs_less_than_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
     const size_t cap = (size_t)ctx->sm_count * 3;
     if (blocks > cap) blocks = cap;
@@ -473,11 +465,7 @@ int launch_range_check(h2svd_ctx* ctx, const Fr* x, size_t count, int range_bits
     fill_limb_consts(k.lc, lb, k.n);
     k.m_shift = k.rem > 1 ? fr::to_mont(fr::pow2(lb - k.rem)) : fr::zero();
     k.c_shift = k.rem > 1 ? fr::mont_mul(k.m_shift, fr::to_mont(fr::pow2(32))) : fr::zero();
-    static bool configured = false;
-    if (!configured) {
-        H2SVD_CUDA(cudaFuncSetAttribute(range_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
-        configured = true;
-    }
+    H2SVD_SET_SMEM(ctx, range_check_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
     const size_t cap = (size_t)ctx->sm_count * 3;
     if (blocks > cap) blocks = cap;

@@ -66,3 +66,22 @@ def test_empty_and_single_element_inputs(handle):
     q, wit = handle.rescale_witness(x, 63, 19)
     eq, _, ewit = corac.rescale_witness(x, 63, 19)
     assert _eq(q.reshape(-1, 4), eq) and _eq(wit, ewit)
+
+
+def test_two_handles_on_two_devices_in_one_process(pkg):
+    """One process, one handle per GPU (the C++/Rust shim's multi-GPU mode): kernels that opt in to large dynamic
+    shared memory must be configured on every device they run on."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(5)
+    a, b = random_fr(rng, 40, 70), random_fr(rng, 70, 33)
+    gamma = random_fr(rng, 1)
+    want = corac.field_mat_mul(a, b)
+    ew = corac.rescale_witness(want.reshape(-1, 4), 63, 19)[2]
+    for dev in (1, 0, 1):
+        with pkg.Handle(dev) as h:
+            res = h.zkmatrix_mul_witness(a, b, gamma, 63, 19)
+            assert _eq(res["c_s"], want) and _eq(res["wit"], ew) and not res["diff"].any()
+            x, s = random_fr(rng, 700, 300), random_fr(rng, 700, 300)
+            assert _eq(h.zkvec_inner_prefix(x, s), corac.zkvec_inner_prefix(x, s))
