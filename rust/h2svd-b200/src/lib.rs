@@ -152,3 +152,104 @@ pub fn verify_mul<F: BigPrimeField>(
              Witness(zf), Constant(F::ZERO)], [0, 4]);
     }
 }
+
+/// Cells of one `range_check(x, n*lb)` given its witnesses `l0, l1, s1, l2, s2, ...` (halo2-base RangeChip):
+/// `[l0, l1, 2^lb, s1, l2, 2^2lb, s2, ...]`, gates at 0, 3, ...; every limb is pushed to the lookup table.
+fn assign_range_check<F: BigPrimeField>(
+    ctx: &mut Context<F>, range: &halo2_base::gates::RangeChip<F>, x: AssignedValue<F>, n: usize, lb: usize, w: &[h2svd_fr],
+) -> usize {
+    use halo2_base::gates::RangeInstructions;
+    if n == 1 {
+        range.add_cell_to_lookup(ctx, x, lb); // halo2-base: the single limb is x itself
+        return 0;
+    }
+    let mut cells = vec![Witness(from_wire::<F>(&w[0]))];
+    for i in 1..n {
+        cells.push(Witness(from_wire::<F>(&w[2 * i - 1])));
+        cells.push(Constant(range.gate().pow_of_two()[lb * i]));
+        cells.push(Witness(from_wire::<F>(&w[2 * i])));
+    }
+    let row = ctx.advice.len();
+    let acc = ctx.assign_region_last(cells, (0..n - 1).map(|i| 3 * i as isize));
+    ctx.constrain_equal(&x, &acc);
+    range.add_cell_to_lookup(ctx, ctx.get(row as isize), lb);
+    for i in 0..n - 1 {
+        range.add_cell_to_lookup(ctx, ctx.get((row + 1 + 3 * i) as isize), lb);
+    }
+    2 * n - 1
+}
+
+/// Cells of one `check_big_less_than_safe(x, bound)` given its witnesses (range_check(x) | chk, xp | range_check(chk)).
+fn assign_cbls<F: BigPrimeField>(
+    ctx: &mut Context<F>, range: &halo2_base::gates::RangeChip<F>, x: AssignedValue<F>, bound: F, n: usize, lb: usize,
+    w: &[h2svd_fr],
+) -> usize {
+    let mut used = assign_range_check(ctx, range, x, n, lb, w);
+    let neg_pow = -range.gate().pow_of_two()[n * lb];
+    ctx.assign_region(
+        [Witness(from_wire::<F>(&w[used])), Constant(bound), Constant(F::ONE), Witness(from_wire::<F>(&w[used + 1])),
+         Constant(neg_pow), Constant(F::ONE), Existing(x)], [0, 3]);
+    let chk = ctx.get(-7);
+    used += 2;
+    used + assign_range_check(ctx, range, chk, n, lb, &w[used..])
+}
+
+/// Drop-in for `ZkMatrix::rescale_matrix` (src/matrix/mod.rs:354-375): ONE GPU call for the whole matrix, then the cells of
+/// `signed_div_scale` per element in the reference's order.  `shift_bits` / `a_num_bits` are the
+/// FixedPointChip041's constants (pass the chip's values; -1 selects 3P / 4P).
+pub fn rescale_matrix<F: BigPrimeField>(
+    gpu: &Gpu, ctx: &mut Context<F>, range: &halo2_base::gates::RangeChip<F>, c_s: &Vec<Vec<AssignedValue<F>>>,
+    precision_bits: u32, lookup_bits: usize, shift_bits: i32, a_num_bits: i32,
+) -> Vec<Vec<AssignedValue<F>>> {
+    use halo2_base::gates::RangeInstructions;
+    let (rows, cols) = (c_s.len(), c_s[0].len());
+    let p = precision_bits as usize;
+    let s = if shift_bits < 0 { 3 * p } else { shift_bits as usize };
+    let a = if a_num_bits < 0 { 4 * p } else { a_num_bits as usize };
+    let w_per = unsafe { h2svd_rescale_witness_count(p as c_int, lookup_bits as c_int, s as c_int, a as c_int) };
+    assert!(w_per > 0, "rescale parameters out of range");
+    let w_per = w_per as usize;
+    let (n_d, n_r) = ((a - p + 1 + lookup_bits - 1) / lookup_bits, (p + 1 + lookup_bits - 1) / lookup_bits);
+    let fc = gather(c_s);
+    let mut q = vec![h2svd_fr::default(); rows * cols];
+    let mut wit = vec![h2svd_fr::default(); rows * cols * w_per];
+    check(unsafe {
+        h2svd_rescale_witness(gpu.0, fc.as_ptr(), rows * cols, p as c_int, lookup_bits as c_int, s as c_int, a as c_int,
+                              q.as_mut_ptr(), wit.as_mut_ptr())
+    });
+    let pow = range.gate().pow_of_two();
+    let mut out = Vec::with_capacity(rows);
+    for i in 0..rows {
+        let mut new_row = Vec::with_capacity(cols);
+        for j in 0..cols {
+            let w = &wit[(i * cols + j) * w_per..(i * cols + j + 1) * w_per];
+            let a_shift = ctx.assign_region_last(
+                [Existing(c_s[i][j]), Constant(pow[s]), Constant(F::ONE), Witness(from_wire::<F>(&w[0]))], [0]);
+            ctx.assign_region(
+                [Witness(from_wire::<F>(&w[1])), Constant(pow[p]), Witness(from_wire::<F>(&w[2])), Existing(a_shift)], [0]);
+            let (rem, div) = (ctx.get(-4), ctx.get(-2));
+            let mut used = 3;
+            used += assign_cbls(ctx, range, div, pow[a - p] + F::ONE, n_d, lookup_bits, &w[used..]);
+            used += assign_cbls(ctx, range, rem, pow[p], n_r, lookup_bits, &w[used..]);
+            ctx.assign_region(
+                [Witness(from_wire::<F>(&w[used])), Constant(pow[s - p]), Constant(F::ONE), Existing(div)], [0]);
+            new_row.push(ctx.get(-4));
+        }
+        out.push(new_row);
+    }
+    out
+}
+
+/// Drop-in for the value side of `ZkVector::inner_product` (:79-106) for ONE pair: running sums from the GPU, cells of
+/// `gate.inner_product(u = x, v = self)`; the caller passes the returned cell to `signed_div_scale` (rescale_matrix on a
+/// 1x1 matrix, or the chip's own method).
+pub fn inner_product_unscaled<F: BigPrimeField>(
+    gpu: &Gpu, ctx: &mut Context<F>, this: &Vec<AssignedValue<F>>, x: &Vec<AssignedValue<F>>,
+) -> AssignedValue<F> {
+    assert!(this.len() == x.len()); // :86
+    let fx: Vec<h2svd_fr> = x.iter().map(|c| to_wire(c.value())).collect();
+    let fs: Vec<h2svd_fr> = this.iter().map(|c| to_wire(c.value())).collect();
+    let mut prefix = vec![h2svd_fr::default(); x.len()];
+    check(unsafe { h2svd_zkvec_inner_prefix(gpu.0, fx.as_ptr(), fs.as_ptr(), 1, x.len(), prefix.as_mut_ptr()) });
+    assign_inner_product_row(ctx, x, this, &prefix)
+}
