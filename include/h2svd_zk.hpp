@@ -560,7 +560,7 @@ class ZkMatrix {
     }
     // verify_mul (:299-342): Freivalds with v = (1, gamma, ..., gamma^(d-1))
     static void verify_mul(Context& ctx, const Chip& fpchip, const ZkMatrix& a, const ZkMatrix& b,
-                           const AssignedMatrix& c_s, const AssignedValue& init_rand) {
+                           const AssignedMatrix& c_s, const AssignedValue& init_rand, bool strict = false) {
         require(a.num_col == b.num_rows, "a.num_col == b.num_rows");            // :307
         require(c_s.size() == a.num_rows, "c_s.len() == a.num_rows");            // :308
         require(!c_s.empty() && c_s[0].size() == b.num_col, "c_s[0].len() == b.num_col");  // :309
@@ -584,8 +584,16 @@ class ZkMatrix {
         for (size_t i = 0; i < n; i++) ab_v.push_back(gate.inner_product(ctx, a.matrix[i], b_v, pabv.data() + i * k)); // :337
         for (size_t i = 0; i < n; i++) {                                                                               // :339-341
             const AssignedValue d = gate.sub(ctx, Existing(cs_v[i]), Existing(ab_v[i]), diff[i]);
-            gate.is_zero(ctx, d, isz[i], inv[i]);  // the returned boolean is discarded, as in the reference
+            const AssignedValue z = gate.is_zero(ctx, d, isz[i], inv[i]);
+            // The reference DISCARDS this boolean (gate.is_equal's result is never constrained, :339-341), so a wrong
+            // c_s still satisfies its circuit.  `strict` is this library's opt-in fix: z == 1.
+            if (strict) gate.assert_is_const(ctx, z, field::one());
         }
+    }
+    // verify_mul with the Freivalds result actually constrained (NOT the reference's constraint system)
+    static void verify_mul_strict(Context& ctx, const Chip& fpchip, const ZkMatrix& a, const ZkMatrix& b,
+                                  const AssignedMatrix& c_s, const AssignedValue& init_rand) {
+        verify_mul(ctx, fpchip, a, b, c_s, init_rand, true);
     }
     // rescale_matrix (:354-375): one signed_div_scale per element, row-major
     static ZkMatrix rescale_matrix(Context& ctx, const Chip& fpchip, const AssignedMatrix& c_s) {

@@ -158,6 +158,26 @@ int zkh_run_bad_shapes(int lb) {
         honest_prover_mat_mul(ctx, a.matrix, b.matrix);
     });
 }
+// A dishonest prover: c_s[0][0] is off by one.  The reference's verify_mul accepts it (the is_equal result is
+// discarded, src/matrix/mod.rs:339-341); verify_mul_strict (this library's opt-in fix) rejects it.
+int zkh_run_dishonest_product(int lb, int strict) {
+    return guarded(lb, [&] {
+        FixedPointChip041<32> fpchip(lb);
+        g_ctx.emplace_back(0);
+        g_ctx.emplace_back(1);
+        Context& ctx = g_ctx[0];
+        const ZkMatrix<32> a = ZkMatrix<32>::create(ctx, fpchip, {{1.5, -2.0, 0.25}, {3.0, 4.5, -1.0}});
+        const ZkMatrix<32> b = ZkMatrix<32>::create(ctx, fpchip, {{0.5, 1.0}, {-1.5, 2.0}, {2.5, -0.75}});
+        std::vector<std::vector<Fr>> c = field_mat_mul(a.matrix, b.matrix);
+        c[0][0] = field::add(c[0][0], field::one());
+        AssignedMatrix c_s;
+        for (const auto& row : c) c_s.push_back(ctx.assign_witnesses(row.data(), row.size()));
+        Context& ctx1 = g_ctx[1];
+        const AssignedValue init_rand = ctx1.load_witness(field::from_u64(0x9e3779b97f4a7c15ull));
+        if (strict) ZkMatrix<32>::verify_mul_strict(ctx1, fpchip, a, b, c_s, init_rand);
+        else ZkMatrix<32>::verify_mul(ctx1, fpchip, a, b, c_s, init_rand);
+    });
+}
 const char* zkh_error() { return g_error.c_str(); }
 const char* zkh_failure(int i) { return i < (int)g_fail.size() ? g_fail[i].c_str() : ""; }
 size_t zkh_ctx_count() { return g_ctx.size(); }

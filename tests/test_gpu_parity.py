@@ -241,6 +241,15 @@ def test_zkvec_inner_prefix_matches_oracle(handle, batch, ln):
     assert _eq(handle.zkvec_inner_prefix(x, s), corac.zkvec_inner_prefix(x, s, threads=0))
 
 
+def test_config1_full_size_zkvector_batch(handle):
+    """BASELINE configs[1] at full size: 4096 batched length-1024 vector pairs, P=32 -- inner-product running sums and qsub
+    differences bit-exact against the oracle (8 threads on the host)."""
+    rng = np.random.default_rng(41)
+    x, s = random_fr(rng, 4096, 1024), random_fr(rng, 4096, 1024)
+    assert _eq(handle.zkvec_inner_prefix(x, s), corac.zkvec_inner_prefix(x, s, threads=8))
+    assert _eq(handle.zkvec_sub(s, x), corac.zkvec_sub(s, x))
+
+
 def test_zkvec_sub_and_dist_pipeline(handle):
     rng = np.random.default_rng(21)
     P, lb = 32, 19

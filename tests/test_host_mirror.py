@@ -48,6 +48,7 @@ def _build(tmp, gpu: bool) -> ct.CDLL:
     lib.zkh_run_svd.argtypes = [ct.c_int, ct.c_int] + [ct.c_void_p] * 4 + [ct.c_size_t] * 3 + [ct.c_void_p]
     lib.zkh_run_mat_times_vec.argtypes = [ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_size_t]
     lib.zkh_run_bad_shapes.argtypes = [ct.c_int]
+    lib.zkh_run_dishonest_product.argtypes = [ct.c_int, ct.c_int]
     lib.zkh_ctx_export.argtypes = [ct.c_size_t] + [ct.c_void_p] * 7
     lib.zkh_scalars.argtypes = [ct.c_void_p]
     return lib
@@ -250,7 +251,24 @@ def test_host_mirror_shape_asserts_cpu(cpu_lib):
     assert b"a[0].len() == b.len()" in cpu_lib.zkh_error()
 
 
+def _check_dishonest(lib):
+    """The reference's verify_mul constrains nothing about the Freivalds comparison (is_equal result discarded,
+    src/matrix/mod.rs:339-341): a wrong product passes.  The opt-in strict variant rejects it in phase 1."""
+    assert lib.zkh_run_dishonest_product(19, 0) == 0, lib.zkh_error()
+    rc = lib.zkh_run_dishonest_product(19, 1)
+    assert rc == 1 and lib.zkh_failure(0).decode().startswith("ctx 1: constant violated"), (rc, lib.zkh_error())
+
+
+def test_verify_mul_reference_bug_and_strict_fix_cpu(cpu_lib):
+    _check_dishonest(cpu_lib)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_verify_mul_reference_bug_and_strict_fix_gpu(gpu_lib):
+    _check_dishonest(gpu_lib)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("P,lb,n,k,m", [(42, 19, 8, 8, 8), (32, 19, 3, 5, 4), (63, 19, 16, 12, 20), (32, 12, 2, 3, 2)])
 def test_host_mirror_zkmatrix_gpu(gpu_lib, P, lb, n, k, m):
