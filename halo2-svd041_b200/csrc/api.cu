@@ -553,7 +553,7 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
         if (bytes) H2SVD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, xs));
         return H2SVD_OK;
     };
-    // inputs: B and gamma first (the C-independent half of verify_mul starts at once), then A
+    // inputs: B and gamma first (the C-independent half of verify_mul starts at once); A follows slab by slab
     H2SVD_TRY(h2d(ctx, db, b, k * m * F));
     H2SVD_TRY(h2d(ctx, dg, gamma, F));
     H2SVD_TRY(launch_check_canonical(ctx, db, k * m, ctx->d_flag));
@@ -561,8 +561,6 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
     H2SVD_TRY(launch_gamma_powers(ctx, dg, m, dpow));                               // :316-326
     H2SVD_TRY(launch_mat_vec_prefix(ctx, db, dpow, k, m, 0, dpbv, dbv));            // :336
     H2SVD_CUDA(cudaEventRecord(ctx->ev[0], cs));
-    H2SVD_TRY(h2d(ctx, da, a, rows * k * F));
-    H2SVD_TRY(launch_check_canonical(ctx, da, rows * k, ctx->d_flag));
     H2SVD_CUDA(cudaStreamWaitEvent(xs, ctx->ev[0], 0));
     H2SVD_TRY(to_host(powers, dpow, m * F));
     H2SVD_TRY(to_host(prefix_bv, dpbv + bv_row0 * m, (bv_row1 - bv_row0) * m * F));
@@ -570,8 +568,13 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
     H2SVD_CUDA(cudaEventRecord(ctx->ev[2], xs));
     H2SVD_CUDA(cudaEventRecord(ctx->ev[3], xs));
     int buf = 0;
-    for (size_t r0 = 0; r0 < rows; r0 += slab, buf ^= 1) {
-        const size_t nr = rows - r0 < slab ? rows - r0 : slab;
+    for (size_t r0 = 0, nr = 0; r0 < rows; r0 += nr, buf ^= 1) {
+        // a short first slab gets the copy engine going early; after that the copies are the bottleneck anyway
+        const size_t want = r0 == 0 && slab >= 8 ? slab / 8 : slab;
+        nr = rows - r0 < want ? rows - r0 : want;
+        // A is uploaded slab by slab too: the first witnesses leave for the host after B + one slab of A, not after all of A
+        H2SVD_TRY(h2d(ctx, da + r0 * k, as_fr(a) + r0 * k, nr * k * F));
+        H2SVD_TRY(launch_check_canonical(ctx, da + r0 * k, nr * k, ctx->d_flag));
         H2SVD_TRY(launch_fr_matmul(ctx, da + r0 * k, db, dc + r0 * m, nr, k, m));                       // :546
         H2SVD_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2 + buf], 0));  // slab buffer `buf` drained two slabs ago
         H2SVD_TRY(launch_rescale(ctx, dc + r0 * m, nr * m, precision_bits, lookup_bits, shift_bits, a_num_bits,
