@@ -341,7 +341,8 @@ int rescale_params(int P, int lb, int S, int A, int* n_d, int* n_r) {
     if (nd * lb > 253 || nr * lb > 253) return -1;
     if (n_d) *n_d = nd;
     if (n_r) *n_r = nr;
-    return 4 + 4 * (nd + nr);
+    // per check_big_less_than_safe: range_check (2n-1) + chk, xp + range_check (2n-1) = 4n; only chk, xp when n == 1
+    return 4 + (nd >= 2 ? 4 * nd : 2) + (nr >= 2 ? 4 * nr : 2);
 }
 
 static int g_force_generic = 0;

@@ -124,7 +124,8 @@ int h2svd_mat_vec_prefix(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, s
  * matrix entry), and out_wit[e*W .. (e+1)*W) = the W `Witness`-kind advice values of that call in
  * assignment order (a_shift, rem, div, 4 limb-decomposition blocks, q).
  * shift_bits / a_num_bits are the chip's constants (third-party, unpinned): pass -1 for the
- * defaults 3P / 4P.  h2svd_rescale_witness_count returns W (= 4 + 4(n_d + n_r)) or <0. */
+ * defaults 3P / 4P.  h2svd_rescale_witness_count returns W (= 4 + f(n_d) + f(n_r) with f(n) = 4n, or 2 when
+ * n == 1: a one-limb range check emits no limb cells) or <0. */
 int h2svd_rescale_witness_count(int precision_bits, int lookup_bits, int shift_bits,
                                 int a_num_bits);
 int h2svd_rescale_witness(h2svd_ctx *ctx, const h2svd_fr *c_s, size_t count, int precision_bits,

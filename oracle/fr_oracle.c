@@ -260,7 +260,8 @@ int orc_rescale_witness_count(int P, int lb, int S, int A) {
     if (P < 1 || P > 63 || lb < 1 || lb > 32 || S < P || S > 252 || A <= P) return -1;
     int n_d = ceil_div(A - P + 1, lb), n_r = ceil_div(P + 1, lb);
     if (n_d * lb > 253 || n_r * lb > 253) return -1;
-    return 4 + 4 * (n_d + n_r);
+    /* per check_big_less_than_safe: range_check (2n-1) + chk, xp + range_check (2n-1) = 4n; only chk, xp when n == 1 */
+    return 4 + (n_d >= 2 ? 4 * n_d : 2) + (n_r >= 2 ? 4 * n_r : 2);
 }
 
 static orc_fr *emit(orc_fr *w, const uint64_t x[4]) {

@@ -47,7 +47,7 @@ int orc_gamma_powers(const orc_fr *gamma, size_t d, orc_fr *out);
 int orc_mat_vec_prefix(const orc_fr *a, const orc_fr *v, size_t rows, size_t len, orc_fr *out,
                        int threads);
 
-/* Witness-count helper for signed_div_scale: W = 4 + 4(n_d+n_r) */
+/* Witness-count helper for signed_div_scale: W = 4 + f(n_d) + f(n_r), f(n) = 4n (n >= 2) or 2 (n == 1) */
 int orc_rescale_witness_count(int precision_bits, int lookup_bits, int shift_bits, int a_num_bits);
 
 /* reference src/matrix/mod.rs:354-375 rescale_matrix -> per element

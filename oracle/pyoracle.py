@@ -149,8 +149,10 @@ class RescaleParams:
         return -(-(self.precision_bits + 1) // self.lookup_bits)
 
     @property
-    def W(self) -> int:  # Witness values per element
-        return 4 + 4 * (self.n_d + self.n_r)
+    def W(self) -> int:  # Witness values per element: 4n per check_big_less_than_safe, 2 when its n == 1
+        def cbl(n):
+            return 4 * n if n >= 2 else 2
+        return 4 + cbl(self.n_d) + cbl(self.n_r)
 
     @property
     def cells(self) -> int:  # advice cells per element

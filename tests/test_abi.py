@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_parameter_helpers_need_no_gpu(pkg):
     lib = pkg._ffi.load()
-    # W = 4 + 4(n_d + n_r), SURVEY.md A.5
+    # W = 4 + 4(n_d + n_r) for n_d, n_r >= 2; a one-limb check_big_less_than_safe has 2 witnesses
+    assert lib.h2svd_rescale_witness_count(15, 32, 39, 30) == 8
     assert lib.h2svd_rescale_witness_count(63, 19, -1, -1) == 60
     assert lib.h2svd_rescale_witness_count(32, 19, -1, -1) == 36
     assert lib.h2svd_rescale_witness_count(42, 19, -1, -1) == 44
