@@ -233,7 +233,8 @@ def test_host_mirror_svd_circuit_cpu(cpu_lib, n, mm, P):
     _check_svd(cpu_lib, n, mm, P, 19)
 
 
-@pytest.mark.parametrize("P,lb,n,k,m", [(42, 19, 8, 8, 8), (32, 19, 3, 5, 4), (63, 19, 4, 4, 4), (32, 12, 2, 3, 2)])
+@pytest.mark.parametrize("P,lb,n,k,m", [(42, 19, 8, 8, 8), (32, 19, 3, 5, 4), (63, 19, 4, 4, 4), (32, 12, 2, 3, 2),
+                                        (32, 32, 2, 2, 3), (63, 8, 2, 3, 2), (42, 25, 3, 2, 2)])
 def test_host_mirror_zkmatrix_cpu(cpu_lib, P, lb, n, k, m):
     _check_zkmatrix(cpu_lib, P, lb, n, k, m, seed=100 + P + n)
 
@@ -270,7 +271,8 @@ def test_verify_mul_reference_bug_and_strict_fix_gpu(gpu_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("P,lb,n,k,m", [(42, 19, 8, 8, 8), (32, 19, 3, 5, 4), (63, 19, 16, 12, 20), (32, 12, 2, 3, 2)])
+@pytest.mark.parametrize("P,lb,n,k,m", [(42, 19, 8, 8, 8), (32, 19, 3, 5, 4), (63, 19, 16, 12, 20), (32, 12, 2, 3, 2),
+                                        (32, 32, 2, 2, 3), (63, 8, 2, 3, 2), (42, 25, 3, 2, 2)])
 def test_host_mirror_zkmatrix_gpu(gpu_lib, P, lb, n, k, m):
     """BASELINE configs[0] shape (8x8, P=42, lb=19) and friends through the CUDA library."""
     _check_zkmatrix(gpu_lib, P, lb, n, k, m, seed=100 + P + n)
