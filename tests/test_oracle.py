@@ -194,3 +194,50 @@ def test_c_oracle_mat_times_diag():
     v = [rng.randrange(po.R_MOD) for _ in range(4)]
     got = corac.mat_times_diag(po.pack_mont(sum(a, [])).reshape(3, 5, 4), po.pack_mont(v))
     assert po.unpack_mont(got) == [a[i][j] * v[j] % po.R_MOD for i in range(3) for j in range(4)]
+
+
+def test_fr_modulus_is_the_order_of_the_reference_srs_points():
+    """The reference ships KZG SRS blobs (params/kzg_bn254_*.srs); their G1 points [tau^i]G lie on BN254
+    (y^2 = x^3 + 3 over Fq) and have order r.  [r]P = O and [r-1]P = -P for those points pins the Fr modulus the whole
+    witness path computes in against data from the reference tree itself (fixture: tests/golden/srs_g1_points.json,
+    extracted by tests/golden/make_srs_points.py)."""
+    import json
+    import os
+    from tests.util import ROOT
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "srs_g1_points.json")))
+    q = 21888242871839275222246405745257275088696311157297823662689037894645226208583   # BN254 base field
+    rinv = pow(1 << 256, -1, q)
+
+    def add(P, Q):
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        (x1, y1), (x2, y2) = P, Q
+        if x1 == x2:
+            if (y1 + y2) % q == 0:
+                return None
+            lam = 3 * x1 * x1 * pow(2 * y1, -1, q) % q
+        else:
+            lam = (y2 - y1) * pow(x2 - x1, -1, q) % q
+        x3 = (lam * lam - x1 - x2) % q
+        return x3, (lam * (x1 - x3) - y1) % q
+
+    def mul(k, P):
+        acc = None
+        while k:
+            if k & 1:
+                acc = add(acc, P)
+            P = add(P, P)
+            k >>= 1
+        return acc
+
+    assert len(fx["points"]) >= 4
+    for p in fx["points"]:
+        x = int.from_bytes(bytes.fromhex(p["x_mont_le_hex"]), "little") * rinv % q
+        y = int.from_bytes(bytes.fromhex(p["y_mont_le_hex"]), "little") * rinv % q
+        assert (y * y - x * x * x - 3) % q == 0, "not on BN254"
+        assert mul(po.R_MOD, (x, y)) is None, "Fr modulus is not the order of the reference's SRS point"
+        assert mul(po.R_MOD - 1, (x, y)) == (x, (-y) % q)
+    g = fx["points"][0]
+    assert int.from_bytes(bytes.fromhex(g["x_mont_le_hex"]), "little") * rinv % q == 1     # g[0] is the generator (1, 2)
