@@ -223,6 +223,8 @@ def run_gpu(args) -> None:
     side = wl.SideStream(torch, h_side, side_stream, stream)
 
     n = k = m = args.n
+    if args.shape:       # e.g. --shape 4096,2048,4096 = BASELINE configs[4] (not the headline configuration)
+        n, k, m = (int(x) for x in args.shape.split(","))
     plan = wl.ShardPlan(n, k, m, world, rank)
     W = h.rescale_witness_count(P_BITS, LOOKUP_BITS)
     bufs = wl.alloc_buffers(torch, plan, W, device)
@@ -246,13 +248,17 @@ def run_gpu(args) -> None:
         pb = pkg.PinnedBuffer(tuple(t.shape), np.uint64)
         return pb
 
+    do_e2e = not args.no_e2e
+    if not do_e2e:
+        pinned_like = lambda t: pkg.PinnedBuffer((1, 4), np.uint64)   # noqa: E731  (placeholders, never used)
     pin_in = {"a": pinned_like(bufs.a_slab), "b": pinned_like(bufs.b)}
-    pin_in["a"].array[...] = bufs.a_slab.cpu().numpy().view(np.uint64)
-    pin_in["b"].array[...] = bufs.b.cpu().numpy().view(np.uint64)
+    if do_e2e:
+        pin_in["a"].array[...] = bufs.a_slab.cpu().numpy().view(np.uint64)
+        pin_in["b"].array[...] = bufs.b.cpu().numpy().view(np.uint64)
     out_shapes = {"c_s": (r1 - r0, m), "q": (r1 - r0, m), "wit": ((r1 - r0) * m, W), "powers": (m,),
                   "prefix_cv": (r1 - r0, m), "prefix_bv": (b1 - b0, m), "prefix_abv": (r1 - r0, k), "diff": (r1 - r0,),
                   "is_zero": (r1 - r0,), "inv": (r1 - r0,)}
-    pin_out = {nm: pkg.PinnedBuffer(shp + (4,), np.uint64) for nm, shp in out_shapes.items()}
+    pin_out = {nm: pkg.PinnedBuffer((shp if do_e2e else (1,) * len(shp)) + (4,), np.uint64) for nm, shp in out_shapes.items()}
     host_out = {nm: pb.array for nm, pb in pin_out.items()}
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
 
@@ -321,12 +327,12 @@ def run_gpu(args) -> None:
     ms_step, ms_mm, ms_rs, ms_fr = [float(x) for x in my_ms.cpu()]
 
     # ---- end-to-end timing (host buffers, copies inside the timed region) ----
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(max(1, min(args.warmup, 3)) if do_e2e else 0):
         e2e_step()
     barrier()
     e2e_steps = args.steps
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(e2e_steps if do_e2e else 0):
         e2e_step()             # synchronous: returns when the step's results are on the host
     t_mine = (time.perf_counter() - t0) / e2e_steps
     barrier()
@@ -344,10 +350,10 @@ def run_gpu(args) -> None:
     h2d_all, d2h_all = [int(x) for x in bytes_t.cpu()]
 
     # ---- sanity: the timed buffers hold a correct witness (honest product => every diff is zero)
-    ok = bool((bufs.diff == 0).all().item()) and not host_out["diff"].any()
+    ok = bool((bufs.diff == 0).all().item()) and (not do_e2e or not host_out["diff"].any())
     # both legs computed the same witness: the fused host call and the device-resident building blocks agree
-    for nm, dev_t in (("c_s", bufs.c_slab), ("q", bufs.q_slab), ("prefix_cv", bufs.prefix_cv), ("prefix_abv", bufs.prefix_abv),
-                      ("wit", bufs.wit_slab)):
+    for nm, dev_t in ((("c_s", bufs.c_slab), ("q", bufs.q_slab), ("prefix_cv", bufs.prefix_cv), ("prefix_abv", bufs.prefix_abv),
+                       ("wit", bufs.wit_slab)) if do_e2e else ()):
         ok = ok and bool((torch.from_numpy(host_out[nm].view(np.int64)).to(device) == dev_t).all().item())
     if not ok:
         raise SystemExit("bench: witness check failed -- refusing to report a number for wrong results")
@@ -368,12 +374,15 @@ def run_gpu(args) -> None:
         fr_bytes = 2.0 * 32.0 * (rows * m + rows * k + (0 if overlap else (b1 - b0) * m))   # mat-vecs inside the timed phase
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if (n, k, m) == (N_DEFAULT,) * 3 else f"Fr mul-add/s for mat-mul+Freivalds+rescale witness, {n}x{k}x{m}",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32x8 (BN254 Fr, 256-bit modular)", "data": "synthetic",
-            "config": {"workload": f"honest_prover_mat_mul + rescale_matrix + verify_mul witness, square N={n}, "
-                                   f"PRECISION_BITS={P_BITS}, LOOKUP_BITS={LOOKUP_BITS} (BASELINE configs[3] + "
-                                   f"Freivalds)", "n": n, "sharding": f"rows of A/C over {world} rank(s), B replicated, "
+            "config": {"workload": (f"honest_prover_mat_mul + rescale_matrix + verify_mul witness, square N={n}, "
+                                    f"PRECISION_BITS={P_BITS}, LOOKUP_BITS={LOOKUP_BITS} (BASELINE configs[3] + Freivalds)")
+                       if n == k == m else
+                       (f"honest_prover_mat_mul + rescale_matrix + verify_mul witness, {n}x{k} . {k}x{m}, "
+                        f"PRECISION_BITS={P_BITS}, LOOKUP_BITS={LOOKUP_BITS}"), "n": n, "k": k, "m": m, "sharding": f"rows of A/C over {world} rank(s), B replicated, "
                                    "(B v) all-gathered", "l2": "256 MiB flush write between timed steps",
                        "inputs": "input-creator.py distribution, seeded, quantized on the GPU"},
             "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds_after_matmul": ms_fr, "freivalds_pre_overlapped_with_matmul": bool(overlap)},
@@ -394,7 +403,7 @@ def run_gpu(args) -> None:
                 "freivalds": {"bound": "hbm", "achieved": fr_bytes / (ms_fr * 1e-3) / 1e9, "peak": hbm_peak,
                               "unit": "GB/s", "frac": fr_bytes / (ms_fr * 1e-3) / 1e9 / hbm_peak},
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
-            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+            "e2e": {"value": units / (e2e_ms * 1e-3) if do_e2e else None, "unit": UNIT, "ms_per_step": e2e_ms if do_e2e else None,
                     "wall_ms_per_step": e2e_wall * 1e3, "h2d_bytes_per_step": h2d_all,
                     "d2h_bytes_per_step": d2h_all,
                     "api": "h2svd_zkmatrix_mul_witness (C ABI, pinned host buffers in/out, slab-pipelined D2H) per rank",
@@ -403,7 +412,9 @@ def run_gpu(args) -> None:
             "verified": "Freivalds diff == 0; fused host call and device building blocks byte-identical",
         }
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_sample(n, 1, mm_rows=256, rs_elems=262144)   # ~15 s of single-thread CPU work
+            cb = cpu_sample(n, 1, mm_rows=256, rs_elems=262144) if n == k == m else None   # ~15 s of 1-thread CPU work
+            if cb is None:
+                cb = {"value": None, "sample": "square jobs only", "t_sample_s": 0.0}
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": cb["sample"] + f" ({cb['t_sample_s']:.1f} s of CPU work, 1 thread: "
                                                              "the reference is single-threaded)"}
@@ -423,7 +434,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--shape", type=str, default="", help="n,k,m of a rectangular job (default: square --n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (large rectangular jobs: pinned host memory)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rules: W >= 3
