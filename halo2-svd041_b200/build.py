@@ -27,10 +27,15 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(f) for f in files)
 
 
+# per-file extra flags (tuning hook: H2SVD_EXTRA_FLAGS_matmul="-Xptxas -O1")
+def _extra(src: str):
+    return os.environ.get("H2SVD_EXTRA_FLAGS_" + src.replace(".cu", ""), "").split()
+
+
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     log = obj + ".log"
-    cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC, *FLAGS, *_extra(src), "-c", os.path.join(CSRC, src), "-o", obj]
     with open(log, "w") as fh:
         rc = subprocess.call(cmd, stdout=fh, stderr=subprocess.STDOUT)
     if rc != 0:
