@@ -134,8 +134,10 @@ fr_matmul_kernel(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restr
 #pragma unroll
         for (int j = 0; j < TN; j++) fr::acc_clear(acc[i][j]);
 
+    const int warp = tid >> 5;
     for (int c = 0; c < nchunks; c++) {
-        if (is_issuer && c + PD < nchunks) {
+        // rotating issuer: warp (c mod 8) stages chunk c + PD (no single warp carries the issue work of every chunk)
+        if (warp == (c & (WARPS - 1)) && c + PD < nchunks) {
             if (c >= 2) mbar_wait(&empty_bar[(c - 2) % STAGES], ((c - 2) / STAGES) & 1);
             issue_chunk(c + PD);
         }
@@ -262,9 +264,10 @@ __device__ __noinline__ int sk_segment(int i) {
     const Fr* pA0 = sA + (threadIdx.x / TX) * BK;   // hoisted: fewer live temporaries in the unit loop
     const Fr* pB0 = sB + (threadIdx.x % TX);
     for (int c = 0; c < cnt; c++, i++) {
-        if (threadIdx.x < 32 && i + PD < sh->nloc) {
+        // rotating issuer (see sk_segment_k): warp (i mod 8) stages unit i + PD
+        if ((int)(threadIdx.x >> 5) == (i & (WARPS - 1)) && i + PD < sh->nloc) {
             if (i >= 2) mbar_wait(&sh->empty_bar[(i - 2) % STAGES], ((i - 2) / STAGES) & 1);
-            sk_issue_unit<TM, TN, BK, STAGES>(i + PD, (int)threadIdx.x);
+            sk_issue_unit<TM, TN, BK, STAGES>(i + PD, (int)(threadIdx.x & 31));
         }
         s = i % STAGES;
         mbar_wait(&sh->full_bar[s], (i / STAGES) & 1);
@@ -457,8 +460,10 @@ fr_matmul_kara_kernel(const KOp* __restrict__ A, const KOp* __restrict__ B, Fr* 
     fr::kacc_clear(p1);
     fr::kacc_clear(p2);
 
+    const int warp = tid >> 5;
     for (int c = 0; c < nchunks; c++) {
-        if (is_issuer && c + PD < nchunks) {
+        // rotating issuer: warp (c mod 8) stages chunk c + PD, so no single warp carries the TMA issue work of every chunk
+        if (warp == (c & (WARPS - 1)) && c + PD < nchunks) {
             if (c >= 2) mbar_wait(&empty_bar[(c - 2) % STAGES], ((c - 2) / STAGES) & 1);
             issue_chunk(c + PD);
         }
@@ -573,9 +578,11 @@ __device__ __noinline__ int sk_segment_k(int i) {
     const KOp* pA0 = sA + (threadIdx.x / TX) * BK;   // hoisted: fewer live temporaries in the unit loop
     const KOp* pB0 = sB + (threadIdx.x % TX);
     for (int c = 0; c < cnt; c++, i++) {
-        if (threadIdx.x < 32 && i + PD < sh->nloc) {
+        // ROTATING issuer: warp (i mod 8) stages unit i + PD, so the ~150 instructions of coordinate arithmetic and TMA
+        // issue are spread over all warps instead of making warp 0 the critical path of every unit (+12 % on one warp)
+        if ((int)(threadIdx.x >> 5) == (i & (WARPS - 1)) && i + PD < sh->nloc) {
             if (i >= 2) mbar_wait(&sh->empty_bar[(i - 2) % STAGES], ((i - 2) / STAGES) & 1);
-            sk_issue_unit_k<BK, STAGES>(i + PD, (int)threadIdx.x);
+            sk_issue_unit_k<BK, STAGES>(i + PD, (int)(threadIdx.x & 31));
         }
         s = i % STAGES;
         mbar_wait(&sh->full_bar[s], (i / STAGES) & 1);
