@@ -103,6 +103,10 @@ __device__ __forceinline__ void st_fr_cs(Fr* p, const Fr& v) {
 int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m);
 int launch_fr_matmul_naive(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k,
                            size_t m);
+// tensor-core engine of the mat-mul (matmul_tc.cu)
+extern int g_matmul_tc;
+bool fr_matmul_tc_supported(size_t n, size_t k, size_t m);
+int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m);
 int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t cols);
 int launch_gamma_powers(h2svd_ctx* ctx, const Fr* gamma, size_t d, Fr* out);
 // totals (optional): last running sum of every row

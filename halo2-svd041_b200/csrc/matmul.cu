@@ -814,6 +814,7 @@ int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, 
         set_error("fr_matmul: dimension too large");
         return H2SVD_EINVAL;
     }
+    if (g_matmul_tc == 1 && fr_matmul_tc_supported(n, k, m)) return launch_fr_matmul_tc(ctx, a, b, c, n, k, m);
     // Karatsuba engine (48 instead of 64 IMAD.WIDE per multiply-add; measured 147 vs 129 G mul-add/s at N=1024) unless
     // the product is too small for the O(N^2) operand split and the two extra launches to pay off
     if (g_kara == 1) return launch_kara<16, 3, 2>(ctx, a, b, c, (int)n, (int)k, (int)m);

@@ -350,6 +350,11 @@ def set_matmul_karatsuba(v: int) -> None:
     _ffi.load().h2svd_debug_set_matmul_karatsuba(v)
 
 
+def set_matmul_tc(v: int) -> None:
+    """Triage hook: -1 auto, 0 never, 1 always use the tensor-core (tcgen05 kind::i8) mat-mul engine."""
+    _ffi.load().h2svd_debug_set_matmul_tc(v)
+
+
 def set_matmul_streamk(v: int) -> None:
     """Triage hook: -1 auto (default), 0 never, 1 always use the stream-K mat-mul schedule."""
     _ffi.load().h2svd_debug_set_matmul_streamk(v)
