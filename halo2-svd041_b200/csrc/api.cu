@@ -60,6 +60,10 @@ static int check_flag(h2svd_ctx* ctx, const char* what) {
     H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
     if (flag) {
         H2SVD_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+        if (flag == 3) {  // a bounded pipeline wait of the tensor-core mat-mul expired (it traps: normally unreachable)
+            set_error("%s: internal error: tensor-core mat-mul pipeline timed out", what);
+            return H2SVD_ECUDA;
+        }
         set_error("%s: operand out of range / non-canonical field element", what);
         return H2SVD_ERANGE;
     }

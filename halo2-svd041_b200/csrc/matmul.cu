@@ -814,7 +814,12 @@ int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, 
         set_error("fr_matmul: dimension too large");
         return H2SVD_EINVAL;
     }
-    if (g_matmul_tc == 1 && fr_matmul_tc_supported(n, k, m)) return launch_fr_matmul_tc(ctx, a, b, c, n, k, m);
+    // Tensor-core engine (matmul_tc.cu: u8 byte planes on tcgen05, ~12x the IMAD engines at N=1024; measured with
+    // tools/tc_check.py: ahead from 64^3 on, behind for very short k where its per-element epilogue dominates).
+    // Forcing one of the IMAD engines / schedules through the triage hooks switches the automatic choice off.
+    const bool imad_forced = g_kara >= 0 || g_streamk >= 0 || g_variant != 0;
+    const bool tc = g_matmul_tc == 1 || (g_matmul_tc < 0 && !imad_forced && k >= 32 && n * k * m >= (1ull << 18));
+    if (tc && fr_matmul_tc_supported(n, k, m)) return launch_fr_matmul_tc(ctx, a, b, c, n, k, m);
     // Karatsuba engine (48 instead of 64 IMAD.WIDE per multiply-add; measured 147 vs 129 G mul-add/s at N=1024) unless
     // the product is too small for the O(N^2) operand split and the two extra launches to pay off
     if (g_kara == 1) return launch_kara<16, 3, 2>(ctx, a, b, c, (int)n, (int)k, (int)m);

@@ -353,7 +353,7 @@ tc_encode_fn tc_encoder() {
 
 }  // namespace
 
-int g_matmul_tc = 0;  // -1 auto, 0 off, 1 force (triage hook; see launch_fr_matmul)
+int g_matmul_tc = -1;  // -1 auto, 0 off, 1 force (triage hook; see launch_fr_matmul)
 
 bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
     // p * n + ib * 128 and the plane sizes are 32-bit TMA coordinates / comfortably below 2^31

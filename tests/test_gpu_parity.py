@@ -83,6 +83,54 @@ def test_fr_matmul_karatsuba_engine(handle, pkg, kara, streamk, n, k, m):
     assert _eq(got, corac.field_mat_mul(a, b))
 
 
+@pytest.mark.parametrize("n,k,m", [(8, 8, 8), (1, 1, 1), (5, 7, 3), (33, 100, 47), (64, 17, 31), (130, 300, 20),
+                                   (128, 1024, 256), (200, 2100, 9), (129, 1025, 17), (256, 256, 256)])
+def test_fr_matmul_tensor_core_engine(handle, pkg, n, k, m):
+    """Tensor-core engine (tcgen05 kind::i8 over the 32 byte planes of each operand, the 63 diagonal sums
+    overlap-added in TMEM, one Montgomery reduction per element) forced on for every shape, incl. ragged tiles,
+    k tails, k > 1024 (several accumulation passes) and adversarial operands: same bytes as the oracle."""
+    rng = np.random.default_rng(n * 13 + k)
+    a, b = random_fr(rng, n, k), random_fr(rng, k, m)
+    adv = adversarial_fr()
+    a.reshape(-1, 4)[: min(len(adv), n * k)] = adv[: n * k]
+    b.reshape(-1, 4)[-min(len(adv), k * m):] = adv[: min(len(adv), k * m)]
+    try:
+        pkg.set_matmul_tc(1)
+        got = handle.fr_matmul(a, b)
+        pkg.set_matmul_tc(0)
+        imad = handle.fr_matmul(a, b)
+    finally:
+        pkg.set_matmul_tc(-1)
+    assert _eq(got, imad)
+    if n * k * m <= 1 << 22:
+        assert _eq(got, corac.field_mat_mul(a, b))
+    else:
+        rows = [0, n // 2, n - 1]
+        assert _eq(got[rows], corac.field_mat_mul(np.ascontiguousarray(a[rows]), b))
+
+
+def test_fr_matmul_tensor_core_worst_case_accumulation(handle, pkg):
+    """Every product (r-1)^2 and every byte of one operand 0xff-heavy, k = 4096 (four accumulation passes):
+    the per-diagonal sums stay below 2^31 by construction (32 * 1024 * 255^2), so this must be exact."""
+    try:
+        pkg.set_matmul_tc(1)
+        big = np.ascontiguousarray(np.broadcast_to(raw_limbs([po.R_MOD - 1])[0], (3, 4096, 4)))
+        bigt = np.ascontiguousarray(np.broadcast_to(raw_limbs([po.R_MOD - 1])[0], (4096, 5, 4)))
+        c = handle.fr_matmul(big, bigt)
+        exp = 4096 * (po.R_MOD - 1) ** 2 * po.MONT_RINV % po.R_MOD
+        assert [int(x) for x in c[0, 0]] == [int(x) for x in raw_limbs([exp])[0]]
+        assert _eq(c, np.broadcast_to(c[0, 0], c.shape))
+        # the largest canonical value whose low 31 bytes are all 0xff
+        ff = (0x2f << 248) | ((1 << 248) - 1)
+        x = np.ascontiguousarray(np.broadcast_to(raw_limbs([ff])[0], (2, 1024, 4)))
+        y = np.ascontiguousarray(np.broadcast_to(raw_limbs([ff])[0], (1024, 2, 4)))
+        c = handle.fr_matmul(x, y)
+        exp = 1024 * ff * ff * po.MONT_RINV % po.R_MOD
+        assert [int(v) for v in c[1, 1]] == [int(v) for v in raw_limbs([exp])[0]]
+    finally:
+        pkg.set_matmul_tc(-1)
+
+
 def test_fr_matmul_adversarial_operands(handle):
     adv = adversarial_fr()  # 0, 1, r-1, R, R^2, 2^253, ...
     k = adv.shape[0]
