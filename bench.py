@@ -363,13 +363,38 @@ def run_gpu(args) -> None:
     line = None
     if rank == 0:
         peaks = measured_peaks()
-        # roofline of the dominant kernel (fr_matmul): integer-pipe bound.  Algorithmic work = 128
-        # IMAD-pipe slots per Fr mul-add; peak = IMAD issue rate measured live.
-        imad_peak = h.microbench_imad(0, 3000)
-        wide_peak = h.microbench_imad(2, 3000)
         rows = r1 - r0
-        mm_imads = rows * k * m * 128.0
-        achieved = mm_imads / (ms_mm * 1e-3)
+        engine = pkg.last_matmul_engine()
+        if engine == "tensor":
+            # roofline of the dominant kernel (fr_matmul_tc_kernel): tensor-pipe bound.  Algorithmic work = 1024 u8
+            # multiply-adds (2048 ops) per Fr mul-add: 32 x 32 byte-plane products (DESIGN.md "K1t").  Peak = twice the
+            # measured dense bf16 rate (8-bit operands run at twice the 16-bit rate on the same pipe).
+            bf16 = peaks.get("bf16_tflops")
+            tensor_peak = 2.0 * (bf16 if bf16 else 1590.0)
+            ops = rows * k * m * 2048.0
+            achieved_t = ops / (ms_mm * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "fr_matmul_tc_kernel (tcgen05.mma kind::i8, u8 x u8 -> s32 in TMEM) + the two "
+                                                     "byte-plane split kernels, which are inside the timed phase",
+                        "achieved": achieved_t, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_t / tensor_peak,
+                        "op": "u8 multiply-add = 2 ops; 1024 multiply-adds per Fr mul-add",
+                        "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst: the kernel runs ~0.6 ms per step); the cuBLAS "
+                                        "bf16 GEMM behind that figure reaches 73 % of the nominal pipe rate, so frac can exceed 1"
+                                        if bf16 else "2 x 1590 TF/s of fallback (B200_PROFILING.md)"),
+                        "frac_of_nominal": achieved_t / 4500.0, "nominal_peak": 4500.0,
+                        "traffic": traffic_from_profile("fr_matmul_tc_kernel", n) if world == 1 else None,
+                        "traffic_source": "profiles/traffic.json (ncu --set full capture of this command, bytes per launch)"}
+        else:
+            # IMAD engines (small or very short-k products): integer-pipe bound.  Algorithmic work = 128 IMAD-pipe slots
+            # per Fr mul-add; peak = IMAD issue rate measured live.
+            imad_peak = h.microbench_imad(0, 3000)
+            achieved = rows * k * m * 128.0 / (ms_mm * 1e-3)
+            roofline = {"bound": "imad", "kernel": "fr_matmul_kara_kernel" if engine == "karatsuba" else "fr_matmul_kernel",
+                        "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": achieved / imad_peak,
+                        "peak_source": "measured live: mad.lo.u32 micro-benchmark, all SMs (h2svd_microbench_imad kind 0)",
+                        "algorithmic": "SURVEY 8(d): 128 IMAD-pipe slots per Fr mul-add (8x8-limb schoolbook); the Karatsuba "
+                                       "kernel executes 108 (profiles/r01c_ncu_full_summary.md), so frac can exceed 1",
+                        "traffic": traffic_from_profile("fr_matmul_kara_kernel", n) if world == 1 else None,
+                        "traffic_source": "profiles/traffic.json"}
         rs_bytes = rows * m * 32.0 * (1 + W)
         fr_bytes = 2.0 * 32.0 * (rows * m + rows * k + (0 if overlap else (b1 - b0) * m))   # mat-vecs inside the timed phase
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -386,17 +411,7 @@ def run_gpu(args) -> None:
                                    "(B v) all-gathered", "l2": "256 MiB flush write between timed steps",
                        "inputs": "input-creator.py distribution, seeded, quantized on the GPU"},
             "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds_after_matmul": ms_fr, "freivalds_pre_overlapped_with_matmul": bool(overlap)},
-            "roofline": {"bound": "imad", "kernel": "fr_matmul_kara_kernel (stream-K variant on row slabs)",
-                         "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": achieved / imad_peak,
-                         "peak_source": "measured live: mad.lo.u32 micro-benchmark, all SMs (h2svd_microbench_imad kind 0)",
-                         "algorithmic": "SURVEY 8(d): 128 IMAD-pipe slots per Fr mul-add (8x8-limb schoolbook, 64 IMAD.WIDE at half "
-                                        "rate); frac can exceed 1 because the kernel is one-level Karatsuba (48 IMAD.WIDE)",
-                         "executed_imad_slots_per_muladd": 108.2,
-                         "imad_pipe_utilization": (rows * k * m * 108.2 / (ms_mm * 1e-3)) / imad_peak,
-                         "executed_source": "profiles/r01c_ncu_full_summary.md: 48 IMAD.WIDE (2 slots) + 6 IMAD.MOV + 6 IMAD.X per mul-add",
-                         "imad_wide_chain_peak": wide_peak / 1e12,
-                         "traffic": traffic_from_profile("fr_matmul_kara_kernel", n) if world == 1 else None,
-                         "traffic_source": "profiles/traffic.json (ncu --set full capture of this command, bytes per launch)"},
+            "roofline": roofline, "matmul_engine": engine,
             "roofline_hbm": {
                 "rescale": {"bound": "hbm", "achieved": rs_bytes / (ms_rs * 1e-3) / 1e9, "peak": hbm_peak,
                             "unit": "GB/s", "frac": rs_bytes / (ms_rs * 1e-3) / 1e9 / hbm_peak},

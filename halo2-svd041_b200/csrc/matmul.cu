@@ -749,6 +749,7 @@ int launch_variant(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k
 
 }  // namespace
 
+static int g_last_engine = -1;  // engine of the last mat-mul launch: 0 schoolbook, 1 Karatsuba, 2 tensor core
 static int g_kara = -1;  // -1 auto, 0 schoolbook kernels only, 1..3 force a Karatsuba variant (triage hook)
 
 template <int BK, int STAGES, int MINBLOCKS>
@@ -819,7 +820,11 @@ int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, 
     // Forcing one of the IMAD engines / schedules through the triage hooks switches the automatic choice off.
     const bool imad_forced = g_kara >= 0 || g_streamk >= 0 || g_variant != 0;
     const bool tc = g_matmul_tc == 1 || (g_matmul_tc < 0 && !imad_forced && k >= 32 && n * k * m >= (1ull << 18));
-    if (tc && fr_matmul_tc_supported(n, k, m)) return launch_fr_matmul_tc(ctx, a, b, c, n, k, m);
+    if (tc && fr_matmul_tc_supported(n, k, m)) {
+        g_last_engine = 2;
+        return launch_fr_matmul_tc(ctx, a, b, c, n, k, m);
+    }
+    g_last_engine = (g_kara >= 1 || (g_kara < 0 && k >= 64 && n * m >= 4096)) ? 1 : 0;
     // Karatsuba engine (48 instead of 64 IMAD.WIDE per multiply-add; measured 147 vs 129 G mul-add/s at N=1024) unless
     // the product is too small for the O(N^2) operand split and the two extra launches to pay off
     if (g_kara == 1) return launch_kara<16, 3, 2>(ctx, a, b, c, (int)n, (int)k, (int)m);
@@ -852,6 +857,7 @@ int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t
 
 }  // namespace h2svd
 
+extern "C" int h2svd_debug_last_matmul_engine(void) { return h2svd::g_last_engine; }
 extern "C" int h2svd_debug_set_matmul_variant(int v) {
     h2svd::g_variant = v;
     return 0;

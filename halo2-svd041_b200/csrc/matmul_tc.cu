@@ -17,8 +17,9 @@
 //   * per 128 bytes of K: one TMA load of the B operand (32 KB, shared by all p) and 32 TMA loads of A planes
 //     (16 KB each, 8-stage ring), 4 MMAs (K = 32 bytes each) per A plane: 128 x 256 x 32 MACs per instruction,
 //     the full-rate shape (128 cycles per instruction per SM).
-//   * epilogue (4 warps, thread = row i): reads the 63 diagonals of one (i, j) from TMEM, carries them into an
-//     18-limb integer, reduces, stores C; then re-zeroes its TMEM lanes for the next tile.
+//   * epilogue (16 warps: thread = row i, 4 warps per TMEM lane quarter with 2 columns j each): reads the 63
+//     diagonals of one (i, j) from TMEM, carries them into an 18-limb integer, reduces, stores C; then re-zeroes
+//     its own accumulator columns for the next tile.
 // Operands are pre-split into byte planes by two O(N^2) kernels (A8[p][i][k], B8[q][j][k], both K-major so that
 // TMA with the 128-byte swizzle delivers the canonical K-major UMMA layout).
 //
@@ -39,7 +40,9 @@ constexpr int TC_SB = 2;         // B buffers
 constexpr int TC_KB_PASS = 8;    // K blocks per accumulation pass: 1024 k values keep every diagonal below 2^31
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BKB;        // 16 KB
 constexpr uint32_t TC_B_BYTES = 32 * TC_BJ * TC_BKB;   // 32 KB
-constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int TC_EPI_WARPS = 16;  // 4 warps per TMEM lane quarter, each owning 2 of the 8 columns j of the tile
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
+constexpr int TC_JPW = TC_BJ / (TC_EPI_WARPS / 4);  // columns j per epilogue warp
 constexpr size_t TC_SMEM = (size_t)TC_SA * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES + 256 + 1024;
 // kind::i8 instruction descriptor: D = S32, A = B = unsigned 8-bit, both K-major, N = 256, M = 128
 constexpr uint32_t TC_IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
@@ -126,16 +129,36 @@ __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
     return v;
 }
-__device__ __forceinline__ void tc_st8_zero(uint32_t taddr) {
-    const uint32_t z = 0;
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(z),
-                 "r"(z), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z)
-                 : "memory");
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, uint32_t& v0, uint32_t& v1) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(taddr));
 }
-// this thread's TMEM lane, all 512 columns := 0, and hand the accumulators (back) to the MMA warp
-__device__ __forceinline__ void tc_zero_and_release(uint32_t tlane, uint32_t bar) {
-#pragma unroll 8
-    for (int cgrp = 0; cgrp < 64; cgrp++) tc_st8_zero(tlane + 8u * cgrp);
+// dg[0..63] (dg[63] = 0): the 63 diagonal sums of one C element  ->  T[0..17] = sum_d dg[d] * 2^(8d)
+__device__ __forceinline__ void tc_carry_diagonals(const uint32_t* dg, uint32_t* T) {
+    uint64_t cy = 0;
+#pragma unroll
+    for (int w = 0; w < 18; w++) {
+        const uint32_t y0 = w < 16 ? dg[4 * w] : 0u;
+        const uint32_t y1 = w < 16 ? dg[4 * w + 1] : 0u, y1p = (w >= 1 && w <= 16) ? dg[4 * w - 3] : 0u;
+        const uint32_t y2 = w < 16 ? dg[4 * w + 2] : 0u, y2p = (w >= 1 && w <= 16) ? dg[4 * w - 2] : 0u;
+        const uint32_t y3 = w < 16 ? dg[4 * w + 3] : 0u, y3p = (w >= 1 && w <= 16) ? dg[4 * w - 1] : 0u;
+        cy += y0;
+        cy += __funnelshift_l(y1p, y1, 8);
+        cy += __funnelshift_l(y2p, y2, 16);
+        cy += __funnelshift_l(y3p, y3, 24);
+        T[w] = (uint32_t)cy;
+        cy >>= 32;
+    }
+}
+__device__ __forceinline__ void tc_st2_zero(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(z), "r"(z) : "memory");
+}
+// this warp's accumulators (its TMEM lanes, its TC_JPW = 2 columns j of every diagonal) := 0, then hand them (back)
+// to the MMA warp.  Each warp reads and zeroes only its own columns, so the warps of a lane quarter never race.
+__device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, uint32_t bar) {
+    static_assert(TC_JPW == 2, "the zeroing store is two columns wide");
+#pragma unroll 9
+    for (int d = 0; d < 63; d++) tc_st2_zero(tcol0 + 8u * d);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     tc_mbar_arrive(bar);
@@ -200,7 +223,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             tc_mbar_init(empty_b + 8 * s, 1);
         }
         tc_mbar_init(tmem_full, 1);
-        tc_mbar_init(tmem_empty, 128);
+        tc_mbar_init(tmem_empty, 32 * TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -279,8 +302,9 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ===== epilogue: thread = row of the tile =====
         const uint32_t quarter = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int il = quarter * 32 + lane;
+        const int j0 = ((warp - 2) >> 2) * TC_JPW;  // this warp's columns j0, j0+1 of the tile
         const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
-        tc_zero_and_release(tlane, tmem_empty);
+        tc_zero_and_release(tlane + j0, tmem_empty);
         uint32_t round = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int ib = tile / tiles_j, jb = tile % tiles_j;
@@ -288,42 +312,37 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_full, round & 1, err);
                 tc_fence_after();
-                for (int j = 0; j < TC_BJ; j++) {
-                    uint32_t dg[64];
+                // Phase 1 (on the critical path of the next tile): read this warp's two columns j0, j0+1 of all 63
+                // diagonals and carry them into two 18-limb integers.  T = sum_d dg[d] * 2^(8d): diagonals d = 4g + r
+                // sit at whole-word offsets g for fixed r, so T = Y0 + (Y1 << 8) + (Y2 << 16) + (Y3 << 24) with
+                // Y_r[g] = dg[4g + r].
+                uint32_t da[64], db[64];
 #pragma unroll
-                    for (int d = 0; d < 63; d++) dg[d] = tc_ld1(tlane + 8u * d + j);
-                    dg[63] = 0;
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // pin the loaded registers behind the wait (the compiler must not read them earlier)
+                for (int d = 0; d < 63; d++) tc_ld2(tlane + 8u * d + j0, da[d], db[d]);
+                da[63] = 0;
+                db[63] = 0;
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // pin the loaded registers behind the wait (the compiler must not read them earlier)
 #pragma unroll
-                    for (int d = 0; d < 63; d++) asm volatile("" : "+r"(dg[d]));
-                    // T = sum_d dg[d] * 2^(8d): diagonals d = 4g + r sit at whole-word offsets g for fixed r,
-                    // so T = Y0 + (Y1 << 8) + (Y2 << 16) + (Y3 << 24) with Y_r[g] = dg[4g + r]
-                    uint32_t T[18];
-                    uint64_t cy = 0;
+                for (int d = 0; d < 63; d++) asm volatile("" : "+r"(da[d]), "+r"(db[d]));
+                uint32_t Ta[18], Tb[18];
+                tc_carry_diagonals(da, Ta);
+                tc_carry_diagonals(db, Tb);
+                // the accumulators are free again: zero them and let the MMA warp start the next tile while the
+                // Montgomery reductions below run
+                tc_fence_before();  // order the TMEM reads above before the zeroing stores / the next MMAs
+                tc_zero_and_release(tlane + j0, tmem_empty);
+                // Phase 2 (overlaps the next tile's MMAs)
 #pragma unroll
-                    for (int w = 0; w < 18; w++) {
-                        const uint32_t y0 = w < 16 ? dg[4 * w] : 0u;
-                        const uint32_t y1 = w < 16 ? dg[4 * w + 1] : 0u, y1p = (w >= 1 && w <= 16) ? dg[4 * w - 3] : 0u;
-                        const uint32_t y2 = w < 16 ? dg[4 * w + 2] : 0u, y2p = (w >= 1 && w <= 16) ? dg[4 * w - 2] : 0u;
-                        const uint32_t y3 = w < 16 ? dg[4 * w + 3] : 0u, y3p = (w >= 1 && w <= 16) ? dg[4 * w - 1] : 0u;
-                        cy += y0;
-                        cy += __funnelshift_l(y1p, y1, 8);
-                        cy += __funnelshift_l(y2p, y2, 16);
-                        cy += __funnelshift_l(y3p, y3, 24);
-                        T[w] = (uint32_t)cy;
-                        cy >>= 32;
-                    }
-                    Fr res = fr::reduce_wide_acc(T);
-                    const int gj = jb * TC_BJ + j;
+                for (int jj = 0; jj < TC_JPW; jj++) {
+                    Fr res = fr::reduce_wide_acc(jj == 0 ? Ta : Tb);
+                    const int gj = jb * TC_BJ + j0 + jj;
                     if (gi < n && gj < m) {
                         Fr* dst = c + (size_t)gi * m + gj;
                         if (pass > 0) res = fr::add(ld_fr(dst), res);
                         st_fr(dst, res);
                     }
                 }
-                tc_fence_before();  // order the TMEM reads above before the zeroing stores / the next MMAs
-                tc_zero_and_release(tlane, tmem_empty);
                 round++;
             }
         }

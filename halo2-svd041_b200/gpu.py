@@ -350,6 +350,11 @@ def set_matmul_karatsuba(v: int) -> None:
     _ffi.load().h2svd_debug_set_matmul_karatsuba(v)
 
 
+def last_matmul_engine() -> str:
+    """Which engine the last fr_matmul launch of this process used (bench.py reports the matching roofline)."""
+    return {0: "schoolbook", 1: "karatsuba", 2: "tensor"}.get(_ffi.load().h2svd_debug_last_matmul_engine(), "none")
+
+
 def set_matmul_tc(v: int) -> None:
     """Triage hook: -1 auto, 0 never, 1 always use the tensor-core (tcgen05 kind::i8) mat-mul engine."""
     _ffi.load().h2svd_debug_set_matmul_tc(v)
