@@ -232,7 +232,15 @@ def run_gpu(args) -> None:
     b0, b1 = plan.brows
     # Measured: under a full-size mat-mul (2 CTAs/SM hold the whole register file) the side kernels only
     # displace mat-mul CTAs (+0.13 ms at 1 GPU); under the small slabs of 4-8 GPUs they fill idle SM time.
-    overlap = (r1 - r0) * m < 512 * 1024
+    # side-stream schedule: always with the tensor-core mat-mul engine (it leaves the integer pipe idle), else only for
+    # small row slabs (the IMAD mat-mul engines saturate the pipe the mat-vecs need)
+    tc_engine = k >= 32 and (r1 - r0) * k * m >= (1 << 18)
+    overlap = tc_engine or (r1 - r0) * m < 512 * 1024
+    # Measured at N=1024 on one GPU (step, ms): no side stream 1.170; C-independent mat-vecs under the tensor-core
+    # mat-mul and C.v next to the rescale 1.116 (the mat-mul gives back most of what the mat-vecs save: they compete
+    # for shared-memory bandwidth); all three mat-vecs next to the rescale 1.143 (its CTAs fill the SMs, the side
+    # kernels only start as they drain).  With several ranks the first schedule also hides the all-gather latency.
+    pre_under_matmul = True
 
     # ---- synthetic inputs: f64 matrices -> pinned host -> GPU quantization kernel (product path)
     a_f, b_f, gamma = make_inputs(n, k, m)
@@ -274,13 +282,16 @@ def run_gpu(args) -> None:
         # same schedule as wl.run_step(..., side=side), with phase events on the main stream
         e = [ev() for _ in range(4)] if times is not None else None
         if e: e[0].record(stream)
-        if overlap:
+        if overlap and pre_under_matmul:
             bv = side.run(lambda be: wl.step_freivalds_pre(be, plan, bufs, dist, comm))   # under the mat-mul
         wl.step_matmul(h, plan, bufs)
         if e: e[1].record(stream)
         if overlap:
-            # small slab: C.v / A.(Bv) / is_equal on the side stream next to the rescale kernel (both only read C)
-            side.run(lambda be: wl.step_freivalds_post(be, plan, bufs, bv))
+            # the mat-vecs (integer-pipe bound) on the side stream next to the rescale kernel (HBM bound)
+            if pre_under_matmul:
+                side.run(lambda be: wl.step_freivalds_post(be, plan, bufs, bv))
+            else:
+                side.run(lambda be: wl.step_freivalds_post(be, plan, bufs, wl.step_freivalds_pre(be, plan, bufs, dist, comm)))
             wl.step_rescale(h, plan, bufs, P_BITS, LOOKUP_BITS)
             if e: e[2].record(stream)
             side.join()

@@ -15,7 +15,7 @@
 //     so the 32 planes p overlap-add straight into the 63 diagonals (x 8 columns j = 504 of the 512 TMEM columns).
 //     Nothing but zero-initialised accumulators and `accumulate` MMAs is needed for the convolution structure.
 //   * per 128 bytes of K: one TMA load of the B operand (32 KB, shared by all p) and 32 TMA loads of A planes
-//     (16 KB each, 8-stage ring), 4 MMAs (K = 32 bytes each) per A plane: 128 x 256 x 32 MACs per instruction,
+//     (16 KB each, 6-stage ring), 4 MMAs (K = 32 bytes each) per A plane: 128 x 256 x 32 MACs per instruction,
 //     the full-rate shape (128 cycles per instruction per SM).
 //   * epilogue (16 warps: thread = row i, 4 warps per TMEM lane quarter with 2 columns j each): reads the 63
 //     diagonals of one (i, j) from TMEM, carries them into an 18-limb integer, reduces, stores C; then re-zeroes
@@ -35,7 +35,7 @@ namespace {
 constexpr int TC_BM = 128;       // rows of C per tile = MMA M = TMEM lanes
 constexpr int TC_BJ = 8;         // columns of C per tile
 constexpr int TC_BKB = 128;      // bytes (= k values) of K per pipeline unit: one 128-byte swizzle span
-constexpr int TC_SA = 8;         // A-plane stages
+constexpr int TC_SA = 6;         // A-plane stages (6 x 16 KB + 2 x 32 KB leaves room for a co-resident mat-vec CTA)
 constexpr int TC_SB = 2;         // B buffers
 constexpr int TC_KB_PASS = 8;    // K blocks per accumulation pass: 1024 k values keep every diagonal below 2^31
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BKB;        // 16 KB

@@ -106,10 +106,9 @@ def step_rescale(backend, plan: ShardPlan, bufs: StepBuffers, precision_bits: in
                                 bufs.wit_slab)
 
 
-def step_freivalds_pre(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None):
-    """The part of ZkMatrix::verify_mul (:299) that does not need C: gamma powers (:316-326), the B.v
-    running sums of this rank's rows of B (:336) and the one exchange step, the all-gather of the k row
-    totals.  Returns the tensor holding (B v)."""
+def _bv_running_sums(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None):
+    """gamma powers (reference src/matrix/mod.rs:316-326), the B.v running sums of this rank's rows of B (:336) and
+    the one exchange step, the all-gather of the k row totals.  Returns the tensor holding (B v)."""
     b0, b1 = plan.brows
     brows = b1 - b0
     backend.gamma_powers_dev(bufs.gamma, plan.m, bufs.powers)
@@ -124,16 +123,24 @@ def step_freivalds_pre(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, c
     return bufs.bv_local
 
 
-def step_freivalds_post(backend, plan: ShardPlan, bufs: StepBuffers, bv) -> None:
-    """The part of verify_mul that needs C: C.v (:335) and A.(Bv) (:337) for this rank's rows, is_equal (:339-341)."""
-    backend.mat_vec_prefix_dev(bufs.c_slab, bufs.powers, bufs.prefix_cv, bufs.csv)
+def step_freivalds_pre(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None):
+    """The part of ZkMatrix::verify_mul (:299) that does not need C: gamma powers (:316-326), the B.v
+    running sums of this rank's rows of B (:336), the one exchange step (the all-gather of the k row
+    totals) and A.(Bv) for this rank's rows (:337).  Returns the tensor holding (B v)."""
+    bv = _bv_running_sums(backend, plan, bufs, dist, comm)
     backend.mat_vec_prefix_dev(bufs.a_slab, bv, bufs.prefix_abv, bufs.abv)
+    return bv
+
+
+def step_freivalds_post(backend, plan: ShardPlan, bufs: StepBuffers, bv) -> None:
+    """The part of verify_mul that needs C: C.v (:335) for this rank's rows, is_equal (:339-341)."""
+    backend.mat_vec_prefix_dev(bufs.c_slab, bufs.powers, bufs.prefix_cv, bufs.csv)
     backend.is_equal_witness_dev(bufs.csv, bufs.abv, bufs.diff, bufs.is_zero, bufs.inv)
 
 
 class SideStream:
-    """A second (backend, CUDA stream) pair on the same GPU: the C-independent half of verify_mul runs there,
-    under the mat-mul, which matters once the row slab is small (8 GPUs: ~45 us of a 1.3 ms step)."""
+    """A second (backend, CUDA stream) pair on the same GPU: the C-independent part of verify_mul (two of its three
+    mat-vecs: integer-pipe work) runs there under the mat-mul (tensor-pipe work), C.v next to the rescale (HBM-bound)."""
 
     def __init__(self, torch, backend, stream, main_stream) -> None:
         self.torch, self.backend, self.stream, self.main = torch, backend, stream, main_stream
@@ -167,6 +174,6 @@ def run_step(backend, plan: ShardPlan, bufs: StepBuffers, precision_bits: int, l
         return
     bv = side.run(lambda be: step_freivalds_pre(be, plan, bufs, dist, comm))
     step_matmul(backend, plan, bufs)
+    side.run(lambda be: step_freivalds_post(be, plan, bufs, bv))   # stream order on the side stream: after the pre part
     step_rescale(backend, plan, bufs, precision_bits, lookup_bits)
     side.join()
-    step_freivalds_post(backend, plan, bufs, bv)
