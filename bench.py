@@ -241,6 +241,9 @@ def run_gpu(args) -> None:
     # for shared-memory bandwidth); all three mat-vecs next to the rescale 1.143 (its CTAs fill the SMs, the side
     # kernels only start as they drain).  With several ranks the first schedule also hides the all-gather latency.
     pre_under_matmul = True
+    fused = tc_engine and args.fuse   # experimental: rescale witnesses from the mat-mul epilogue (measured not to pay)
+    if fused:
+        pkg.set_fuse_rescale(1)
 
     # ---- synthetic inputs: f64 matrices -> pinned host -> GPU quantization kernel (product path)
     a_f, b_f, gamma = make_inputs(n, k, m)
@@ -282,16 +285,26 @@ def run_gpu(args) -> None:
         # same schedule as wl.run_step(..., side=side), with phase events on the main stream
         e = [ev() for _ in range(4)] if times is not None else None
         if e: e[0].record(stream)
+        if fused:
+            # mat-mul + rescale witnesses in one launch (tensor-core engine, witnesses written from its epilogue); the
+            # C-independent Freivalds mat-vecs under it on the side stream, C.v after it
+            bv = side.run(lambda be: wl.step_freivalds_pre(be, plan, bufs, dist, comm))
+            wl.step_matmul_rescale(h, plan, bufs, P_BITS, LOOKUP_BITS)
+            if e: e[1].record(stream)
+            if e: e[2].record(stream)
+            side.join()
+            wl.step_freivalds_post(h, plan, bufs, bv)
+            if e:
+                e[3].record(stream)
+                times.append(e)
+            return
         if overlap and pre_under_matmul:
             bv = side.run(lambda be: wl.step_freivalds_pre(be, plan, bufs, dist, comm))   # under the mat-mul
         wl.step_matmul(h, plan, bufs)
         if e: e[1].record(stream)
         if overlap:
             # the mat-vecs (integer-pipe bound) on the side stream next to the rescale kernel (HBM bound)
-            if pre_under_matmul:
-                side.run(lambda be: wl.step_freivalds_post(be, plan, bufs, bv))
-            else:
-                side.run(lambda be: wl.step_freivalds_post(be, plan, bufs, wl.step_freivalds_pre(be, plan, bufs, dist, comm)))
+            side.run(lambda be: wl.step_freivalds_post(be, plan, bufs, bv))
             wl.step_rescale(h, plan, bufs, P_BITS, LOOKUP_BITS)
             if e: e[2].record(stream)
             side.join()
@@ -421,11 +434,14 @@ def run_gpu(args) -> None:
                         f"PRECISION_BITS={P_BITS}, LOOKUP_BITS={LOOKUP_BITS}"), "n": n, "k": k, "m": m, "sharding": f"rows of A/C over {world} rank(s), B replicated, "
                                    "(B v) all-gathered", "l2": "256 MiB flush write between timed steps",
                        "inputs": "input-creator.py distribution, seeded, quantized on the GPU"},
-            "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds_after_matmul": ms_fr, "freivalds_pre_overlapped_with_matmul": bool(overlap)},
+            "phase_ms": {"fr_matmul": ms_mm, "rescale": ms_rs, "freivalds_after_matmul": ms_fr, "freivalds_pre_overlapped_with_matmul": bool(overlap),
+                         "rescale_fused_into_matmul_epilogue": bool(fused)},
             "roofline": roofline, "matmul_engine": engine,
             "roofline_hbm": {
-                "rescale": {"bound": "hbm", "achieved": rs_bytes / (ms_rs * 1e-3) / 1e9, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": rs_bytes / (ms_rs * 1e-3) / 1e9 / hbm_peak},
+                # fused: the witness stream is written during the whole mat-mul launch (phase "fr_matmul")
+                "rescale": {"bound": "hbm", "achieved": rs_bytes / ((ms_mm if fused else ms_rs) * 1e-3) / 1e9, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": rs_bytes / ((ms_mm if fused else ms_rs) * 1e-3) / 1e9 / hbm_peak,
+                            "timed_over": "the fused mat-mul + rescale launch" if fused else "rescale_kernel"},
                 "freivalds": {"bound": "hbm", "achieved": fr_bytes / (ms_fr * 1e-3) / 1e9, "peak": hbm_peak,
                               "unit": "GB/s", "frac": fr_bytes / (ms_fr * 1e-3) / 1e9 / hbm_peak},
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
@@ -462,6 +478,7 @@ def main() -> None:
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--shape", type=str, default="", help="n,k,m of a rectangular job (default: square --n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fuse", action="store_true", help="experimental fused mat-mul + rescale launch (tuning)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (large rectangular jobs: pinned host memory)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -64,6 +64,7 @@ SIGNATURES = {
     "h2svd_rescale_witness_count": (_I, [_I, _I, _I, _I]),
     "h2svd_rescale_witness": (_I, [_P, _P, _Z, _I, _I, _I, _I, _P, _P]),
     "h2svd_rescale_witness_dev": (_I, [_P, _P, _Z, _I, _I, _I, _I, _P, _P]),
+    "h2svd_fr_matmul_rescale_dev": (_I, [_P, _P, _P, _Z, _Z, _Z, _I, _I, _I, _I, _P, _P, _P]),
     "h2svd_zkvec_inner_prefix": (_I, [_P, _P, _P, _Z, _Z, _P]),
     "h2svd_zkvec_inner_prefix_dev": (_I, [_P, _P, _P, _Z, _Z, _P]),
     "h2svd_zkvec_sub": (_I, [_P, _P, _P, _Z, _P]),
@@ -83,6 +84,9 @@ DEBUG_SIGNATURES = {
     "h2svd_debug_set_matmul_streamk": (_I, [_I]),
     "h2svd_debug_set_matmul_karatsuba": (_I, [_I]),
     "h2svd_debug_set_matvec_warp_kernel": (_I, [_I]),
+    "h2svd_debug_set_matmul_tc": (_I, [_I]),
+    "h2svd_debug_set_fuse_rescale": (_I, [_I]),
+    "h2svd_debug_last_matmul_engine": (_I, []),
 }
 
 _LIB = None

@@ -375,6 +375,18 @@ int h2svd_rescale_witness_dev(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count,
                           as_fr(out_q), as_fr(out_wit));
 }
 
+int h2svd_fr_matmul_rescale_dev(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, size_t n, size_t k, size_t m,
+                                int precision_bits, int lookup_bits, int shift_bits, int a_num_bits, h2svd_fr* c_s,
+                                h2svd_fr* out_q, h2svd_fr* out_wit) {
+    REQUIRE(ctx && a && b && c_s && out_q && out_wit, "fr_matmul_rescale: null argument");
+    REQUIRE(k >= 1, "fr_matmul_rescale: empty inner dimension");
+    REQUIRE(rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr) > 0,
+            "fr_matmul_rescale: rescale parameters out of range");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_fr_matmul_rescale(ctx, as_fr(a), as_fr(b), as_fr(c_s), n, k, m, precision_bits, lookup_bits, shift_bits,
+                                    a_num_bits, as_fr(out_q), as_fr(out_wit));
+}
+
 int h2svd_rescale_witness(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count, int precision_bits, int lookup_bits,
                           int shift_bits, int a_num_bits, h2svd_fr* out_q, h2svd_fr* out_wit) {
     REQUIRE(ctx && c_s && out_q && out_wit, "rescale_witness: null argument");
@@ -579,10 +591,9 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
         // A is uploaded slab by slab too: the first witnesses leave for the host after B + one slab of A, not after all of A
         H2SVD_TRY(h2d(ctx, da + r0 * k, as_fr(a) + r0 * k, nr * k * F));
         H2SVD_TRY(launch_check_canonical(ctx, da + r0 * k, nr * k, ctx->d_flag));
-        H2SVD_TRY(launch_fr_matmul(ctx, da + r0 * k, db, dc + r0 * m, nr, k, m));                       // :546
         H2SVD_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2 + buf], 0));  // slab buffer `buf` drained two slabs ago
-        H2SVD_TRY(launch_rescale(ctx, dc + r0 * m, nr * m, precision_bits, lookup_bits, shift_bits, a_num_bits,
-                                 dq + r0 * m, dw[buf]));                                                 // :354
+        H2SVD_TRY(launch_fr_matmul_rescale(ctx, da + r0 * k, db, dc + r0 * m, nr, k, m, precision_bits, lookup_bits,
+                                           shift_bits, a_num_bits, dq + r0 * m, dw[buf]));               // :546, :354
         H2SVD_TRY(launch_mat_vec_prefix(ctx, dc + r0 * m, dpow, nr, m, 0, dpcv + r0 * m, dcsv + r0));    // :335
         H2SVD_TRY(launch_mat_vec_prefix(ctx, da + r0 * k, dbv, nr, k, 0, dpabv + r0 * k, dabv + r0));    // :337
         H2SVD_TRY(launch_is_equal(ctx, dcsv + r0, dabv + r0, nr, ddiff + r0, dz + r0, dinv + r0));       // :339-341

@@ -106,7 +106,13 @@ int launch_fr_matmul_naive(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size
 // tensor-core engine of the mat-mul (matmul_tc.cu)
 extern int g_matmul_tc;
 bool fr_matmul_tc_supported(size_t n, size_t k, size_t m);
-int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m);
+namespace rs { struct RescaleConsts; }
+// fuse != nullptr: the epilogue also writes the rescale_matrix witnesses of C (out_q, out_wit as in launch_rescale)
+int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m,
+                        const rs::RescaleConsts* fuse = nullptr, Fr* out_q = nullptr, Fr* out_wit = nullptr);
+// mat-mul followed by rescale_matrix of the product: one fused launch when the tensor-core engine applies
+int launch_fr_matmul_rescale(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m, int P, int lb,
+                             int S, int A, Fr* out_q, Fr* out_wit);
 int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t cols);
 int launch_gamma_powers(h2svd_ctx* ctx, const Fr* gamma, size_t d, Fr* out);
 // totals (optional): last running sum of every row

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "fr_acc.cuh"
 #include "fr_kara.cuh"
+#include "rescale_dev.cuh"
 
 namespace h2svd {
 
@@ -809,18 +810,38 @@ static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, i
     return H2SVD_OK;
 }
 
+// Tensor-core engine (matmul_tc.cu: u8 byte planes on tcgen05, ~12x the IMAD engines at N=1024; measured with
+// tools/tc_check.py: ahead from 64^3 on, behind for very short k where its per-element epilogue dominates).
+// Forcing one of the IMAD engines / schedules through the triage hooks switches the automatic choice off.
+static bool use_tensor_engine(size_t n, size_t k, size_t m) {
+    const bool imad_forced = g_kara >= 0 || g_streamk >= 0 || g_variant != 0;
+    const bool tc = g_matmul_tc == 1 || (g_matmul_tc < 0 && !imad_forced && k >= 32 && n * k * m >= (1ull << 18));
+    return tc && fr_matmul_tc_supported(n, k, m);
+}
+
+static int g_fuse_rescale = 0;  // 1: emit the rescale witnesses from the tensor-core epilogue (experimental, see matmul_tc.cu)
+
+int launch_fr_matmul_rescale(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m, int P, int lb,
+                             int S, int A, Fr* out_q, Fr* out_wit) {
+    if (n == 0 || m == 0) return H2SVD_OK;
+    rs::RescaleConsts kc;
+    const int W = make_rescale_consts(P, lb, S, A, &kc);
+    if (g_fuse_rescale > 0 && W > 0 && m * (size_t)W < (1ull << 31) && n <= (1u << 30) && m <= (1u << 30) &&
+        k <= (1u << 30) && use_tensor_engine(n, k, m)) {
+        g_last_engine = 2;
+        return launch_fr_matmul_tc(ctx, a, b, c, n, k, m, &kc, out_q, out_wit);
+    }
+    H2SVD_TRY(launch_fr_matmul(ctx, a, b, c, n, k, m));
+    return launch_rescale(ctx, c, n * m, P, lb, S, A, out_q, out_wit);
+}
+
 int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m) {
     if (n == 0 || m == 0) return H2SVD_OK;
     if (n > (1u << 30) || m > (1u << 30) || k > (1u << 30)) {
         set_error("fr_matmul: dimension too large");
         return H2SVD_EINVAL;
     }
-    // Tensor-core engine (matmul_tc.cu: u8 byte planes on tcgen05, ~12x the IMAD engines at N=1024; measured with
-    // tools/tc_check.py: ahead from 64^3 on, behind for very short k where its per-element epilogue dominates).
-    // Forcing one of the IMAD engines / schedules through the triage hooks switches the automatic choice off.
-    const bool imad_forced = g_kara >= 0 || g_streamk >= 0 || g_variant != 0;
-    const bool tc = g_matmul_tc == 1 || (g_matmul_tc < 0 && !imad_forced && k >= 32 && n * k * m >= (1ull << 18));
-    if (tc && fr_matmul_tc_supported(n, k, m)) {
+    if (use_tensor_engine(n, k, m)) {
         g_last_engine = 2;
         return launch_fr_matmul_tc(ctx, a, b, c, n, k, m);
     }
@@ -857,6 +878,10 @@ int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t
 
 }  // namespace h2svd
 
+extern "C" int h2svd_debug_set_fuse_rescale(int v) {
+    h2svd::g_fuse_rescale = v;
+    return 0;
+}
 extern "C" int h2svd_debug_last_matmul_engine(void) { return h2svd::g_last_engine; }
 extern "C" int h2svd_debug_set_matmul_variant(int v) {
     h2svd::g_variant = v;

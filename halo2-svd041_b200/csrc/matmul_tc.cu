@@ -27,6 +27,7 @@
 #include <cuda.h>  // CUtensorMap and enums only; the encoder comes from cudaGetDriverEntryPoint (no -lcuda)
 
 #include "common.cuh"
+#include "rescale_dev.cuh"
 
 namespace h2svd {
 
@@ -35,15 +36,31 @@ namespace {
 constexpr int TC_BM = 128;       // rows of C per tile = MMA M = TMEM lanes
 constexpr int TC_BJ = 8;         // columns of C per tile
 constexpr int TC_BKB = 128;      // bytes (= k values) of K per pipeline unit: one 128-byte swizzle span
-constexpr int TC_SA = 6;         // A-plane stages (6 x 16 KB + 2 x 32 KB leaves room for a co-resident mat-vec CTA)
+constexpr int TC_SA_PLAIN = 6;   // A-plane stages (6 x 16 KB + 2 x 32 KB leaves room for a co-resident mat-vec CTA)
+#ifndef TC_SA_FUSED_CFG
+#define TC_SA_FUSED_CFG 5
+#endif
+#ifndef TC_CH_CFG
+#define TC_CH_CFG 4
+#endif
+constexpr int TC_SA_FUSED = TC_SA_FUSED_CFG;   // one stage less when the epilogue stages rescale witnesses in shared memory
 constexpr int TC_SB = 2;         // B buffers
 constexpr int TC_KB_PASS = 8;    // K blocks per accumulation pass: 1024 k values keep every diagonal below 2^31
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BKB;        // 16 KB
 constexpr uint32_t TC_B_BYTES = 32 * TC_BJ * TC_BKB;   // 32 KB
-constexpr int TC_EPI_WARPS = 16;  // 4 warps per TMEM lane quarter, each owning 2 of the 8 columns j of the tile
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
-constexpr int TC_JPW = TC_BJ / (TC_EPI_WARPS / 4);  // columns j per epilogue warp
-constexpr size_t TC_SMEM = (size_t)TC_SA * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES + 256 + 1024;
+// Epilogue warps: 4 per TMEM lane quarter with 2 of the 8 columns j each.  (Measured for the fused-rescale variant: 3 per
+// quarter with 3/3/2 columns and 128 spill-free registers is slower, 1.03 vs 0.91 ms at N=1024 -- the code below still
+// handles MAXC = 3.)
+__host__ __device__ constexpr int tc_epi_warps(bool) { return 16; }
+__host__ __device__ constexpr int tc_threads(bool fused) { return 64 + 32 * tc_epi_warps(fused); }  // + TMA producer warp + MMA issuer warp
+// fused rescale: every epilogue warp stages 4 witnesses (128 B + 16 B skew) per lane, single-buffered
+using TcWitnessStream = rs::WitnessStreamT<TC_CH_CFG, 1>;
+constexpr uint32_t TC_STAGE_BYTES = tc_epi_warps(true) * 32 * TcWitnessStream::ROW_U4 * 16;
+static_assert((size_t)TC_SA_FUSED_CFG * 16384 + 65536 + 1280 + TC_STAGE_BYTES <= 232448, "fused kernel: shared memory");
+constexpr size_t tc_smem_bytes(bool fused) {
+    return (size_t)(fused ? TC_SA_FUSED : TC_SA_PLAIN) * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES + 256 + 1024 +
+           (fused ? TC_STAGE_BYTES : 0);
+}
 // kind::i8 instruction descriptor: D = S32, A = B = unsigned 8-bit, both K-major, N = 256, M = 128
 constexpr uint32_t TC_IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -149,16 +166,27 @@ __device__ __forceinline__ void tc_carry_diagonals(const uint32_t* dg, uint32_t*
         cy >>= 32;
     }
 }
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t& v0, uint32_t& v1, uint32_t& v2, uint32_t& v3) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tc_st2_zero(uint32_t taddr) {
     const uint32_t z = 0;
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(z), "r"(z) : "memory");
 }
-// this warp's accumulators (its TMEM lanes, its TC_JPW = 2 columns j of every diagonal) := 0, then hand them (back)
-// to the MMA warp.  Each warp reads and zeroes only its own columns, so the warps of a lane quarter never race.
-__device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, uint32_t bar) {
-    static_assert(TC_JPW == 2, "the zeroing store is two columns wide");
+__device__ __forceinline__ void tc_st1_zero(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+// this warp's accumulators (its TMEM lanes, its cnt = 2 or 3 columns j of every diagonal) := 0, then hand them (back)
+// to the MMA warp.  Each warp zeroes only its own columns, so the warps of a lane quarter never race.
+__device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, int cnt, uint32_t bar) {
 #pragma unroll 9
-    for (int d = 0; d < 63; d++) tc_st2_zero(tcol0 + 8u * d);
+    for (int d = 0; d < 63; d++) {
+        tc_st2_zero(tcol0 + 8u * d);
+        if (cnt == 3) tc_st1_zero(tcol0 + 8u * d + 2);  // warp-uniform
+    }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     tc_mbar_arrive(bar);
@@ -199,9 +227,21 @@ __global__ void tc_split_b_kernel(const Fr* __restrict__ b, uint32_t* __restrict
 }
 
 // ---- the tensor-core kernel ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// FUSE (experimental, off by default -- h2svd_debug_set_fuse_rescale): the epilogue also emits the rescale_matrix
+// witnesses (K4, rescale_dev.cuh) of every C element it produces, so that the witness stream (2 KB per element) is
+// written under the MMAs of the next tile instead of after the mat-mul.  Bit-identical, but measured NOT to pay: the
+// MMAs read their operands from shared memory at 96 of the SM's 128 B/clk, and staging the witnesses for the bulk
+// stores needs another ~60 B/clk, so a fused tile takes 126 us against 69 us (MMAs) + 58 us (stand-alone rescale):
+// N=1024 0.91 ms fused vs 1.01 ms as two kernels (a wave-rounding gain only), slower on 1-4 wave slabs.  Direct 32-byte
+// global stores instead of staging: 1.37 ms.  It would need the A operand in TMEM or 2-CTA MMAs (halved B reads).
+template <bool FUSE>
+__global__ void __launch_bounds__(tc_threads(FUSE), 1)
 fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    Fr* __restrict__ c, int n, int k, int m, int tiles_j, int num_tiles, int* err) {
+                    Fr* __restrict__ c, int n, int k, int m, int tiles_j, int num_tiles, int* err,
+                    const __grid_constant__ rs::RescaleConsts kc, Fr* __restrict__ out_q, Fr* __restrict__ out_wit) {
+    constexpr int TC_SA = FUSE ? TC_SA_FUSED : TC_SA_PLAIN;
+    constexpr int EPI_WARPS = 16;
+    constexpr int MAXC = TC_BJ / (EPI_WARPS / 4);  // columns j per epilogue warp (the last warp of a quarter may own fewer)
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = tc_smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
@@ -211,6 +251,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t full_a = bars, empty_a = bars + 8 * TC_SA, full_b = bars + 16 * TC_SA,
                    empty_b = full_b + 8 * TC_SB, tmem_full = empty_b + 8 * TC_SB, tmem_empty = tmem_full + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (tmem_empty + 8 - base));
+    uint4* stage = reinterpret_cast<uint4*>(smem + (bars + 256 - base));  // FUSE only: witness staging rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -223,7 +264,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             tc_mbar_init(empty_b + 8 * s, 1);
         }
         tc_mbar_init(tmem_full, 1);
-        tc_mbar_init(tmem_empty, 32 * TC_EPI_WARPS);
+        tc_mbar_init(tmem_empty, 32 * EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -302,9 +343,20 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ===== epilogue: thread = row of the tile =====
         const uint32_t quarter = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int il = quarter * 32 + lane;
-        const int j0 = ((warp - 2) >> 2) * TC_JPW;  // this warp's columns j0, j0+1 of the tile
+        // this warp's columns j0 .. j0+cnt-1 of the tile: 2 each with 16 warps, 3/3/2 with 12 warps
+        const int jg = (warp - 2) >> 2;
+        const int j0 = jg * MAXC;
+        const int cnt = TC_BJ - j0 < MAXC ? TC_BJ - j0 : MAXC;
         const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
-        tc_zero_and_release(tlane + j0, tmem_empty);
+        tc_zero_and_release(tlane + j0, cnt, tmem_empty);
+        TcWitnessStream ws;
+        if (FUSE) {
+            ws.warp_row0 = stage + (size_t)(warp - 2) * 32 * TcWitnessStream::ROW_U4;
+            ws.row0 = ws.warp_row0 + (size_t)lane * TcWitnessStream::ROW_U4;
+            ws.W = m * kc.p.W;
+            ws.buf = 0;
+            ws.fill = 0;
+        }
         uint32_t round = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int ib = tile / tiles_j, jb = tile % tiles_j;
@@ -312,40 +364,67 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_full, round & 1, err);
                 tc_fence_after();
-                // Phase 1 (on the critical path of the next tile): read this warp's two columns j0, j0+1 of all 63
-                // diagonals and carry them into two 18-limb integers.  T = sum_d dg[d] * 2^(8d): diagonals d = 4g + r
-                // sit at whole-word offsets g for fixed r, so T = Y0 + (Y1 << 8) + (Y2 << 16) + (Y3 << 24) with
-                // Y_r[g] = dg[4g + r].
-                uint32_t da[64], db[64];
+                // Phase 1 (on the critical path of the next tile): read this warp's columns of all 63 diagonals and
+                // carry them into 18-limb integers.  T = sum_d dg[d] * 2^(8d): diagonals d = 4g + r sit at whole-word
+                // offsets g for fixed r, so T = Y0 + (Y1 << 8) + (Y2 << 16) + (Y3 << 24) with Y_r[g] = dg[4g + r].
+                uint32_t dg[MAXC][64];
 #pragma unroll
-                for (int d = 0; d < 63; d++) tc_ld2(tlane + 8u * d + j0, da[d], db[d]);
-                da[63] = 0;
-                db[63] = 0;
+                for (int d = 0; d < 63; d++) {
+                    if (MAXC == 2) {
+                        tc_ld2(tlane + 8u * d + j0, dg[0][d], dg[1][d]);
+                    } else {
+                        uint32_t unused;  // 4-column load; a 2-column warp reads (and ignores) its neighbours' columns
+                        tc_ld4(tlane + 8u * d + j0, dg[0][d], dg[1][d], dg[MAXC - 1][d], unused);
+                    }
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 // pin the loaded registers behind the wait (the compiler must not read them earlier)
 #pragma unroll
-                for (int d = 0; d < 63; d++) asm volatile("" : "+r"(da[d]), "+r"(db[d]));
-                uint32_t Ta[18], Tb[18];
-                tc_carry_diagonals(da, Ta);
-                tc_carry_diagonals(db, Tb);
-                // the accumulators are free again: zero them and let the MMA warp start the next tile while the
-                // Montgomery reductions below run
-                tc_fence_before();  // order the TMEM reads above before the zeroing stores / the next MMAs
-                tc_zero_and_release(tlane + j0, tmem_empty);
-                // Phase 2 (overlaps the next tile's MMAs)
+                for (int d = 0; d < 63; d++)
 #pragma unroll
-                for (int jj = 0; jj < TC_JPW; jj++) {
-                    Fr res = fr::reduce_wide_acc(jj == 0 ? Ta : Tb);
-                    const int gj = jb * TC_BJ + j0 + jj;
-                    if (gi < n && gj < m) {
+                    for (int q = 0; q < MAXC; q++) asm volatile("" : "+r"(dg[q][d]));
+                uint32_t T[MAXC][18];
+#pragma unroll
+                for (int q = 0; q < MAXC; q++) {
+                    dg[q][63] = 0;
+                    tc_carry_diagonals(dg[q], T[q]);
+                }
+                // the accumulators are free again: zero them and let the MMA warp start the next tile while the
+                // Montgomery reductions (and the rescale witnesses) below run
+                tc_fence_before();  // order the TMEM reads above before the zeroing stores / the next MMAs
+                tc_zero_and_release(tlane + j0, cnt, tmem_empty);
+                // Phase 2 (overlaps the next tile's MMAs)
+                Fr res[MAXC];
+#pragma unroll
+                for (int q = 0; q < MAXC; q++) {
+                    res[q] = fr::reduce_wide_acc(T[q]);
+                    const int gj = jb * TC_BJ + j0 + q;
+                    if (q < cnt && gi < n && gj < m) {
                         Fr* dst = c + (size_t)gi * m + gj;
-                        if (pass > 0) res = fr::add(ld_fr(dst), res);
-                        st_fr(dst, res);
+                        if (pass > 0) res[q] = fr::add(ld_fr(dst), res[q]);
+                        st_fr(dst, res[q]);
+                    }
+                }
+                if (FUSE && pass == passes - 1) {
+                    // this warp's 32 lanes hold rows row0 .. row0+31 of one column: stripes m*W witnesses apart
+                    const int row0 = ib * TC_BM + (int)quarter * 32;
+                    const int valid = n - row0 < 32 ? n - row0 : 32;
+#pragma unroll
+                    for (int q = 0; q < MAXC; q++) {
+                        const int gj = jb * TC_BJ + j0 + q;
+                        if (q < cnt && gj < m && valid > 0) {  // warp-uniform
+                            ws.valid = valid;
+                            ws.gwarp = out_wit + ((size_t)row0 * m + gj) * (size_t)kc.p.W;
+                            const Fr qv = rs::rescale_element(ws, kc, gi < n ? res[q] : fr::zero());
+                            if (gi < n) st_fr(out_q + (size_t)gi * m + gj, qv);
+                        }
                     }
                 }
                 round++;
             }
         }
+        // shared memory must outlive every bulk read, and the witness writes must be complete at kernel end
+        if (FUSE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -379,7 +458,8 @@ bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
     return k >= 1 && n * 32 < (1ull << 31) && m * 32 < (1ull << 31) && k < (1ull << 30);
 }
 
-int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m) {
+int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m,
+                        const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit) {
     if (n == 0 || m == 0) return H2SVD_OK;
     tc_encode_fn encode = tc_encoder();
     if (!encode) {
@@ -442,10 +522,17 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
         set_error("fr_matmul (tensor-core engine): too many tiles");
         return H2SVD_EINVAL;
     }
-    H2SVD_SET_SMEM(ctx, fr_matmul_tc_kernel, TC_SMEM);
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    fr_matmul_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j,
-                                                                   (int)tiles, ctx->d_flag);
+    if (fuse) {
+        H2SVD_SET_SMEM(ctx, fr_matmul_tc_kernel<true>, tc_smem_bytes(true));
+        fr_matmul_tc_kernel<true><<<grid, tc_threads(true), tc_smem_bytes(true), ctx->stream>>>(
+            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, *fuse, out_q, out_wit);
+    } else {
+        static const rs::RescaleConsts none{};
+        H2SVD_SET_SMEM(ctx, fr_matmul_tc_kernel<false>, tc_smem_bytes(false));
+        fr_matmul_tc_kernel<false><<<grid, tc_threads(false), tc_smem_bytes(false), ctx->stream>>>(
+            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, none, nullptr, nullptr);
+    }
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }

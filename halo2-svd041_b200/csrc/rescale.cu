@@ -26,30 +26,14 @@
 //    issued by the copy engine, no thread ever issues a 32-byte scattered store.
 #include "common.cuh"
 #include "fr_fast.cuh"
+#include "rescale_dev.cuh"
 
 namespace h2svd {
 
 namespace {
 
-constexpr int MAX_POS = 32;  // limb positions the staged kernel supports (n_d, n_r <= 32)
+using namespace rs;
 
-struct RescaleParams {
-    int P, lb, S, A, n_d, n_r, W;
-};
-
-// Host-precomputed constants of one (P, lb, S, A) configuration, passed by value (constant bank).
-// limb-decomposition constants shared by every range-check style kernel
-struct LimbConsts {
-    int lb;
-    uint32_t lb_mask;
-    Fr c[MAX_POS];  // c[i] = 2^(lb*i) * 2^288 mod r
-};
-struct RescaleConsts {
-    RescaleParams p;
-    Fr i_2S, i_pow_d, i_bound_d, i_pow_r, i_bound_r;   // canonical integers
-    Fr m_2S, m_2SP, m_pow_d, m_bound_d, m_pow_r, m_bound_r;  // Montgomery forms
-    LimbConsts lc;
-};
 // check_abs_less_than / check_mat_diff (reference src/matrix/mod.rs:425-459)
 struct AbsLtConsts {
     int n, W, with_diff;
@@ -113,103 +97,18 @@ rescale_generic_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __
 // ---------------------------------------------------------------------------------------------------
 // staged kernel
 constexpr int RS_THREADS = 128;
-constexpr int RS_CH = 8;                      // witnesses per bulk store (256 B)
+#ifndef RS_CH_CFG
+#define RS_CH_CFG 8
+#endif
+#ifndef RS_NBUF_CFG
+#define RS_NBUF_CFG 2
+#endif
+constexpr int RS_CH = RS_CH_CFG;              // witnesses per bulk store (256 B)
+constexpr int RS_NBUF = RS_NBUF_CFG;          // staging rows per lane
 constexpr int RS_ROW_U4 = RS_CH * 2 + 1;      // staging row in 16-byte units: 256 B + 16 B skew
-constexpr size_t RS_SMEM = (size_t)RS_THREADS * 2 * RS_ROW_U4 * sizeof(uint4);
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-// one lane of the (converged) warp; ptxas then knows the guarded region runs single-threaded and
-// feeds the uniform-operand bulk copies without a per-lane serialisation loop
-__device__ __forceinline__ bool elect_one() {
-    uint32_t is_leader;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
-    return is_leader != 0;
-}
-
-// Per-lane witness stream: values go to this lane's shared-memory row; every RS_CH values (and at the
-// end of the element) the warp ships its 32 rows to their places in out_wit.  cp.async.bulk takes
-// uniform operands, so ONE elected lane issues the 32 row copies of the warp (per-lane issue would be
-// serialised by the compiler into a 32-trip loop of ~14 instructions each -- measured: 44 % of all
-// executed instructions); the warp's 32 elements are consecutive, so row r goes to gbase + r*W.
-struct WitnessStream {
-    uint4* row0;      // this lane's two consecutive rows of RS_ROW_U4 16-byte units
-    uint4* warp_row0; // lane 0's rows (the elected lane walks all 32)
-    Fr* gwarp;        // out_wit position of lane 0's element, advanced by every flush
-    int W, valid;     // witnesses per element; lanes of this warp that hold a real element
-    int buf, fill;
-
-    __device__ __forceinline__ void put(const Fr& v) {
-        uint4* s = row0 + buf * RS_ROW_U4 + 2 * fill;
-        s[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        s[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-        if (++fill == RS_CH) flush();
-    }
-    __device__ __forceinline__ void flush() {  // warp-uniform: every lane has the same `fill`
-        if (fill == 0) return;
-        // generic-proxy writes of every lane -> visible to the async proxy, then the elected lane ships
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (elect_one()) {
-            const uint32_t bytes = (uint32_t)(fill * sizeof(Fr));
-            uint32_t src = smem_addr(warp_row0 + buf * RS_ROW_U4);
-            Fr* dst = gwarp;
-            for (int r = 0; r < valid; r++) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
-                             "r"(bytes)
-                             : "memory");
-                src += 2 * RS_ROW_U4 * sizeof(uint4);
-                dst += W;
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // the rows we switch to were shipped one flush ago: wait until the engine has read them
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        }
-        __syncwarp();
-        gwarp += fill;
-        fill = 0;
-        buf ^= 1;
-    }
-};
-
-__device__ __forceinline__ Fr shr_small(const Fr& y, int s) {  // 1 <= s <= 32
-    Fr o;
-#pragma unroll
-    for (int j = 0; j < 7; j++) o.l[j] = __funnelshift_rc(y.l[j], y.l[j + 1], s);
-    o.l[7] = __funnelshift_rc(y.l[7], 0u, s);
-    return o;
-}
-
-// RangeChip::range_check(x, n*lb): limbs l_i and running sums s_i = x mod 2^(lb*(i+1)), Montgomery form
-__device__ __forceinline__ void stream_range_check(WitnessStream& ws, const LimbConsts& k, Fr y, int n) {
-    if (n == 1) return;
-    Fr sum;
-    for (int i = 0; i < n; i++) {
-        const uint32_t l = y.l[0] & k.lb_mask;
-        y = shr_small(y, k.lb);
-        const Fr ml = fr::mont_mul_small(l, k.c[0]);
-        ws.put(ml);
-        if (i == 0) {
-            sum = ml;
-        } else {
-            sum = fr::add_fast(sum, fr::mont_mul_small(l, k.c[i]));
-            ws.put(sum);
-        }
-    }
-}
-
-// RangeChip::check_big_less_than_safe(x, B)
-__device__ __forceinline__ void stream_cbls(WitnessStream& ws, const LimbConsts& k, const Fr& x_int,
-                                            const Fr& x_mont, int n, const Fr& i_pow, const Fr& i_bound,
-                                            const Fr& m_pow, const Fr& m_bound) {
-    stream_range_check(ws, k, x_int, n);
-    const Fr chk_int = fr::sub_fast(fr::add_fast(x_int, i_pow), i_bound);  // x + 2^bits - B (mod r)
-    const Fr m_xp = fr::add_fast(x_mont, m_pow);
-    ws.put(fr::sub_fast(m_xp, m_bound));
-    ws.put(m_xp);
-    stream_range_check(ws, k, chk_int, n);
-}
+constexpr size_t RS_SMEM = (size_t)RS_THREADS * RS_NBUF * RS_ROW_U4 * sizeof(uint4);
+constexpr int RS_CTAS_PER_SM = (int)((227 * 1024) / (RS_SMEM + 1024)) > 0 ? (int)((227 * 1024) / (RS_SMEM + 1024)) : 1;
+using WitnessStream = WitnessStreamT<RS_CH, RS_NBUF>;   // 256-byte bursts, double-buffered rows
 
 __global__ void __launch_bounds__(RS_THREADS)
 rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
@@ -217,8 +116,8 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
     WitnessStream ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * 2 * RS_ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * 2 * RS_ROW_U4;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_NBUF * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_NBUF * RS_ROW_U4;
     ws.W = k.p.W;
     ws.buf = 0;
     ws.fill = 0;
@@ -231,20 +130,7 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
         const bool live = lane < ws.valid;
         const size_t e = live ? e0 + lane : count - 1;
         const Fr am = ldg_fr(cs + e);
-        const Fr a = fr::from_mont_fast(am);                    // canonical integer
-        const Fr ash = fr::add_fast(a, k.i_2S);                 // gate.add(a, Constant(2^S))
-        const Fr div = fr::shr(ash, k.p.P);                     // div_mod_floor by 2^P
-        const Fr rem = fr::low_bits(ash, k.p.P);
-        const Fr m_div = fr::to_mont_fast(div);
-        const Fr m_rem = fr::to_mont_fast(rem);
-        ws.put(fr::add_fast(am, k.m_2S));
-        ws.put(m_rem);
-        ws.put(m_div);
-        stream_cbls(ws, k.lc, div, m_div, k.p.n_d, k.i_pow_d, k.i_bound_d, k.m_pow_d, k.m_bound_d);
-        stream_cbls(ws, k.lc, rem, m_rem, k.p.n_r, k.i_pow_r, k.i_bound_r, k.m_pow_r, k.m_bound_r);
-        const Fr q = fr::sub_fast(m_div, k.m_2SP);              // gate.sub(div, Constant(2^(S-P)))
-        ws.put(q);
-        ws.flush();
+        const Fr q = rescale_element(ws, k, am);
         if (live) st_fr(out_q + e, q);
     }
     // shared memory must outlive every bulk read, and the writes must be complete at kernel end
@@ -259,8 +145,8 @@ abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __r
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
     WitnessStream ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * 2 * RS_ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * 2 * RS_ROW_U4;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_NBUF * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_NBUF * RS_ROW_U4;
     ws.W = k.W;
     ws.buf = 0;
     ws.fill = 0;
@@ -290,8 +176,8 @@ range_check_kernel(const Fr* __restrict__ x, Fr* __restrict__ out_wit, size_t co
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
     WitnessStream ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * 2 * RS_ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * 2 * RS_ROW_U4;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_NBUF * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_NBUF * RS_ROW_U4;
     ws.W = k.W;
     ws.buf = 0;
     ws.fill = 0;
@@ -360,6 +246,31 @@ static int bit_length(const Fr& x) {
     return 0;
 }
 
+int make_rescale_consts(int P, int lb, int S, int A, rs::RescaleConsts* out) {
+    if (S < 0) S = 3 * P;
+    if (A < 0) A = 4 * P;
+    RescaleConsts& k = *out;
+    RescaleParams& p = k.p;
+    p.P = P; p.lb = lb; p.S = S; p.A = A;
+    p.W = rescale_params(P, lb, S, A, &p.n_d, &p.n_r);
+    if (p.W < 0 || p.n_d > MAX_POS || p.n_r > MAX_POS) return -1;
+    // constants of this configuration (fr.cuh is host-callable)
+    fill_limb_consts(k.lc, lb, p.n_d > p.n_r ? p.n_d : p.n_r);
+    k.i_2S = fr::pow2(S);
+    k.i_pow_d = fr::pow2(p.n_d * lb);
+    k.i_bound_d = fr::pow2(A - P);
+    k.i_bound_d.l[0] |= 1u;  // 2^A / 2^P + 1   (A > P)
+    k.i_pow_r = fr::pow2(p.n_r * lb);
+    k.i_bound_r = fr::pow2(P);
+    k.m_2S = fr::to_mont(k.i_2S);
+    k.m_2SP = fr::to_mont(fr::pow2(S - P));
+    k.m_pow_d = fr::to_mont(k.i_pow_d);
+    k.m_bound_d = fr::to_mont(k.i_bound_d);
+    k.m_pow_r = fr::to_mont(k.i_pow_r);
+    k.m_bound_r = fr::to_mont(k.i_bound_r);
+    return p.W;
+}
+
 int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, int S, int A, Fr* out_q,
                    Fr* out_wit) {
     if (S < 0) S = 3 * P;
@@ -377,25 +288,11 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
         H2SVD_LAUNCH_CHECK(ctx);
         return H2SVD_OK;
     }
-    // constants of this configuration (fr.cuh is host-callable)
     RescaleConsts k;
-    k.p = p;
-    fill_limb_consts(k.lc, lb, p.n_d > p.n_r ? p.n_d : p.n_r);
-    k.i_2S = fr::pow2(S);
-    k.i_pow_d = fr::pow2(p.n_d * lb);
-    k.i_bound_d = fr::pow2(A - P);
-    k.i_bound_d.l[0] |= 1u;  // 2^A / 2^P + 1   (A > P)
-    k.i_pow_r = fr::pow2(p.n_r * lb);
-    k.i_bound_r = fr::pow2(P);
-    k.m_2S = fr::to_mont(k.i_2S);
-    k.m_2SP = fr::to_mont(fr::pow2(S - P));
-    k.m_pow_d = fr::to_mont(k.i_pow_d);
-    k.m_bound_d = fr::to_mont(k.i_bound_d);
-    k.m_pow_r = fr::to_mont(k.i_pow_r);
-    k.m_bound_r = fr::to_mont(k.i_bound_r);
+    make_rescale_consts(P, lb, S, A, &k);
     H2SVD_SET_SMEM(ctx, rescale_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
-    const size_t cap = (size_t)ctx->sm_count * 3;  // 3 CTAs (69.6 KB of staging each) per SM, grid-stride beyond
+    const size_t cap = (size_t)ctx->sm_count * RS_CTAS_PER_SM;  // resident CTAs (staging-limited), grid-stride beyond
     if (blocks > cap) blocks = cap;
     rescale_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
     H2SVD_LAUNCH_CHECK(ctx);
@@ -439,7 +336,7 @@ int launch_abs_less_than(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count,
     k.m_bound = fr::to_mont(bound);
     H2SVD_SET_SMEM(ctx, abs_less_than_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
-    const size_t cap = (size_t)ctx->sm_count * 3;
+    const size_t cap = (size_t)ctx->sm_count * RS_CTAS_PER_SM;
     if (blocks > cap) blocks = cap;
     abs_less_than_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, y, out_wit, count, k);
     H2SVD_LAUNCH_CHECK(ctx);
@@ -468,7 +365,7 @@ int launch_range_check(h2svd_ctx* ctx, const Fr* x, size_t count, int range_bits
     k.c_shift = k.rem > 1 ? fr::mont_mul(k.m_shift, fr::to_mont(fr::pow2(32))) : fr::zero();
     H2SVD_SET_SMEM(ctx, range_check_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
-    const size_t cap = (size_t)ctx->sm_count * 3;
+    const size_t cap = (size_t)ctx->sm_count * RS_CTAS_PER_SM;
     if (blocks > cap) blocks = cap;
     range_check_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, out_wit, count, k);
     H2SVD_LAUNCH_CHECK(ctx);

@@ -1,0 +1,175 @@
+// Device-side pieces of the rescale witness generator (K4) shared by rescale.cu (stand-alone kernels) and
+// matmul_tc.cu (the mat-mul epilogue that emits the rescale witnesses of each C element as it is produced).
+// See rescale.cu for the cell model (FixedPointChip041::signed_div_scale, reference src/matrix/mod.rs:354-375).
+#pragma once
+#include "common.cuh"
+#include "fr_fast.cuh"
+
+namespace h2svd {
+namespace rs {
+
+constexpr int MAX_POS = 32;  // limb positions the staged kernel supports (n_d, n_r <= 32)
+
+struct RescaleParams {
+    int P, lb, S, A, n_d, n_r, W;
+};
+
+// Host-precomputed constants of one (P, lb, S, A) configuration, passed by value (constant bank).
+// limb-decomposition constants shared by every range-check style kernel
+struct LimbConsts {
+    int lb;
+    uint32_t lb_mask;
+    Fr c[MAX_POS];  // c[i] = 2^(lb*i) * 2^288 mod r
+};
+struct RescaleConsts {
+    RescaleParams p;
+    Fr i_2S, i_pow_d, i_bound_d, i_pow_r, i_bound_r;   // canonical integers
+    Fr m_2S, m_2SP, m_pow_d, m_bound_d, m_pow_r, m_bound_r;  // Montgomery forms
+    LimbConsts lc;
+};
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// one lane of the (converged) warp; ptxas then knows the guarded region runs single-threaded and
+// feeds the uniform-operand bulk copies without a per-lane serialisation loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+    return is_leader != 0;
+}
+
+// Per-lane witness stream: values go to this lane's shared-memory row; every CH values (and at the
+// end of the element) the warp ships its 32 rows to their places in out_wit.  cp.async.bulk takes
+// uniform operands, so ONE elected lane issues the 32 row copies of the warp (per-lane issue would be
+// serialised by the compiler into a 32-trip loop of ~14 instructions each -- measured: 44 % of all
+// executed instructions); the warp's 32 elements are consecutive, so row r goes to gbase + r*W.
+template <int CH, int NBUF>
+struct WitnessStreamT {
+    static constexpr int ROW_U4 = CH * 2 + 1;  // staging row in 16-byte units: CH witnesses + 16 B skew (conflict-free)
+    uint4* row0;      // this lane's two consecutive rows of ROW_U4 16-byte units
+    uint4* warp_row0; // lane 0's rows (the elected lane walks all 32)
+    Fr* gwarp;        // out_wit position of lane 0's element, advanced by every flush
+    int W, valid;     // distance (in witnesses) between the stripes of consecutive lanes -- W for consecutive elements;
+                      // lanes of this warp that hold a real element
+    int buf, fill;
+
+    __device__ __forceinline__ void put(const Fr& v) {
+        uint4* s = row0 + buf * ROW_U4 + 2 * fill;
+        s[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        s[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        if (++fill == CH) flush();
+    }
+    __device__ __forceinline__ void flush() {  // warp-uniform: every lane has the same `fill`
+        if (fill == 0) return;
+        // generic-proxy writes of every lane -> visible to the async proxy, then the elected lane ships
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (elect_one()) {
+            const uint32_t bytes = (uint32_t)(fill * sizeof(Fr));
+            uint32_t src = smem_addr(warp_row0 + buf * ROW_U4);
+            Fr* dst = gwarp;
+            for (int r = 0; r < valid; r++) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                             "r"(bytes)
+                             : "memory");
+                src += NBUF * ROW_U4 * sizeof(uint4);
+                dst += W;
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the rows written next were shipped NBUF-1 flushes ago: wait until the engine has read them
+            if (NBUF == 2)
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        gwarp += fill;
+        fill = 0;
+        if (NBUF == 2) buf ^= 1;
+    }
+};
+
+__device__ __forceinline__ Fr shr_small(const Fr& y, int s) {  // 1 <= s <= 32
+    Fr o;
+#pragma unroll
+    for (int j = 0; j < 7; j++) o.l[j] = __funnelshift_rc(y.l[j], y.l[j + 1], s);
+    o.l[7] = __funnelshift_rc(y.l[7], 0u, s);
+    return o;
+}
+
+// RangeChip::range_check(x, n*lb): limbs l_i and running sums s_i = x mod 2^(lb*(i+1)), Montgomery form
+template <class WS>
+__device__ __forceinline__ void stream_range_check(WS& ws, const LimbConsts& k, Fr y, int n) {
+    if (n == 1) return;
+    Fr sum;
+    for (int i = 0; i < n; i++) {
+        const uint32_t l = y.l[0] & k.lb_mask;
+        y = shr_small(y, k.lb);
+        const Fr ml = fr::mont_mul_small(l, k.c[0]);
+        ws.put(ml);
+        if (i == 0) {
+            sum = ml;
+        } else {
+            sum = fr::add_fast(sum, fr::mont_mul_small(l, k.c[i]));
+            ws.put(sum);
+        }
+    }
+}
+
+// RangeChip::check_big_less_than_safe(x, B)
+template <class WS>
+__device__ __forceinline__ void stream_cbls(WS& ws, const LimbConsts& k, const Fr& x_int,
+                                            const Fr& x_mont, int n, const Fr& i_pow, const Fr& i_bound,
+                                            const Fr& m_pow, const Fr& m_bound) {
+    stream_range_check(ws, k, x_int, n);
+    const Fr chk_int = fr::sub_fast(fr::add_fast(x_int, i_pow), i_bound);  // x + 2^bits - B (mod r)
+    const Fr m_xp = fr::add_fast(x_mont, m_pow);
+    ws.put(fr::sub_fast(m_xp, m_bound));
+    ws.put(m_xp);
+    stream_range_check(ws, k, chk_int, n);
+}
+
+// Unstaged alternative with the same interface: every lane writes its witnesses straight to its own stripe with one
+// 32-byte store each (st.global.v8.b32, sm_100+).  No shared memory, no waits: for callers whose stores ride under
+// other work (the mat-mul epilogue), where L2 write-back merges a lane's consecutive 32-byte sectors into full lines.
+struct DirectStream {
+    Fr* g;       // this lane's next witness slot
+    bool live;   // lanes without a real element compute along and store nothing
+    __device__ __forceinline__ void put(const Fr& v) {
+        if (live)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(g), "r"(v.l[0]), "r"(v.l[1]),
+                         "r"(v.l[2]), "r"(v.l[3]), "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7])
+                         : "memory");
+        g++;
+    }
+    __device__ __forceinline__ void flush() {}
+};
+
+// One element of rescale_matrix: the W witnesses of signed_div_scale(c) go to `ws` in assignment order, the quotient
+// (Montgomery form) is returned.  Warp-uniform control flow (every lane streams the same number of witnesses).
+template <class WS>
+__device__ __forceinline__ Fr rescale_element(WS& ws, const RescaleConsts& k, const Fr& am) {
+    const Fr a = fr::from_mont_fast(am);                    // canonical integer
+    const Fr ash = fr::add_fast(a, k.i_2S);                 // gate.add(a, Constant(2^S))
+    const Fr div = fr::shr(ash, k.p.P);                     // div_mod_floor by 2^P
+    const Fr rem = fr::low_bits(ash, k.p.P);
+    const Fr m_div = fr::to_mont_fast(div);
+    const Fr m_rem = fr::to_mont_fast(rem);
+    ws.put(fr::add_fast(am, k.m_2S));
+    ws.put(m_rem);
+    ws.put(m_div);
+    stream_cbls(ws, k.lc, div, m_div, k.p.n_d, k.i_pow_d, k.i_bound_d, k.m_pow_d, k.m_bound_d);
+    stream_cbls(ws, k.lc, rem, m_rem, k.p.n_r, k.i_pow_r, k.i_bound_r, k.m_pow_r, k.m_bound_r);
+    const Fr q = fr::sub_fast(m_div, k.m_2SP);              // gate.sub(div, Constant(2^(S-P)))
+    ws.put(q);
+    ws.flush();
+    return q;
+}
+
+}  // namespace rs
+
+// host side (rescale.cu): the constants of one (P, lb, S, A) configuration; returns W, or -1 if the parameters are out
+// of range or need more limb positions than the staged kernels support
+int make_rescale_consts(int P, int lb, int S, int A, rs::RescaleConsts* out);
+
+}  // namespace h2svd

@@ -314,6 +314,14 @@ class Handle:
                                                       lookup_bits, shift_bits, a_num_bits,
                                                       self._tp(out_q), self._tp(out_wit)))
 
+    def fr_matmul_rescale_dev(self, a, b, c_s, precision_bits: int, lookup_bits: int, out_q, out_wit,
+                              shift_bits: int = -1, a_num_bits: int = -1) -> None:
+        """c_s = a.b and the rescale_matrix witnesses of c_s in one call."""
+        n, k, m = a.shape[0], a.shape[1], b.shape[1]
+        _ffi.check(self._lib.h2svd_fr_matmul_rescale_dev(self._h, self._tp(a), self._tp(b), n, k, m, precision_bits,
+                                                        lookup_bits, shift_bits, a_num_bits, self._tp(c_s),
+                                                        self._tp(out_q), self._tp(out_wit)))
+
     def zkvec_inner_prefix_dev(self, x, self_, out) -> None:
         batch, ln = x.shape[0], x.shape[1]
         _ffi.check(self._lib.h2svd_zkvec_inner_prefix_dev(self._h, self._tp(x), self._tp(self_), batch, ln,
@@ -353,6 +361,11 @@ def set_matmul_karatsuba(v: int) -> None:
 def last_matmul_engine() -> str:
     """Which engine the last fr_matmul launch of this process used (bench.py reports the matching roofline)."""
     return {0: "schoolbook", 1: "karatsuba", 2: "tensor"}.get(_ffi.load().h2svd_debug_last_matmul_engine(), "none")
+
+
+def set_fuse_rescale(v: int) -> None:
+    """Tuning hook: 1 = emit the rescale witnesses from the tensor-core mat-mul epilogue (experimental), 0 = off (default)."""
+    _ffi.load().h2svd_debug_set_fuse_rescale(v)
 
 
 def set_matmul_tc(v: int) -> None:

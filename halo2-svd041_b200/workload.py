@@ -123,6 +123,17 @@ def _bv_running_sums(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, com
     return bufs.bv_local
 
 
+def step_matmul_rescale(backend, plan: ShardPlan, bufs: StepBuffers, precision_bits: int, lookup_bits: int) -> None:
+    """honest_prover_mat_mul (:546) + rescale_matrix (:354) of this rank's rows of C through the one-call entry point
+    h2svd_fr_matmul_rescale_dev (two kernels back to back, or the experimental fused launch when the tuning hook is on)."""
+    fused = getattr(backend, "fr_matmul_rescale_dev", None)
+    if fused is None:   # CPU stand-in of the sharding tests
+        step_matmul(backend, plan, bufs)
+        step_rescale(backend, plan, bufs, precision_bits, lookup_bits)
+        return
+    fused(bufs.a_slab, bufs.b, bufs.c_slab, precision_bits, lookup_bits, bufs.q_slab, bufs.wit_slab)
+
+
 def step_freivalds_pre(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None):
     """The part of ZkMatrix::verify_mul (:299) that does not need C: gamma powers (:316-326), the B.v
     running sums of this rank's rows of B (:336), the one exchange step (the all-gather of the k row

@@ -135,6 +135,13 @@ int h2svd_rescale_witness_dev(h2svd_ctx *ctx, const h2svd_fr *c_s, size_t count,
                               int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
                               h2svd_fr *out_q, h2svd_fr *out_wit);
 
+/* honest_prover_mat_mul followed by rescale_matrix of the product (the README.md:34-47 sequence; src/matrix/mod.rs:546
+ * then :354): c_s = A.B, out_q / out_wit exactly as h2svd_rescale_witness_dev(c_s, n*m, ...) would fill them.  Runs the
+ * two kernels back to back (an experimental fused launch exists behind a tuning hook; same bytes).  Device pointers. */
+int h2svd_fr_matmul_rescale_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, size_t n, size_t k,
+                                size_t m, int precision_bits, int lookup_bits, int shift_bits,
+                                int a_num_bits, h2svd_fr *c_s, h2svd_fr *out_q, h2svd_fr *out_wit);
+
 /* ---- range-check witnesses of the SVD verifier's helpers ---------------------------------------------
  * h2svd_abs_less_than_witness: check_abs_less_than (src/matrix/mod.rs:425-437) for `count` elements, optionally of a
  *   difference (check_mat_diff :441-459, check_mat_id :461-483; pass y = NULL for check_mat_entries_bounded :490-501):

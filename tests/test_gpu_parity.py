@@ -384,6 +384,36 @@ def test_dev_entry_points_with_torch_tensors(handle):
     assert handle.launch_count == before + 1
 
 
+@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("n,k,m,P,lb", [(8, 8, 8, 42, 19), (64, 64, 64, 63, 19), (130, 300, 20, 63, 19),
+                                        (100, 1500, 77, 32, 12), (256, 128, 200, 63, 19)])
+def test_fr_matmul_rescale_one_call(handle, pkg, fuse, n, k, m, P, lb):
+    """h2svd_fr_matmul_rescale_dev: C, quotients and rescale witnesses of the product in one call, as two kernels
+    (default) and with the experimental fused tensor-core epilogue: both byte-identical to the oracle."""
+    import torch
+    rng = np.random.default_rng(n + k + m + P)
+    a, b = quantized_matrix(rng, n, k, P), quantized_matrix(rng, k, m, P)
+    dev = torch.device("cuda", handle.device)
+    ta = torch.from_numpy(a.view(np.int64)).to(dev)
+    tb = torch.from_numpy(b.view(np.int64)).to(dev)
+    W = handle.rescale_witness_count(P, lb)
+    tc = torch.full((n, m, 4), -1, dtype=torch.int64, device=dev)
+    tq = torch.full((n, m, 4), -1, dtype=torch.int64, device=dev)
+    tw = torch.full((n * m, W, 4), -1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    try:
+        pkg.set_fuse_rescale(fuse)
+        handle.fr_matmul_rescale_dev(ta, tb, tc, P, lb, tq, tw)
+        handle.sync()
+    finally:
+        pkg.set_fuse_rescale(0)
+    c = corac.field_mat_mul(a, b)
+    q, _rem, wit = corac.rescale_witness(c.reshape(-1, 4), P, lb, threads=0)
+    assert _eq(tc.cpu().numpy().view(np.uint64), c)
+    assert _eq(tq.cpu().numpy().view(np.uint64).reshape(-1, 4), q)
+    assert _eq(tw.cpu().numpy().view(np.uint64), wit)
+
+
 # ---------------------------------------------------------------- fused, slab-pipelined sequence
 @pytest.mark.parametrize("rows,k,m,P,bv", [(8, 8, 8, 42, None), (37, 20, 45, 63, (3, 11)), (300, 64, 700, 32, None)])
 def test_zkmatrix_mul_witness_fused_matches_oracle(handle, pkg, rows, k, m, P, bv):

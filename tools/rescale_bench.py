@@ -21,6 +21,7 @@ for (N, P, lb) in ((1024, 63, 19), (1024, 32, 19), (2048, 63, 19)):
         e0.record(stream); h.rescale_witness_dev(cs, N * N, P, lb, q, wit); e1.record(stream); e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     b = N * N * 32 * (1 + W)
-    print(f"N={N} P={P} lb={lb} W={W}: best {min(ts[2:]):.4f} ms med {np.median(ts[2:]):.4f} ms -> {b/min(ts[2:])/1e6:.0f} GB/s", flush=True)
+    chk = int(wit.sum().item()) ^ int(q.sum().item())
+    print(f"chk={chk & 0xffffffff:08x} N={N} P={P} lb={lb} W={W}: best {min(ts[2:]):.4f} ms med {np.median(ts[2:]):.4f} ms -> {b/min(ts[2:])/1e6:.0f} GB/s", flush=True)
     del wit, q, cs, a
 h.close()
