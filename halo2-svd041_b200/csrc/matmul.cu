@@ -1,4 +1,5 @@
-// K1: C = A * B over BN254-Fr  (replaces reference src/matrix/mod.rs:510-537 field_mat_mul).
+// K1: C = A * B over BN254-Fr  (replaces reference src/matrix/mod.rs:510-537 field_mat_mul): the integer-pipe (IMAD)
+// engines and the dispatch between them and the tensor-core engine of matmul_tc.cu (launch_fr_matmul, at the end).
 //
 // Design (sm_100a, integer-pipe bound -- see DESIGN.md "K1"):
 //  * CTA tile (16*TM) x (16*TN) of C, 256 consumer threads in a 16x16 layout, each owning a TM x TN

@@ -62,7 +62,10 @@ uint64_t h2svd_launch_count(h2svd_ctx *ctx);
  * honest_prover_mat_mul (:546-568).  c[n x m] = a[n x k] * b[k x m] over Fr.  With
  * b_transposed != 0, `b` holds the m x k matrix B^T (what ZkMatrix::transpose_matrix, :408, would
  * have been called on), so callers such as check_svd_phase0 (src/svd/mod.rs:96,109,112) need not
- * materialise the transpose.  Asserts of the reference (:515) become H2SVD_EINVAL. */
+ * materialise the transpose.  Asserts of the reference (:515) become H2SVD_EINVAL.
+ * Two engines compute the same bytes: from 64^3 on (and k >= 32) the product runs on the tensor cores as exact u8 x u8
+ * integer MMAs over the 32 byte planes of each operand (csrc/matmul_tc.cu), smaller products on the integer pipe
+ * (csrc/matmul.cu).  The choice is internal; results do not depend on it. */
 int h2svd_fr_matmul(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *c, size_t n,
                     size_t k, size_t m, int b_transposed);
 int h2svd_fr_matmul_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *c,
