@@ -816,7 +816,12 @@ static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, i
 // Forcing one of the IMAD engines / schedules through the triage hooks switches the automatic choice off.
 static bool use_tensor_engine(size_t n, size_t k, size_t m) {
     const bool imad_forced = g_kara >= 0 || g_streamk >= 0 || g_variant != 0;
-    const bool tc = g_matmul_tc == 1 || (g_matmul_tc < 0 && !imad_forced && k >= 32 && n * k * m >= (1ull << 18));
+    // a handful of 128 x 8 tiles with a long k (e.g. 64 x 4096 x 64: 0.31 vs 0.15 ms) is the one skinny shape the IMAD
+    // engines win: their stream-K schedule splits k over the SMs, the tensor-core kernel walks it tile by tile
+    const size_t tiles = ((n + 127) / 128) * ((m + 7) / 8);
+    const bool few_long = tiles * 8 < 148 && k > 2048;
+    const bool tc = g_matmul_tc == 1 ||
+                    (g_matmul_tc < 0 && !imad_forced && !few_long && k >= 32 && n * k * m >= (1ull << 18));
     return tc && fr_matmul_tc_supported(n, k, m);
 }
 
