@@ -241,3 +241,34 @@ def test_fr_modulus_is_the_order_of_the_reference_srs_points():
         assert mul(po.R_MOD - 1, (x, y)) == (x, (-y) % q)
     g = fx["points"][0]
     assert int.from_bytes(bytes.fromhex(g["x_mont_le_hex"]), "little") * rinv % q == 1     # g[0] is the generator (1, 2)
+
+
+def test_byte_plane_diagonal_identity_of_the_tensor_core_engine():
+    """The algorithm of csrc/matmul_tc.cu restated with numpy integers: splitting Montgomery-form operands into their 32
+    bytes, sum_k a_k*b_k = sum_d 2^(8d) * D_d with D_d = sum_{p+q=d} sum_k a_p(k)*b_q(k) (u8 x u8 products, 63 diagonals);
+    every D_d of a 1024-long pass stays below 2^31, so 32-bit accumulators are exact; one Montgomery reduction of the
+    recombined integer gives the same canonical bytes as the reference's chain of `elem += a*b` (the oracle)."""
+    assert 32 * 1024 * 255 * 255 < 1 << 31
+    rng = random.Random(99)
+    k = 1024
+    a = [rng.randrange(po.R_MOD) for _ in range(k)]
+    b = [rng.randrange(po.R_MOD) for _ in range(k)]
+    a[0], b[1], a[2], b[2] = 0, po.R_MOD - 1, po.R_MOD - 1, po.R_MOD - 1
+    a[3] = b[3] = (0x2f << 248) | ((1 << 248) - 1)          # the largest canonical value with 31 low bytes of 0xff
+    am = [po.to_mont(x) for x in a]
+    bm = [po.to_mont(x) for x in b]
+    planes_a = np.array([[(x >> (8 * p)) & 0xff for x in am] for p in range(32)], dtype=np.int64)   # [p][k]
+    planes_b = np.array([[(x >> (8 * q)) & 0xff for x in bm] for q in range(32)], dtype=np.int64)   # [q][k]
+    pq = planes_a @ planes_b.T                                                                     # [p][q] = sum_k
+    diag = [int(sum(pq[p, d - p] for p in range(32) if 0 <= d - p < 32)) for d in range(63)]
+    assert max(diag) < 1 << 31
+    T = sum(dg << (8 * d) for d, dg in enumerate(diag))
+    assert T == sum(x * y for x, y in zip(am, bm))
+    assert T < 1 << 540                                      # fr::reduce_wide_acc's precondition (18 limbs)
+    got = T * po.MONT_RINV % po.R_MOD                        # one Montgomery reduction per C element
+    want = po.to_mont(sum(x * y for x, y in zip(a, b)) % po.R_MOD)
+    assert got == want
+    # ... and the C oracle's field_mat_mul (the reference's loop restated) agrees on the same 1 x k . k x 1 product
+    from tests.util import raw_limbs
+    c = corac.field_mat_mul(raw_limbs(am).reshape(1, k, 4), raw_limbs(bm).reshape(k, 1, 4))
+    assert [int(v) for v in c[0, 0]] == [int(v) for v in raw_limbs([want])[0]]
