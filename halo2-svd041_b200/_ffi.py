@@ -86,7 +86,6 @@ DEBUG_SIGNATURES = {
     "h2svd_debug_set_matvec_warp_kernel": (_I, [_I]),
     "h2svd_debug_set_matmul_tc": (_I, [_I]),
     "h2svd_debug_set_fuse_rescale": (_I, [_I]),
-    "h2svd_debug_set_tc_two_cta": (_I, [_I]),
     "h2svd_debug_last_matmul_engine": (_I, []),
 }
 

@@ -433,284 +433,6 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
 }
 
-// ---- 2-CTA variant --------------------------------------------------------------------------------------
-// Same algorithm on a CTA PAIR (cluster of 2, tcgen05 cta_group::2): the tile is 256 rows x 8 columns of C, each CTA
-// holds its own 128 rows of the A plane and HALF of the B operand (16 of the 32 planes q), and the pair's tensor cores
-// share the B halves -- per SM the MMAs read 64 instead of 96 B/clk from shared memory, which is the bandwidth the fused
-// rescale epilogue needs for its witness staging.  Protocol differences to the 1-CTA kernel:
-//  * full barriers live in the leader (rank 0): both producers arrive there, both CTAs' TMA loads complete there;
-//  * only the leader issues MMAs; its commits are multicast to the empty / tmem_full barriers of both CTAs;
-//  * the epilogue warps of both CTAs release the accumulators on the leader's tmem_empty barrier;
-//  * TMEM is allocated / freed by warp 1 of both CTAs together; cluster barriers bracket the kernel.
-constexpr uint32_t TC2_B_BYTES = 16 * TC_BJ * TC_BKB;  // this CTA's half of the B operand: 16 KB
-constexpr int TC2_SA_PLAIN = 12, TC2_SA_FUSED = 5;
-using Tc2WitnessStream = rs::WitnessStreamT<6, 1>;
-constexpr uint32_t TC2_STAGE_BYTES = 16 * 32 * Tc2WitnessStream::ROW_U4 * 16;
-constexpr size_t tc2_smem_bytes(bool fused) {
-    return (size_t)(fused ? TC2_SA_FUSED : TC2_SA_PLAIN) * TC_A_BYTES + (size_t)TC_SB * TC2_B_BYTES + 256 + 1024 +
-           (fused ? TC2_STAGE_BYTES : 0);
-}
-static_assert(tc2_smem_bytes(true) <= 232448, "2-CTA fused kernel: shared memory");
-// M = 256 (two CTAs x 128 rows), N = 256
-constexpr uint32_t TC2_IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
-
-__device__ __forceinline__ uint32_t tc_cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void tc_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t tc_mapa(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void tc_mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tc2_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
-        : "memory");
-}
-__device__ __forceinline__ void tc2_tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                           uint32_t bar_cluster) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
-        : "memory");
-}
-__device__ __forceinline__ void tc2_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
-        "}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC2_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u),
-        "r"(0u), "r"(0u), "r"(0u)
-        : "memory");
-}
-// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc2_commit(uint32_t bar) {
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(mask)
-                 : "memory");
-}
-// zero this warp's accumulator columns, then one arrive per warp on the LEADER's tmem_empty barrier
-__device__ __forceinline__ void tc2_zero_and_release(uint32_t tcol0, int cnt, uint32_t leader_bar, int lane) {
-#pragma unroll 9
-    for (int d = 0; d < 63; d++) {
-        tc_st2_zero(tcol0 + 8u * d);
-        if (cnt == 3) tc_st1_zero(tcol0 + 8u * d + 2);  // warp-uniform
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) tc_mbar_arrive_cluster(leader_bar);
-}
-
-template <bool FUSE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(FUSE), 1)
-fr_matmul_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                     Fr* __restrict__ c, int n, int k, int m, int tiles_j, int num_tiles, int* err,
-                     const __grid_constant__ rs::RescaleConsts kc, Fr* __restrict__ out_q, Fr* __restrict__ out_wit) {
-    constexpr int SA = FUSE ? TC2_SA_FUSED : TC2_SA_PLAIN;
-    constexpr int EPI_WARPS = 16;
-    constexpr int MAXC = TC_BJ / (EPI_WARPS / 4);
-    extern __shared__ uint8_t tc_smem_raw[];
-    const uint32_t raw = tc_smem_u32(tc_smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t* smem = tc_smem_raw + (base - raw);
-    const uint32_t s_a = base, s_b = base + SA * TC_A_BYTES;
-    const uint32_t bars = s_b + TC_SB * TC2_B_BYTES;
-    const uint32_t full_a = bars, empty_a = bars + 8 * SA, full_b = bars + 16 * SA, empty_b = full_b + 8 * TC_SB,
-                   tmem_full = empty_b + 8 * TC_SB, tmem_empty = tmem_full + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (tmem_empty + 8 - base));
-    uint4* stage = reinterpret_cast<uint4*>(smem + (bars + 256 - base));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = tc_cluster_rank();
-    const bool leader = rank == 0;
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < SA; s++) {
-            tc_mbar_init(full_a + 8 * s, 2);   // both producers arrive (on the leader's copy)
-            tc_mbar_init(empty_a + 8 * s, 1);  // one multicast commit
-        }
-        for (int s = 0; s < TC_SB; s++) {
-            tc_mbar_init(full_b + 8 * s, 2);
-            tc_mbar_init(empty_b + 8 * s, 1);
-        }
-        tc_mbar_init(tmem_full, 1);
-        tc_mbar_init(tmem_empty, 2 * EPI_WARPS);  // one arrive per epilogue warp of both CTAs (leader's copy)
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    tc_cluster_sync();  // both CTAs' barriers exist before anything remote touches them
-    if (warp == 1) {    // collective of warp 1 of both CTAs
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    tc_cluster_sync();
-    tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-
-    const int kblocks = (k + TC_BKB - 1) / TC_BKB;
-    const int passes = (kblocks + TC_KB_PASS - 1) / TC_KB_PASS;
-    // the leader's copies of the barriers both producers / all epilogue warps signal
-    const uint32_t l_full_a = tc_mapa(full_a, 0), l_full_b = tc_mapa(full_b, 0), l_tmem_empty = tc_mapa(tmem_empty, 0);
-
-    if (warp == 0) {
-        // ===== TMA producer (both CTAs: own A rows, own half of B) =====
-        if (lane == 0) {
-            uint32_t ua = 0, ub = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int ib = tile / tiles_j, jb = tile % tiles_j;
-                const int row0 = ib * 2 * TC_BM + (int)rank * TC_BM;
-                for (int kb = 0; kb < kblocks; kb++) {
-                    const uint32_t sb = ub % TC_SB;
-                    tc_mbar_wait(empty_b + 8 * sb, ((ub / TC_SB) & 1) ^ 1, err);
-                    if (leader) tc_mbar_expect_tx(full_b + 8 * sb, 2 * TC2_B_BYTES);  // arrive + bytes of both halves
-                    else tc_mbar_arrive_cluster(l_full_b + 8 * sb);
-                    tc2_tma_3d(s_b + sb * TC2_B_BYTES, &tm_b, kb * TC_BKB, jb * TC_BJ, 16 * (int)rank, l_full_b + 8 * sb);
-                    ub++;
-                    for (int p = 0; p < 32; p++) {
-                        const uint32_t sa = ua % SA;
-                        tc_mbar_wait(empty_a + 8 * sa, ((ua / SA) & 1) ^ 1, err);
-                        if (leader) tc_mbar_expect_tx(full_a + 8 * sa, 2 * TC_A_BYTES);
-                        else tc_mbar_arrive_cluster(l_full_a + 8 * sa);
-                        tc2_tma_2d(s_a + sa * TC_A_BYTES, &tm_a, kb * TC_BKB, p * n + row0, l_full_a + 8 * sa);
-                        ua++;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (leader CTA only) =====
-        if (leader) {
-            uint32_t ua = 0, ub = 0, round = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                for (int pass = 0; pass < passes; pass++) {
-                    tc_mbar_wait(tmem_empty, round & 1, err);
-                    tc_fence_after();
-                    const int kb_end = min(kblocks, (pass + 1) * TC_KB_PASS);
-                    for (int kb = pass * TC_KB_PASS; kb < kb_end; kb++) {
-                        const uint32_t sb = ub % TC_SB;
-                        tc_mbar_wait(full_b + 8 * sb, (ub / TC_SB) & 1, err);
-                        const uint64_t bdesc = tc_smem_desc(s_b + sb * TC2_B_BYTES);
-                        for (int p = 0; p < 32; p++) {
-                            const uint32_t sa = ua % SA;
-                            tc_mbar_wait(full_a + 8 * sa, (ua / SA) & 1, err);
-                            tc_fence_after();
-                            if (lane == 0) {
-                                const uint64_t adesc = tc_smem_desc(s_a + sa * TC_A_BYTES);
-#pragma unroll
-                                for (int s = 0; s < TC_BKB / 32; s++)
-                                    tc2_mma_i8(tmem_base + 8u * p, adesc + 2u * s, bdesc + 2u * s, 1u);
-                                tc2_commit(empty_a + 8 * sa);
-                            }
-                            __syncwarp();
-                            ua++;
-                        }
-                        if (lane == 0) tc2_commit(empty_b + 8 * sb);
-                        __syncwarp();
-                        ub++;
-                    }
-                    if (lane == 0) tc2_commit(tmem_full);
-                    __syncwarp();
-                    round++;
-                }
-            }
-        }
-    } else {
-        // ===== epilogue (both CTAs: own 128 rows) =====
-        const uint32_t quarter = warp & 3;
-        const int il = quarter * 32 + lane;
-        const int jg = (warp - 2) >> 2;
-        const int j0 = jg * MAXC;
-        const int cnt = TC_BJ - j0 < MAXC ? TC_BJ - j0 : MAXC;
-        const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
-        tc2_zero_and_release(tlane + j0, cnt, l_tmem_empty, lane);
-        Tc2WitnessStream ws;
-        if (FUSE) {
-            ws.warp_row0 = stage + (size_t)(warp - 2) * 32 * Tc2WitnessStream::ROW_U4;
-            ws.row0 = ws.warp_row0 + (size_t)lane * Tc2WitnessStream::ROW_U4;
-            ws.W = m * kc.p.W;
-            ws.buf = 0;
-            ws.fill = 0;
-        }
-        uint32_t round = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-            const int ib = tile / tiles_j, jb = tile % tiles_j;
-            const int row_base = ib * 2 * TC_BM + (int)rank * TC_BM;
-            const int gi = row_base + il;
-            for (int pass = 0; pass < passes; pass++) {
-                tc_mbar_wait(tmem_full, round & 1, err);
-                tc_fence_after();
-                uint32_t dg[MAXC][64];
-#pragma unroll
-                for (int d = 0; d < 63; d++) tc_ld2(tlane + 8u * d + j0, dg[0][d], dg[1][d]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int d = 0; d < 63; d++)
-#pragma unroll
-                    for (int q = 0; q < MAXC; q++) asm volatile("" : "+r"(dg[q][d]));
-                uint32_t T[MAXC][18];
-#pragma unroll
-                for (int q = 0; q < MAXC; q++) {
-                    dg[q][63] = 0;
-                    tc_carry_diagonals(dg[q], T[q]);
-                }
-                tc_fence_before();
-                tc2_zero_and_release(tlane + j0, cnt, l_tmem_empty, lane);
-                Fr res[MAXC];
-#pragma unroll
-                for (int q = 0; q < MAXC; q++) {
-                    res[q] = fr::reduce_wide_acc(T[q]);
-                    const int gj = jb * TC_BJ + j0 + q;
-                    if (q < cnt && gi < n && gj < m) {
-                        Fr* dst = c + (size_t)gi * m + gj;
-                        if (pass > 0) res[q] = fr::add(ld_fr(dst), res[q]);
-                        st_fr(dst, res[q]);
-                    }
-                }
-                if (FUSE && pass == passes - 1) {
-                    const int row0 = row_base + (int)quarter * 32;
-                    const int valid = n - row0 < 32 ? n - row0 : 32;
-#pragma unroll
-                    for (int q = 0; q < MAXC; q++) {
-                        const int gj = jb * TC_BJ + j0 + q;
-                        if (q < cnt && gj < m && valid > 0) {  // warp-uniform
-                            ws.valid = valid;
-                            ws.gwarp = out_wit + ((size_t)row0 * m + gj) * (size_t)kc.p.W;
-                            const Fr qv = rs::rescale_element(ws, kc, gi < n ? res[q] : fr::zero());
-                            if (gi < n) st_fr(out_q + (size_t)gi * m + gj, qv);
-                        }
-                    }
-                }
-                round++;
-            }
-        }
-        if (FUSE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-    // neither CTA may exit (or free TMEM) while its partner can still read its shared memory or signal its barriers
-    tc_fence_before();
-    tc_cluster_sync();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
 typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -730,7 +452,6 @@ tc_encode_fn tc_encoder() {
 }  // namespace
 
 int g_matmul_tc = -1;  // -1 auto, 0 off, 1 force (triage hook; see launch_fr_matmul)
-int g_tc_two_cta = 0;   // 1: CTA-pair kernel (cta_group::2) instead of the 1-CTA kernel (tuning hook)
 
 bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
     // p * n + ib * 128 and the plane sizes are 32-bit TMA coordinates / comfortably below 2^31
@@ -795,36 +516,6 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
             return H2SVD_ECUDA;
         }
     }
-    if (g_tc_two_cta) {
-        // CTA-pair kernel: 256-row tiles, each CTA loads 16 of the 32 byte planes of B per K block
-        CUtensorMap tm_b2;
-        const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)m, 32};
-        const cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)(m * ldk)};
-        const cuuint32_t box[3] = {(cuuint32_t)TC_BKB, (cuuint32_t)TC_BJ, 16};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult r = encode(&tm_b2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, b8, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("fr_matmul (tensor-core engine): tensor map for B halves failed (CUresult %d)", (int)r);
-            return H2SVD_ECUDA;
-        }
-        const int tj = (int)((m + TC_BJ - 1) / TC_BJ);
-        const long long tiles2 = (long long)((n + 2 * TC_BM - 1) / (2 * TC_BM)) * tj;
-        const int pairs = (int)(tiles2 < ctx->sm_count / 2 ? tiles2 : ctx->sm_count / 2);
-        static const rs::RescaleConsts none2{};
-        if (fuse) {
-            H2SVD_SET_SMEM(ctx, fr_matmul_tc2_kernel<true>, tc2_smem_bytes(true));
-            fr_matmul_tc2_kernel<true><<<2 * pairs, tc_threads(true), tc2_smem_bytes(true), ctx->stream>>>(
-                tm_a, tm_b2, c, (int)n, (int)k, (int)m, tj, (int)tiles2, ctx->d_flag, *fuse, out_q, out_wit);
-        } else {
-            H2SVD_SET_SMEM(ctx, fr_matmul_tc2_kernel<false>, tc2_smem_bytes(false));
-            fr_matmul_tc2_kernel<false><<<2 * pairs, tc_threads(false), tc2_smem_bytes(false), ctx->stream>>>(
-                tm_a, tm_b2, c, (int)n, (int)k, (int)m, tj, (int)tiles2, ctx->d_flag, none2, nullptr, nullptr);
-        }
-        H2SVD_LAUNCH_CHECK(ctx);
-        return H2SVD_OK;
-    }
     const int tiles_i = (int)((n + TC_BM - 1) / TC_BM), tiles_j = (int)((m + TC_BJ - 1) / TC_BJ);
     const long long tiles = (long long)tiles_i * tiles_j;
     if (tiles >= (1LL << 31)) {
@@ -848,10 +539,6 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
 
 }  // namespace h2svd
 
-extern "C" int h2svd_debug_set_tc_two_cta(int v) {
-    h2svd::g_tc_two_cta = v;
-    return 0;
-}
 extern "C" int h2svd_debug_set_matmul_tc(int v) {
     h2svd::g_matmul_tc = v;
     return 0;

@@ -363,11 +363,6 @@ def last_matmul_engine() -> str:
     return {0: "schoolbook", 1: "karatsuba", 2: "tensor"}.get(_ffi.load().h2svd_debug_last_matmul_engine(), "none")
 
 
-def set_tc_two_cta(v: int) -> None:
-    """Tuning hook: 1 = CTA-pair (cta_group::2) tensor-core mat-mul kernel, 0 = one CTA per tile (default)."""
-    _ffi.load().h2svd_debug_set_tc_two_cta(v)
-
-
 def set_fuse_rescale(v: int) -> None:
     """Tuning hook: 1 = emit the rescale witnesses from the tensor-core mat-mul epilogue (experimental), 0 = off (default)."""
     _ffi.load().h2svd_debug_set_fuse_rescale(v)

@@ -20,8 +20,6 @@ def main():
     h = pkg.Handle(0, stream.cuda_stream)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(5)
-    if os.environ.get("TC2"):
-        pkg.set_tc_two_cta(1)   # CTA-pair kernel
     for P, lb in ((63, 19), (32, 12)):
         W = h.rescale_witness_count(P, lb)
         for n, k, m in shapes:

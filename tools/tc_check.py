@@ -28,8 +28,6 @@ def main():
     h = pkg.Handle(0, stream.cuda_stream)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(11)
-    if os.environ.get("TC2"):
-        pkg.set_tc_two_cta(1)   # CTA-pair kernel
     for n, k, m in shapes:
         a, b = rand_fr(gen, n, k), rand_fr(gen, k, m)
         if n >= 4 and k >= 4 and m >= 2:  # edge values: zero, one (Montgomery R mod r), r-1 patterns already canonical
