@@ -129,22 +129,6 @@ __device__ __forceinline__ void stream_cbls(WS& ws, const LimbConsts& k, const F
     stream_range_check(ws, k, chk_int, n);
 }
 
-// Unstaged alternative with the same interface: every lane writes its witnesses straight to its own stripe with one
-// 32-byte store each (st.global.v8.b32, sm_100+).  No shared memory, no waits: for callers whose stores ride under
-// other work (the mat-mul epilogue), where L2 write-back merges a lane's consecutive 32-byte sectors into full lines.
-struct DirectStream {
-    Fr* g;       // this lane's next witness slot
-    bool live;   // lanes without a real element compute along and store nothing
-    __device__ __forceinline__ void put(const Fr& v) {
-        if (live)
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(g), "r"(v.l[0]), "r"(v.l[1]),
-                         "r"(v.l[2]), "r"(v.l[3]), "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7])
-                         : "memory");
-        g++;
-    }
-    __device__ __forceinline__ void flush() {}
-};
-
 // One element of rescale_matrix: the W witnesses of signed_div_scale(c) go to `ws` in assignment order, the quotient
 // (Montgomery form) is returned.  Warp-uniform control flow (every lane streams the same number of witnesses).
 template <class WS>
