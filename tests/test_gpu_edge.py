@@ -79,9 +79,12 @@ def test_two_handles_on_two_devices_in_one_process(pkg):
     gamma = random_fr(rng, 1)
     want = corac.field_mat_mul(a, b)
     ew = corac.rescale_witness(want.reshape(-1, 4), 63, 19)[2]
+    a2, b2 = random_fr(rng, 96, 80), random_fr(rng, 80, 72)     # large enough for the tensor-core mat-mul engine
+    want2 = corac.field_mat_mul(a2, b2)
     for dev in (1, 0, 1):
         with pkg.Handle(dev) as h:
             res = h.zkmatrix_mul_witness(a, b, gamma, 63, 19)
             assert _eq(res["c_s"], want) and _eq(res["wit"], ew) and not res["diff"].any()
+            assert _eq(h.fr_matmul(a2, b2), want2) and pkg.last_matmul_engine() == "tensor"
             x, s = random_fr(rng, 700, 300), random_fr(rng, 700, 300)
             assert _eq(h.zkvec_inner_prefix(x, s), corac.zkvec_inner_prefix(x, s))
