@@ -97,7 +97,7 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity, int*
     while (!tc_mbar_try(bar, parity)) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) {  // 4 s
+        if (t1 - t0 > 10000000000ull) {  // 10 s
             atomicExch(err, 3);
             __trap();
         }
