@@ -141,11 +141,6 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
-    uint32_t v;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
-    return v;
-}
 __device__ __forceinline__ void tc_ld2(uint32_t taddr, uint32_t& v0, uint32_t& v1) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(taddr));
 }
