@@ -239,7 +239,9 @@ def run_gpu(args) -> None:
     # Measured at N=1024 on one GPU (step, ms): no side stream 1.170; C-independent mat-vecs under the tensor-core
     # mat-mul and C.v next to the rescale 1.116 (the mat-mul gives back most of what the mat-vecs save: they compete
     # for shared-memory bandwidth); all three mat-vecs next to the rescale 1.143 (its CTAs fill the SMs, the side
-    # kernels only start as they drain).  With several ranks the first schedule also hides the all-gather latency.
+    # kernels only start as they drain); C-independent mat-vecs beside a hoisted operand split, the mat-mul after both
+    # 1.162 (they take 130 us next to the split kernels).  With several ranks the second schedule (the one used) also
+    # hides the all-gather latency.
     pre_under_matmul = True
     fused = tc_engine and args.fuse   # experimental: rescale witnesses from the mat-mul epilogue (measured not to pay)
     if fused:
