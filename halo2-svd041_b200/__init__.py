@@ -7,6 +7,6 @@ Importing the package does NOT load the CUDA library (so CPU-only tooling can in
 """
 from . import _ffi  # noqa: F401
 from ._ffi import H2svdError  # noqa: F401
-from .gpu import Handle, PinnedBuffer, last_matmul_engine, set_matmul_karatsuba, set_matmul_streamk, set_matmul_tc, set_fuse_rescale, set_matmul_variant, set_matvec_warp_kernel, set_rescale_generic  # noqa: F401
+from .gpu import Graph, Handle, MultiHandle, PinnedBuffer  # noqa: F401
 
-__all__ = ["Handle", "PinnedBuffer", "H2svdError", "last_matmul_engine", "set_matmul_karatsuba", "set_matmul_streamk", "set_matmul_tc", "set_fuse_rescale", "set_matmul_variant", "set_matvec_warp_kernel", "set_rescale_generic"]
+__all__ = ["Handle", "MultiHandle", "Graph", "PinnedBuffer", "H2svdError"]

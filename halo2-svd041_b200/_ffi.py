@@ -59,6 +59,17 @@ SIGNATURES = {
     "h2svd_mat_times_diag": (_I, [_P, _P, _P, _Z, _Z, _Z, _P]),
     "h2svd_mat_times_diag_dev": (_I, [_P, _P, _P, _Z, _Z, _Z, _P]),
     "h2svd_zkmatrix_mul_witness": (_I, [_P, _P, _P, _P, _Z, _Z, _Z, _I, _I, _I, _I, _Z, _Z] + [_P] * 10),
+    "h2svd_zkmatrix_mul_witness_dev": (_I, [_P, _P, _P, _P, _Z, _Z, _Z, _I, _I, _I, _I, _Z, _Z] + [_P] * 10),
+    "h2svd_mat_vec_totals_dev": (_I, [_P, _P, _P, _Z, _Z, _P]),
+    "h2svd_graph_begin": (_I, [_P]),
+    "h2svd_graph_end": (_I, [_P, ct.POINTER(_P)]),
+    "h2svd_graph_launch": (_I, [_P, _P]),
+    "h2svd_graph_destroy": (None, [_P]),
+    "h2svd_multi_create": (_I, [ct.POINTER(_P), ct.POINTER(_I), _I]),
+    "h2svd_multi_destroy": (None, [_P]),
+    "h2svd_multi_count": (_I, [_P]),
+    "h2svd_multi_ctx": (_P, [_P, _I]),
+    "h2svd_multi_zkmatrix_mul_witness": (_I, [_P, _P, _P, _P, _Z, _Z, _Z, _I, _I, _I, _I] + [_P] * 10),
     "h2svd_host_alloc": (_I, [_Z, ct.POINTER(_P)]),
     "h2svd_host_free": (None, [_P]),
     "h2svd_rescale_witness_count": (_I, [_I, _I, _I, _I]),
@@ -79,14 +90,8 @@ SIGNATURES = {
 # not part of the public header: triage helpers
 DEBUG_SIGNATURES = {
     "h2svd_debug_fr_matmul_naive_dev": (_I, [_P, _P, _P, _P, _Z, _Z, _Z]),
-    "h2svd_debug_set_matmul_variant": (_I, [_I]),
-    "h2svd_debug_set_rescale_generic": (_I, [_I]),
-    "h2svd_debug_set_matmul_streamk": (_I, [_I]),
-    "h2svd_debug_set_matmul_karatsuba": (_I, [_I]),
-    "h2svd_debug_set_matvec_warp_kernel": (_I, [_I]),
-    "h2svd_debug_set_matmul_tc": (_I, [_I]),
-    "h2svd_debug_set_fuse_rescale": (_I, [_I]),
-    "h2svd_debug_last_matmul_engine": (_I, []),
+    "h2svd_debug_tune": (_I, [_P, ct.c_char_p, _I]),          # per-handle tuning switches
+    "h2svd_debug_last_matmul_engine": (_I, [_P]),
 }
 
 _LIB = None

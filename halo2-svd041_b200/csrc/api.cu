@@ -5,6 +5,9 @@
 #include <string.h>
 
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -26,15 +29,37 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 int ws_reserve(h2svd_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return H2SVD_OK;
+    if (ctx->capturing) {
+        set_error("graph capture: the workspace would have to grow -- run the same calls once before h2svd_graph_begin");
+        return H2SVD_EINVAL;
+    }
     // the old block may still be in use by queued work: drain first
     H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
     H2SVD_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    H2SVD_CUDA(cudaStreamSynchronize(ctx->side_stream));
     if (ctx->ws) H2SVD_CUDA(cudaFree(ctx->ws));
     ctx->ws = nullptr;
     ctx->ws_bytes = 0;
     size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
     H2SVD_CUDA(cudaMalloc(&ctx->ws, want));
     ctx->ws_bytes = want;
+    return H2SVD_OK;
+}
+
+// grow-only side buffers (operand planes, stream-K partials): same rules as ws_reserve
+int ws_grow(h2svd_ctx* ctx, void** buf, size_t* cur, size_t need) {
+    if (*cur >= need) return H2SVD_OK;
+    if (ctx->capturing) {
+        set_error("graph capture: a workspace would have to grow -- run the same calls once before h2svd_graph_begin");
+        return H2SVD_EINVAL;
+    }
+    H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
+    H2SVD_CUDA(cudaStreamSynchronize(ctx->side_stream));
+    if (*buf) H2SVD_CUDA(cudaFree(*buf));
+    *buf = nullptr;
+    *cur = 0;
+    H2SVD_CUDA(cudaMalloc(buf, need));
+    *cur = need;
     return H2SVD_OK;
 }
 
@@ -60,10 +85,6 @@ static int check_flag(h2svd_ctx* ctx, const char* what) {
     H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
     if (flag) {
         H2SVD_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
-        if (flag == 3) {  // a bounded pipeline wait of the tensor-core mat-mul expired (it traps: normally unreachable)
-            set_error("%s: internal error: tensor-core mat-mul pipeline timed out", what);
-            return H2SVD_ECUDA;
-        }
         set_error("%s: operand out of range / non-canonical field element", what);
         return H2SVD_ERANGE;
     }
@@ -147,12 +168,14 @@ int h2svd_create(h2svd_ctx** out, int device, void* stream) {
         ctx->owns_stream = true;
     }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void**)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
-        cudaMemset(ctx->d_flag, 0, sizeof(int)) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_flag, 4 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->d_flag, 0, 4 * sizeof(int)) != cudaSuccess) {
         h2svd_destroy(ctx);
         return cuda_fail(cudaGetLastError(), "handle setup", __FILE__, __LINE__);
     }
-    for (int i = 0; i < 4; i++) {
+    ctx->d_mode = ctx->d_flag + 1;
+    for (int i = 0; i < 8; i++) {
         if (cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming) != cudaSuccess) {
             h2svd_destroy(ctx);
             return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
@@ -170,7 +193,11 @@ void h2svd_destroy(h2svd_ctx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (int i = 0; i < 4; i++)
+    if (ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
+    for (int i = 0; i < 8; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->sk_ws) cudaFree(ctx->sk_ws);
@@ -524,28 +551,86 @@ int h2svd_mat_times_diag(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* v, s
     return check_flag(ctx, "mat_times_diag");
 }
 
-/* ---- fused, slab-pipelined sequence ---- */
-int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t rows,
-                               size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
-                               size_t bv_row0, size_t bv_row1, h2svd_fr* c_s, h2svd_fr* q, h2svd_fr* wit,
-                               h2svd_fr* powers, h2svd_fr* prefix_cv, h2svd_fr* prefix_bv, h2svd_fr* prefix_abv,
-                               h2svd_fr* diff, h2svd_fr* is_zero, h2svd_fr* inv) {
-    REQUIRE(ctx && a && b && gamma && c_s && q && wit && powers && prefix_cv && prefix_abv && diff && is_zero && inv,
-            "zkmatrix_mul_witness: null argument");
-    REQUIRE(rows >= 1 && k >= 1 && m >= 1, "zkmatrix_mul_witness: empty matrix");
-    REQUIRE(bv_row0 <= bv_row1 && bv_row1 <= k, "zkmatrix_mul_witness: bad prefix_bv row range");
-    REQUIRE(bv_row0 == bv_row1 || prefix_bv, "zkmatrix_mul_witness: null prefix_bv");
-    const int W = rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr);
-    REQUIRE(W > 0, "zkmatrix_mul_witness: rescale parameters out of range");
-    H2SVD_CUDA(cudaSetDevice(ctx->device));
+/* ---- the README.md:34-47 sequence: device-pointer form (two streams, graph-capturable) ---- */
+namespace h2svd {
+
+// runs `fn` with the handle's launchers pointed at `st`
+struct StreamScope {
+    h2svd_ctx* ctx;
+    cudaStream_t saved;
+    StreamScope(h2svd_ctx* c, cudaStream_t st) : ctx(c), saved(c->stream) { c->stream = st; }
+    ~StreamScope() { ctx->stream = saved; }
+};
+
+// gamma powers (:316-326), the running sums of rows [bv0, bv1) of b . v (:336) and ALL k row totals (b v) on the current stream
+static int bv_part(h2svd_ctx* ctx, const Fr* db, const Fr* dg, size_t k, size_t m, size_t bv0, size_t bv1, Fr* dpow,
+                   Fr* dpbv_rows, Fr* dbv) {
+    H2SVD_TRY(launch_gamma_powers(ctx, dg, m, dpow));
+    if (bv0 == 0 && bv1 == k) return launch_mat_vec_prefix(ctx, db, dpow, k, m, 0, dpbv_rows, dbv);
+    // a row-sharded caller: every handle needs all k totals (the second operand of a . (b v)) but emits the running-sum
+    // witnesses of its own rows only -- the totals are recomputed lazily instead of exchanged (no collective)
+    H2SVD_TRY(launch_mat_vec_totals(ctx, db, dpow, k, m, dbv));
+    if (bv1 > bv0) H2SVD_TRY(launch_mat_vec_prefix(ctx, db + bv0 * m, dpow, bv1 - bv0, m, 0, dpbv_rows, nullptr));
+    return H2SVD_OK;
+}
+
+static int mul_witness_dev(h2svd_ctx* ctx, const Fr* da, const Fr* db, const Fr* dg, size_t rows, size_t k, size_t m, int P,
+                           int lb, int S, int A, size_t bv0, size_t bv1, Fr* dc, Fr* dq, Fr* dw, Fr* dpow, Fr* dpcv,
+                           Fr* dpbv, Fr* dpabv, Fr* ddiff, Fr* dz, Fr* dinv) {
+    H2SVD_TRY(ws_reserve(ctx, Carver::need(k * sizeof(Fr)) + 2 * Carver::need(rows * sizeof(Fr))));
+    Carver cv(ctx->ws);
+    Fr* dbv = cv.take<Fr>(k);
+    Fr* dcsv = cv.take<Fr>(rows);
+    Fr* dabv = cv.take<Fr>(rows);
+    cudaStream_t main = ctx->stream, side = ctx->side_stream;
+    cudaEvent_t ev_fork = ctx->ev[4], ev_mid = ctx->ev[5], ev_join = ctx->ev[6];
+    // fork: the C-independent half of verify_mul (integer-pipe mat-vecs) runs under the mat-mul (tensor pipe)
+    H2SVD_CUDA(cudaEventRecord(ev_fork, main));
+    H2SVD_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    {
+        StreamScope sc(ctx, side);
+        H2SVD_TRY(bv_part(ctx, db, dg, k, m, bv0, bv1, dpow, dpbv, dbv));
+        H2SVD_TRY(launch_mat_vec_prefix(ctx, da, dbv, rows, k, 0, dpabv, dabv));                  // :337
+    }
+    H2SVD_TRY(launch_fr_matmul(ctx, da, db, dc, rows, k, m));                                     // :546
+    H2SVD_CUDA(cudaEventRecord(ev_mid, main));
+    H2SVD_CUDA(cudaStreamWaitEvent(side, ev_mid, 0));
+    {
+        StreamScope sc(ctx, side);   // C.v (integer pipe) next to the rescale kernel (HBM writes)
+        H2SVD_TRY(launch_mat_vec_prefix(ctx, dc, dpow, rows, m, 0, dpcv, dcsv));                  // :335
+        H2SVD_TRY(launch_is_equal(ctx, dcsv, dabv, rows, ddiff, dz, dinv));                       // :339-341
+        H2SVD_CUDA(cudaEventRecord(ev_join, side));
+    }
+    H2SVD_TRY(launch_rescale(ctx, dc, rows * m, P, lb, S, A, dq, dw));                            // :354
+    H2SVD_CUDA(cudaStreamWaitEvent(main, ev_join, 0));
+    return H2SVD_OK;
+}
+
+// after a failure inside a pipelined host call: nothing may still be writing the caller's buffers, no stale flag
+static void drain_after_error(h2svd_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaMemset(ctx->d_flag, 0, sizeof(int));
+    cudaGetLastError();
+}
+
+static int mul_witness_host(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t rows,
+                            size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
+                            size_t bv_row0, size_t bv_row1, h2svd_fr* c_s, h2svd_fr* q, h2svd_fr* wit, h2svd_fr* powers,
+                            h2svd_fr* prefix_cv, h2svd_fr* prefix_bv, h2svd_fr* prefix_abv, h2svd_fr* diff,
+                            h2svd_fr* is_zero, h2svd_fr* inv, int W) {
     const size_t F = sizeof(Fr);
-    // slab height: ~96 MB of rescale witnesses per slab (two slab buffers are in flight)
-    size_t slab = ((size_t)96 << 20) / (m * (size_t)W * F);
+    // slab height: 128 rows (one row of mat-mul tiles) unless that is more than ~256 MB of rescale witnesses per slab
+    size_t slab = ((size_t)256 << 20) / (m * (size_t)W * F);
+    if (slab > 128) slab = 128;
     if (slab < 1) slab = 1;
     if (slab > rows) slab = rows;
+    const size_t bvn = bv_row1 - bv_row0;
     const size_t need = Carver::need(rows * k * F) + Carver::need(k * m * F) + 3 * Carver::need(rows * m * F) +
-                        Carver::need(F) + Carver::need(m * F) + Carver::need(k * m * F) + Carver::need(rows * k * F) +
-                        Carver::need(k * F) + 5 * Carver::need(rows * F) + 2 * Carver::need(slab * m * (size_t)W * F);
+                        Carver::need(F) + Carver::need(m * F) + Carver::need((bvn ? bvn : 1) * m * F) +
+                        Carver::need(rows * k * F) + Carver::need(k * F) + 5 * Carver::need(rows * F) +
+                        2 * Carver::need(slab * m * (size_t)W * F);
     H2SVD_TRY(ws_reserve(ctx, need));
     Carver cv(ctx->ws);
     Fr* da = cv.take<Fr>(rows * k);
@@ -555,7 +640,7 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
     Fr* dpcv = cv.take<Fr>(rows * m);
     Fr* dg = cv.take<Fr>(1);
     Fr* dpow = cv.take<Fr>(m);
-    Fr* dpbv = cv.take<Fr>(k * m);
+    Fr* dpbv = cv.take<Fr>((bvn ? bvn : 1) * m);
     Fr* dpabv = cv.take<Fr>(rows * k);
     Fr* dbv = cv.take<Fr>(k);
     Fr* dcsv = cv.take<Fr>(rows);
@@ -569,35 +654,41 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
         if (bytes) H2SVD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, xs));
         return H2SVD_OK;
     };
-    // inputs: B and gamma first (the C-independent half of verify_mul starts at once); A follows slab by slab
+    // inputs: B and gamma first (the C-independent half of verify_mul starts at once), then the first slab of A
     H2SVD_TRY(h2d(ctx, db, b, k * m * F));
     H2SVD_TRY(h2d(ctx, dg, gamma, F));
     H2SVD_TRY(launch_check_canonical(ctx, db, k * m, ctx->d_flag));
     H2SVD_TRY(launch_check_canonical(ctx, dg, 1, ctx->d_flag));
-    H2SVD_TRY(launch_gamma_powers(ctx, dg, m, dpow));                               // :316-326
-    H2SVD_TRY(launch_mat_vec_prefix(ctx, db, dpow, k, m, 0, dpbv, dbv));            // :336
+    H2SVD_TRY(bv_part(ctx, db, dg, k, m, bv_row0, bv_row1, dpow, dpbv, dbv));                     // :316-326, :336
     H2SVD_CUDA(cudaEventRecord(ctx->ev[0], cs));
     H2SVD_CUDA(cudaStreamWaitEvent(xs, ctx->ev[0], 0));
     H2SVD_TRY(to_host(powers, dpow, m * F));
-    H2SVD_TRY(to_host(prefix_bv, dpbv + bv_row0 * m, (bv_row1 - bv_row0) * m * F));
-    // the copy stream must not start overwriting dw[] users... nothing pending yet; make the reuse events signalled
+    H2SVD_TRY(to_host(prefix_bv, dpbv, bvn * m * F));
+    // make the slab-buffer reuse events signalled
     H2SVD_CUDA(cudaEventRecord(ctx->ev[2], xs));
     H2SVD_CUDA(cudaEventRecord(ctx->ev[3], xs));
+    // The product is taken in TWO mat-muls -- the first slab alone (its witnesses leave for the host after B + one slab
+    // of A), then all remaining rows at once -- so that B is split into byte planes twice, not once per slab, and every
+    // MMA tile but the last is a full 128 rows.
+    H2SVD_TRY(h2d(ctx, da, a, slab * k * F));
+    H2SVD_TRY(launch_check_canonical(ctx, da, slab * k, ctx->d_flag));
+    H2SVD_TRY(launch_fr_matmul(ctx, da, db, dc, slab, k, m));                                     // :546
     int buf = 0;
     for (size_t r0 = 0, nr = 0; r0 < rows; r0 += nr, buf ^= 1) {
-        // a short first slab gets the copy engine going early; after that the copies are the bottleneck anyway
-        const size_t want = r0 == 0 && slab >= 8 ? slab / 8 : slab;
-        nr = rows - r0 < want ? rows - r0 : want;
-        // A is uploaded slab by slab too: the first witnesses leave for the host after B + one slab of A, not after all of A
-        H2SVD_TRY(h2d(ctx, da + r0 * k, as_fr(a) + r0 * k, nr * k * F));
-        H2SVD_TRY(launch_check_canonical(ctx, da + r0 * k, nr * k, ctx->d_flag));
+        nr = rows - r0 < slab ? rows - r0 : slab;
         H2SVD_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2 + buf], 0));  // slab buffer `buf` drained two slabs ago
-        H2SVD_TRY(launch_fr_matmul_rescale(ctx, da + r0 * k, db, dc + r0 * m, nr, k, m, precision_bits, lookup_bits,
-                                           shift_bits, a_num_bits, dq + r0 * m, dw[buf]));               // :546, :354
+        H2SVD_TRY(launch_rescale(ctx, dc + r0 * m, nr * m, precision_bits, lookup_bits, shift_bits, a_num_bits,
+                                 dq + r0 * m, dw[buf]));                                          // :354
         H2SVD_TRY(launch_mat_vec_prefix(ctx, dc + r0 * m, dpow, nr, m, 0, dpcv + r0 * m, dcsv + r0));    // :335
         H2SVD_TRY(launch_mat_vec_prefix(ctx, da + r0 * k, dbv, nr, k, 0, dpabv + r0 * k, dabv + r0));    // :337
         H2SVD_TRY(launch_is_equal(ctx, dcsv + r0, dabv + r0, nr, ddiff + r0, dz + r0, dinv + r0));       // :339-341
         H2SVD_CUDA(cudaEventRecord(ctx->ev[buf], cs));
+        if (r0 == 0 && rows > slab) {
+            // the rest of A and its product, queued behind the first slab's kernels and under its D2H
+            H2SVD_TRY(h2d(ctx, da + slab * k, as_fr(a) + slab * k, (rows - slab) * k * F));
+            H2SVD_TRY(launch_check_canonical(ctx, da + slab * k, (rows - slab) * k, ctx->d_flag));
+            H2SVD_TRY(launch_fr_matmul(ctx, da + slab * k, db, dc + slab * m, rows - slab, k, m));
+        }
         H2SVD_CUDA(cudaStreamWaitEvent(xs, ctx->ev[buf], 0));
         H2SVD_TRY(to_host(as_fr(wit) + r0 * m * (size_t)W, dw[buf], nr * m * (size_t)W * F));
         H2SVD_CUDA(cudaEventRecord(ctx->ev[2 + buf], xs));
@@ -613,6 +704,195 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
     H2SVD_TRY(to_host(inv, dinv, rows * F));
     H2SVD_CUDA(cudaStreamSynchronize(xs));
     return check_flag(ctx, "zkmatrix_mul_witness");
+}
+
+}  // namespace h2svd
+
+int h2svd_zkmatrix_mul_witness_dev(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t rows,
+                                   size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
+                                   size_t bv_row0, size_t bv_row1, h2svd_fr* c_s, h2svd_fr* q, h2svd_fr* wit,
+                                   h2svd_fr* powers, h2svd_fr* prefix_cv, h2svd_fr* prefix_bv, h2svd_fr* prefix_abv,
+                                   h2svd_fr* diff, h2svd_fr* is_zero, h2svd_fr* inv) {
+    REQUIRE(ctx && a && b && gamma && c_s && q && wit && powers && prefix_cv && prefix_abv && diff && is_zero && inv,
+            "zkmatrix_mul_witness_dev: null argument");
+    REQUIRE(rows >= 1 && k >= 1 && m >= 1, "zkmatrix_mul_witness_dev: empty matrix");
+    REQUIRE(bv_row0 <= bv_row1 && bv_row1 <= k, "zkmatrix_mul_witness_dev: bad prefix_bv row range");
+    REQUIRE(bv_row0 == bv_row1 || prefix_bv, "zkmatrix_mul_witness_dev: null prefix_bv");
+    REQUIRE(rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr) > 0,
+            "zkmatrix_mul_witness_dev: rescale parameters out of range");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return mul_witness_dev(ctx, as_fr(a), as_fr(b), as_fr(gamma), rows, k, m, precision_bits, lookup_bits, shift_bits,
+                           a_num_bits, bv_row0, bv_row1, as_fr(c_s), as_fr(q), as_fr(wit), as_fr(powers), as_fr(prefix_cv),
+                           prefix_bv ? as_fr(prefix_bv) : nullptr, as_fr(prefix_abv), as_fr(diff), as_fr(is_zero),
+                           as_fr(inv));
+}
+
+int h2svd_mat_vec_totals_dev(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* v, size_t rows, size_t len,
+                             h2svd_fr* out_totals) {
+    REQUIRE(ctx && a && v && out_totals, "mat_vec_totals: null argument");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_mat_vec_totals(ctx, as_fr(a), as_fr(v), rows, len, as_fr(out_totals));
+}
+
+/* ---- fused, slab-pipelined sequence (host pointers) ---- */
+int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t rows,
+                               size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
+                               size_t bv_row0, size_t bv_row1, h2svd_fr* c_s, h2svd_fr* q, h2svd_fr* wit,
+                               h2svd_fr* powers, h2svd_fr* prefix_cv, h2svd_fr* prefix_bv, h2svd_fr* prefix_abv,
+                               h2svd_fr* diff, h2svd_fr* is_zero, h2svd_fr* inv) {
+    REQUIRE(ctx && a && b && gamma && c_s && q && wit && powers && prefix_cv && prefix_abv && diff && is_zero && inv,
+            "zkmatrix_mul_witness: null argument");
+    REQUIRE(rows >= 1 && k >= 1 && m >= 1, "zkmatrix_mul_witness: empty matrix");
+    REQUIRE(bv_row0 <= bv_row1 && bv_row1 <= k, "zkmatrix_mul_witness: bad prefix_bv row range");
+    REQUIRE(bv_row0 == bv_row1 || prefix_bv, "zkmatrix_mul_witness: null prefix_bv");
+    const int W = rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr);
+    REQUIRE(W > 0, "zkmatrix_mul_witness: rescale parameters out of range");
+    REQUIRE(!ctx->capturing, "zkmatrix_mul_witness: host-pointer entry points cannot be captured into a graph");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    const int rc = mul_witness_host(ctx, a, b, gamma, rows, k, m, precision_bits, lookup_bits, shift_bits, a_num_bits,
+                                    bv_row0, bv_row1, c_s, q, wit, powers, prefix_cv, prefix_bv, prefix_abv, diff, is_zero,
+                                    inv, W);
+    if (rc != H2SVD_OK) drain_after_error(ctx);
+    return rc;
+}
+
+/* ---- CUDA-graph capture of any sequence of *_dev calls on one handle ---- */
+struct h2svd_graph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;   // kernel launches recorded between begin and end
+};
+
+int h2svd_graph_begin(h2svd_ctx* ctx) {
+    REQUIRE(ctx, "graph_begin: null handle");
+    REQUIRE(!ctx->capturing, "graph_begin: a capture is already in progress on this handle");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    H2SVD_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    ctx->capture_launches0 = ctx->launches;
+    return H2SVD_OK;
+}
+
+int h2svd_graph_end(h2svd_ctx* ctx, h2svd_graph** out) {
+    REQUIRE(ctx && out, "graph_end: null argument");
+    REQUIRE(ctx->capturing, "graph_end: no capture in progress");
+    *out = nullptr;
+    ctx->capturing = false;
+    cudaGraph_t g = nullptr;
+    H2SVD_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+    h2svd_graph* gr = new (std::nothrow) h2svd_graph();
+    if (!gr) {
+        cudaGraphDestroy(g);
+        return H2SVD_ENOMEM;
+    }
+    const cudaError_t e = cudaGraphInstantiate(&gr->exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        delete gr;
+        return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    }
+    gr->launches = ctx->launches - ctx->capture_launches0;
+    ctx->launches = ctx->capture_launches0;   // nothing has run yet: h2svd_graph_launch accounts for every replay
+    *out = gr;
+    return H2SVD_OK;
+}
+
+int h2svd_graph_launch(h2svd_ctx* ctx, h2svd_graph* graph) {
+    REQUIRE(ctx && graph && graph->exec, "graph_launch: null argument");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    H2SVD_CUDA(cudaGraphLaunch(graph->exec, ctx->stream));
+    ctx->launches += graph->launches;
+    return H2SVD_OK;
+}
+
+void h2svd_graph_destroy(h2svd_graph* graph) {
+    if (!graph) return;
+    if (graph->exec) cudaGraphExecDestroy(graph->exec);
+    delete graph;
+}
+
+/* ---- one process, several GPUs: rows of A / C partitioned over the handles, B replicated ---- */
+struct h2svd_multi {
+    std::vector<h2svd_ctx*> ctx;
+};
+
+int h2svd_multi_create(h2svd_multi** out, const int* devices, int n_dev) {
+    REQUIRE(out && devices, "multi_create: null argument");
+    REQUIRE(n_dev >= 1 && n_dev <= 64, "multi_create: device count out of range");
+    *out = nullptr;
+    h2svd_multi* mh = new (std::nothrow) h2svd_multi();
+    if (!mh) return H2SVD_ENOMEM;
+    for (int i = 0; i < n_dev; i++) {
+        h2svd_ctx* c = nullptr;
+        const int rc = h2svd_create(&c, devices[i], nullptr);   // the same device may appear more than once
+        if (rc != H2SVD_OK) {
+            h2svd_multi_destroy(mh);
+            return rc;
+        }
+        mh->ctx.push_back(c);
+    }
+    *out = mh;
+    return H2SVD_OK;
+}
+
+void h2svd_multi_destroy(h2svd_multi* mh) {
+    if (!mh) return;
+    for (h2svd_ctx* c : mh->ctx) h2svd_destroy(c);
+    delete mh;
+}
+
+int h2svd_multi_count(h2svd_multi* mh) { return mh ? (int)mh->ctx.size() : 0; }
+h2svd_ctx* h2svd_multi_ctx(h2svd_multi* mh, int i) { return (mh && i >= 0 && i < (int)mh->ctx.size()) ? mh->ctx[i] : nullptr; }
+
+// contiguous near-equal split: the first (total % parts) parts get one extra row
+static void split_rows(size_t total, size_t parts, size_t idx, size_t* lo, size_t* hi) {
+    const size_t base = total / parts, extra = total % parts;
+    *lo = idx * base + (idx < extra ? idx : extra);
+    *hi = *lo + base + (idx < extra ? 1 : 0);
+}
+
+int h2svd_multi_zkmatrix_mul_witness(h2svd_multi* mh, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t n,
+                                     size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
+                                     h2svd_fr* c_s, h2svd_fr* q, h2svd_fr* wit, h2svd_fr* powers, h2svd_fr* prefix_cv,
+                                     h2svd_fr* prefix_bv, h2svd_fr* prefix_abv, h2svd_fr* diff, h2svd_fr* is_zero,
+                                     h2svd_fr* inv) {
+    REQUIRE(mh && !mh->ctx.empty(), "multi_zkmatrix_mul_witness: null handle");
+    REQUIRE(a && b && gamma && c_s && q && wit && powers && prefix_cv && prefix_bv && prefix_abv && diff && is_zero && inv,
+            "multi_zkmatrix_mul_witness: null argument");
+    REQUIRE(n >= 1 && k >= 1 && m >= 1, "multi_zkmatrix_mul_witness: empty matrix");
+    const int W = rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr);
+    REQUIRE(W > 0, "multi_zkmatrix_mul_witness: rescale parameters out of range");
+    // every participating handle gets at least one row of A; the rows of b . v are split over the same handles.  No
+    // exchange step: each handle derives all k totals of (b v) itself (h2svd_zkmatrix_mul_witness), field addition is
+    // exact, so the assembled witness is byte-identical to the single-GPU one.
+    const size_t parts = mh->ctx.size() < n ? mh->ctx.size() : n;
+    std::vector<int> rc(parts, H2SVD_OK);
+    std::vector<std::string> msg(parts);
+    std::vector<std::vector<h2svd_fr>> pow_tmp(parts);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < parts; g++) {
+        th.emplace_back([&, g]() {
+            size_t r0, r1, b0, b1;
+            split_rows(n, parts, g, &r0, &r1);
+            split_rows(k, parts, g, &b0, &b1);
+            h2svd_fr* pw = powers;
+            if (g != 0) {   // every handle returns the same gamma powers: only the first writes the caller's buffer
+                pow_tmp[g].resize(m);
+                pw = pow_tmp[g].data();
+            }
+            rc[g] = h2svd_zkmatrix_mul_witness(mh->ctx[g], a + r0 * k, b, gamma, r1 - r0, k, m, precision_bits, lookup_bits,
+                                               shift_bits, a_num_bits, b0, b1, c_s + r0 * m, q + r0 * m,
+                                               wit + r0 * m * (size_t)W, pw, prefix_cv + r0 * m, prefix_bv + b0 * m,
+                                               prefix_abv + r0 * k, diff + r0, is_zero + r0, inv + r0);
+            if (rc[g] != H2SVD_OK) msg[g] = h2svd_last_error();   // the message is thread-local: carry it over
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < parts; g++)
+        if (rc[g] != H2SVD_OK) {
+            set_error("device %d (part %zu of %zu): %s", mh->ctx[g]->device, g, parts, msg[g].c_str());
+            return rc[g];
+        }
+    return H2SVD_OK;
 }
 
 int h2svd_host_alloc(size_t bytes, void** out) {
@@ -752,6 +1032,34 @@ int h2svd_microbench_imad(h2svd_ctx* ctx, int kind, int iters, double* ops_per_s
     REQUIRE(ctx, "microbench: null handle");
     H2SVD_CUDA(cudaSetDevice(ctx->device));
     return launch_microbench(ctx, kind, iters, ops_per_s);
+}
+
+/* debug / triage only (not in the public header): per-handle tuning switches and the engine of the last mat-mul */
+int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
+    REQUIRE(ctx && key, "debug_tune: null argument");
+    struct { const char* name; int* slot; } const keys[] = {
+        {"matmul_tc", &ctx->tune.matmul_tc},       {"matmul_small", &ctx->tune.matmul_small},
+        {"matmul_karatsuba", &ctx->tune.kara},     {"matmul_streamk", &ctx->tune.streamk},
+        {"matmul_variant", &ctx->tune.variant},    {"fuse_rescale", &ctx->tune.fuse_rescale},
+        {"rescale_generic", &ctx->tune.rescale_generic}, {"matvec_warp_kernel", &ctx->tune.matvec_warp},
+    };
+    for (const auto& e : keys)
+        if (strcmp(e.name, key) == 0) {
+            *e.slot = value;
+            return H2SVD_OK;
+        }
+    set_error("debug_tune: unknown key '%s'", key);
+    return H2SVD_EINVAL;
+}
+int h2svd_debug_last_matmul_engine(h2svd_ctx* ctx) {
+    if (!ctx) return -1;
+    if (ctx->last_engine != 3) return ctx->last_engine;
+    // both tensor-core engines were enqueued: the device flag says which one did the work (synchronises the stream)
+    int mode = 1;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+        cudaMemcpy(&mode, ctx->d_mode, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    return mode == 0 ? 3 : 2;
 }
 
 /* debug / triage only: fully reduced one-thread-per-element mat-mul on device pointers */

@@ -17,13 +17,30 @@ struct h2svd_ctx {
     size_t ws_bytes = 0;
     // second stream + events for copy/compute overlap in the host-pointer entry points
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // third stream: the C-independent half of verify_mul (integer-pipe mat-vecs) under the mat-mul, C.v next to the rescale
+    cudaStream_t side_stream = nullptr;
+    bool capturing = false;       // between h2svd_graph_begin and h2svd_graph_end
+    uint64_t capture_launches0 = 0;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 0-3 copy pipelines, 4-6 fork/mid/join of the two-stream step
     void* kara_ws = nullptr;  // pre-split (Karatsuba) operands of the mat-mul
     size_t kara_ws_bytes = 0;
     void* sk_ws = nullptr;  // stream-K partial-tile workspace of the mat-mul
     size_t sk_ws_bytes = 0;
     int* d_flag = nullptr;  // device flag for validation kernels
+    int* d_mode = nullptr;  // device flag of the tensor-core mat-mul: 0 = small-operand engine, 1 = full-width engine (d_flag + 1)
     uint64_t launches = 0;
+    // Triage / tuning switches (h2svd_debug_tune).  Per handle: two handles on two streams never see each other's settings.
+    struct Tuning {
+        int matmul_tc = -1;       // tensor-core mat-mul engines: -1 auto, 0 never, 1 always
+        int matmul_small = -1;    // small-operand tensor-core engine: -1 auto (range-detected on the device), 0 never
+        int kara = -1;            // IMAD engines: -1 auto, 0 schoolbook kernels only, 1..3 force a Karatsuba variant
+        int streamk = -1;         // IMAD engines: -1 auto, 0 never, 1 always use the stream-K schedule
+        int variant = 0;          // schoolbook tile variant
+        int fuse_rescale = 0;     // 1: rescale witnesses from the tensor-core epilogue (experimental)
+        int rescale_generic = 0;  // 1: force the generic (unstaged) rescale kernel
+        int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel
+    } tune;
+    int last_engine = -1;         // engine of the last mat-mul launch: 0 schoolbook, 1 Karatsuba, 2 tensor core, 3 small-operand
 };
 
 namespace h2svd {
@@ -32,6 +49,8 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // Ensures ctx->ws has at least `bytes`; returns H2SVD_OK / H2SVD_ENOMEM.
 int ws_reserve(h2svd_ctx* ctx, size_t bytes);
+// Same for a dedicated buffer (*buf, *cur bytes): grows it to `need` (drains the streams first; refused during graph capture).
+int ws_grow(h2svd_ctx* ctx, void** buf, size_t* cur, size_t need);
 
 #define H2SVD_CUDA(call)                                                        \
     do {                                                                        \
@@ -104,7 +123,6 @@ int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, 
 int launch_fr_matmul_naive(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k,
                            size_t m);
 // tensor-core engine of the mat-mul (matmul_tc.cu)
-extern int g_matmul_tc;
 bool fr_matmul_tc_supported(size_t n, size_t k, size_t m);
 namespace rs { struct RescaleConsts; }
 // fuse != nullptr: the epilogue also writes the rescale_matrix witnesses of C (out_q, out_wit as in launch_rescale)
@@ -120,6 +138,8 @@ int launch_mat_vec_prefix(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows,
                           size_t v_row_stride, Fr* out, Fr* totals);
 int launch_mat_vec_prefix2(h2svd_ctx* ctx, const Fr* a0, size_t rows0, Fr* out0, Fr* totals0, const Fr* a1,
                            size_t rows1, Fr* out1, Fr* totals1, const Fr* v, size_t len);
+// row totals only, lazily accumulated (no running sums)
+int launch_mat_vec_totals(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t len, Fr* totals);
 int launch_gather(h2svd_ctx* ctx, const Fr* src, size_t count, size_t stride, size_t offset,
                   Fr* out);
 int launch_is_equal(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, Fr* diff, Fr* is_zero,

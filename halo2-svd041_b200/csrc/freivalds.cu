@@ -9,6 +9,7 @@
 //    is a warp-shuffle inclusive scan in the field plus the carry from the previous 32-block.
 //  * is_equal cells (:339-341).
 #include "common.cuh"
+#include "fr_acc.cuh"
 #include "fr_fast.cuh"
 
 namespace h2svd {
@@ -258,6 +259,36 @@ mat_vec_prefix_tile_kernel(const __grid_constant__ MvJobs jobs, const Fr* __rest
     }
 }
 
+// Row totals only (no running sums): totals[row] = sum_t a[row][t] * v[t].  Used by row-sharded callers for (B v): every
+// rank needs all k totals as the second operand of A.(Bv) (reference src/matrix/mod.rs:337) but emits the running-sum
+// witnesses of its own rows of B only -- computing the totals redundantly is cheaper than a collective.  No canonical
+// intermediate is needed, so the products are accumulated lazily (fr_acc.cuh: 64 IMAD.WIDE per element, one reduction
+// per lane) -- the same value as the last running sum of mat_vec_prefix, since the canonical representative is unique.
+constexpr int MVT_WARPS = 8;
+__global__ void __launch_bounds__(MVT_WARPS * 32)
+mat_vec_totals_kernel(const Fr* __restrict__ a, const Fr* __restrict__ v, Fr* __restrict__ totals, size_t rows, size_t len) {
+    const int lane = threadIdx.x & 31;
+    const size_t warps_total = (size_t)gridDim.x * MVT_WARPS;
+    for (size_t row = (size_t)blockIdx.x * MVT_WARPS + (threadIdx.x >> 5); row < rows; row += warps_total) {
+        fr::WideAcc w;
+        fr::acc_clear(w);
+        const Fr* ar = a + row * len;
+        for (size_t j = lane; j < len; j += 32) {
+            const Fr x = ldg_fr(ar + j), y = ldg_fr(v + j);
+            fr::mul_acc(w, x.l, y.l);
+        }
+        Fr p = fr::acc_finalize(w);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            Fr t;
+#pragma unroll
+            for (int i = 0; i < 8; i++) t.l[i] = __shfl_down_sync(0xffffffffu, p.l[i], d);
+            p = fr::add_fast(p, t);
+        }
+        if (lane == 0) st_fr(totals + row, p);
+    }
+}
+
 __global__ void gather_kernel(const Fr* __restrict__ src, Fr* __restrict__ out, size_t count, size_t stride,
                               size_t offset) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,8 +342,6 @@ int launch_gamma_powers(h2svd_ctx* ctx, const Fr* gamma, size_t d, Fr* out) {
     return H2SVD_OK;
 }
 
-static int g_mv_force_warp = 0;  // triage hook: 1 = always use the warp-per-segment kernel
-
 template <int WPR>
 static int launch_mv(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, const Fr* v, size_t len, size_t vs) {
     constexpr int RPC = MV_WARPS / WPR;
@@ -328,7 +357,7 @@ static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_
     size_t total_rows = 0;
     for (int q = 0; q < jobs.njobs; q++) total_rows += jobs.job[q].rows;
     if (total_rows == 0 || len == 0) return H2SVD_OK;
-    if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && g_mv_force_warp == 0) {
+    if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && ctx->tune.matvec_warp == 0) {
         // one warp per row, consecutive elements per lane (mat_vec_prefix_tile_kernel); needs enough rows to
         // give every SM a few warps, otherwise the row-splitting kernel below is the better fit
         H2SVD_SET_SMEM(ctx, mat_vec_prefix_tile_kernel, MT_SMEM);
@@ -368,6 +397,16 @@ int launch_mat_vec_prefix2(h2svd_ctx* ctx, const Fr* a0, size_t rows0, Fr* out0,
     return launch_mv_jobs(ctx, jobs, v, len, 0);
 }
 
+int launch_mat_vec_totals(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t len, Fr* totals) {
+    if (rows == 0) return H2SVD_OK;
+    size_t blocks = (rows + MVT_WARPS - 1) / MVT_WARPS;
+    const size_t cap = (size_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    mat_vec_totals_kernel<<<(unsigned)blocks, MVT_WARPS * 32, 0, ctx->stream>>>(a, v, totals, rows, len);
+    H2SVD_LAUNCH_CHECK(ctx);
+    return H2SVD_OK;
+}
+
 int launch_gather(h2svd_ctx* ctx, const Fr* src, size_t count, size_t stride, size_t offset, Fr* out) {
     if (count == 0) return H2SVD_OK;
     gather_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(src, out, count, stride, offset);
@@ -384,7 +423,3 @@ int launch_is_equal(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count, Fr* 
 
 }  // namespace h2svd
 
-extern "C" int h2svd_debug_set_matvec_warp_kernel(int v) {
-    h2svd::g_mv_force_warp = v;
-    return 0;
-}

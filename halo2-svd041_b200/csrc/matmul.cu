@@ -704,9 +704,6 @@ __global__ void transpose_kernel(const Fr* __restrict__ src, Fr* __restrict__ ds
     }
 }
 
-int g_variant = 0;
-int g_streamk = -1;  // -1 auto, 0 never, 1 always (triage hook)
-
 template <int TM, int TN, int BK, int STAGES, int MINBLOCKS>
 int launch_variant(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k, int m) {
     using cfg = Cfg<TM, TN, BK, STAGES>;
@@ -718,22 +715,15 @@ int launch_variant(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k
     // 129 G mul-add/s once there are >= ~3.5 waves of tiles (a partial last wave is softened because an SM
     // holding one CTA instead of two runs it ~1.6x faster), but drops to 106-110 G/s at 0.9-1.7 waves (the
     // 128- and 256-row slabs of the 8- and 4-GPU split of N=1024); stream-K holds ~118 G/s regardless.
-    const bool streamk = g_streamk < 0 ? (tiles * 2 < 5LL * slots && nchunks >= 4 && tiles * nchunks >= 2LL * slots)
-                                       : g_streamk != 0;
+    const bool streamk = ctx->tune.streamk < 0 ? (tiles * 2 < 5LL * slots && nchunks >= 4 && tiles * nchunks >= 2LL * slots)
+                                       : ctx->tune.streamk != 0;
     if (streamk && nchunks >= 1 && tiles * nchunks < (1LL << 31)) {
         auto kern = fr_matmul_streamk_kernel<TM, TN, BK, STAGES, MINBLOCKS>;
         H2SVD_SET_SMEM(ctx, kern, cfg::SMEM);
         const long long total_units = tiles * nchunks;
         const int G = (int)(total_units < slots ? total_units : slots);
         const size_t part_bytes = (size_t)G * 2 * cfg::BM * cfg::BN * sizeof(Fr);
-        if (ctx->sk_ws_bytes < part_bytes) {
-            H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (ctx->sk_ws) H2SVD_CUDA(cudaFree(ctx->sk_ws));
-            ctx->sk_ws = nullptr;
-            ctx->sk_ws_bytes = 0;
-            H2SVD_CUDA(cudaMalloc(&ctx->sk_ws, part_bytes));
-            ctx->sk_ws_bytes = part_bytes;
-        }
+        H2SVD_TRY(ws_grow(ctx, &ctx->sk_ws, &ctx->sk_ws_bytes, part_bytes));
         kern<<<G, THREADS, cfg::SMEM, ctx->stream>>>(a, b, c, (Fr*)ctx->sk_ws, n, k, m, tiles_x, nchunks, total_units);
         H2SVD_LAUNCH_CHECK(ctx);
         fr_matmul_fixup_kernel<cfg::BM, cfg::BN><<<(unsigned)tiles, 256, 0, ctx->stream>>>(
@@ -751,9 +741,6 @@ int launch_variant(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k
 
 }  // namespace
 
-static int g_last_engine = -1;  // engine of the last mat-mul launch: 0 schoolbook, 1 Karatsuba, 2 tensor core
-static int g_kara = -1;  // -1 auto, 0 schoolbook kernels only, 1..3 force a Karatsuba variant (triage hook)
-
 template <int BK, int STAGES, int MINBLOCKS>
 static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, int k, int m) {
     using cfg = KCfg<BK, STAGES>;
@@ -762,14 +749,7 @@ static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, i
     // pre-split operands (48 bytes per element) in a dedicated workspace
     const size_t na = (size_t)n * k, nb = (size_t)k * m;
     const size_t bytes = (na + nb) * sizeof(KOp);
-    if (ctx->kara_ws_bytes < bytes) {
-        H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->kara_ws) H2SVD_CUDA(cudaFree(ctx->kara_ws));
-        ctx->kara_ws = nullptr;
-        ctx->kara_ws_bytes = 0;
-        H2SVD_CUDA(cudaMalloc(&ctx->kara_ws, bytes));
-        ctx->kara_ws_bytes = bytes;
-    }
+    H2SVD_TRY(ws_grow(ctx, &ctx->kara_ws, &ctx->kara_ws_bytes, bytes));
     KOp* ka = (KOp*)ctx->kara_ws;
     KOp* kb = ka + na;
     const unsigned sb = (unsigned)std::min<size_t>((na + 255) / 256, (size_t)ctx->sm_count * 8);
@@ -782,22 +762,15 @@ static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, i
     const long long tiles = (long long)tiles_x * tiles_y;
     const int nchunks = (k + BK - 1) / BK;
     const int slots = ctx->sm_count * MINBLOCKS;
-    const bool streamk = g_streamk < 0 ? (tiles * 2 < 7LL * slots && nchunks >= 4 && tiles * nchunks >= 2LL * slots)
-                                       : g_streamk != 0;
+    const bool streamk = ctx->tune.streamk < 0 ? (tiles * 2 < 7LL * slots && nchunks >= 4 && tiles * nchunks >= 2LL * slots)
+                                       : ctx->tune.streamk != 0;
     if (streamk && tiles * nchunks < (1LL << 31)) {
         auto skern = fr_matmul_streamk_kara_kernel<BK, STAGES, MINBLOCKS>;
         H2SVD_SET_SMEM(ctx, skern, cfg::SMEM);
         const long long total_units = tiles * nchunks;
         const int G = (int)(total_units < slots ? total_units : slots);
         const size_t part_bytes = (size_t)G * 2 * cfg::BM * cfg::BN * sizeof(Fr);
-        if (ctx->sk_ws_bytes < part_bytes) {
-            H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (ctx->sk_ws) H2SVD_CUDA(cudaFree(ctx->sk_ws));
-            ctx->sk_ws = nullptr;
-            ctx->sk_ws_bytes = 0;
-            H2SVD_CUDA(cudaMalloc(&ctx->sk_ws, part_bytes));
-            ctx->sk_ws_bytes = part_bytes;
-        }
+        H2SVD_TRY(ws_grow(ctx, &ctx->sk_ws, &ctx->sk_ws_bytes, part_bytes));
         skern<<<G, THREADS, cfg::SMEM, ctx->stream>>>(ka, kb, c, (Fr*)ctx->sk_ws, n, k, m, tiles_x, nchunks, total_units);
         H2SVD_LAUNCH_CHECK(ctx);
         fr_matmul_fixup_kernel<cfg::BM, cfg::BN><<<(unsigned)tiles, 256, 0, ctx->stream>>>(
@@ -814,27 +787,26 @@ static int launch_kara(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, int n, i
 // Tensor-core engine (matmul_tc.cu: u8 byte planes on tcgen05, ~12x the IMAD engines at N=1024; measured with
 // tools/tc_check.py: ahead from 64^3 on, behind for very short k where its per-element epilogue dominates).
 // Forcing one of the IMAD engines / schedules through the triage hooks switches the automatic choice off.
-static bool use_tensor_engine(size_t n, size_t k, size_t m) {
-    const bool imad_forced = g_kara >= 0 || g_streamk >= 0 || g_variant != 0;
+static bool use_tensor_engine(const h2svd_ctx* ctx, size_t n, size_t k, size_t m) {
+    const int g_matmul_tc = ctx->tune.matmul_tc;
+    const bool imad_forced = ctx->tune.kara >= 0 || ctx->tune.streamk >= 0 || ctx->tune.variant != 0;
     // a handful of 128 x 8 tiles with a long k (e.g. 64 x 4096 x 64: 0.31 vs 0.15 ms) is the one skinny shape the IMAD
     // engines win: their stream-K schedule splits k over the SMs, the tensor-core kernel walks it tile by tile
     const size_t tiles = ((n + 127) / 128) * ((m + 7) / 8);
-    const bool few_long = tiles * 8 < 148 && k > 2048;
+    const bool few_long = tiles * 8 < (size_t)ctx->sm_count && k > 2048;
     const bool tc = g_matmul_tc == 1 ||
                     (g_matmul_tc < 0 && !imad_forced && !few_long && k >= 32 && n * k * m >= (1ull << 18));
     return tc && fr_matmul_tc_supported(n, k, m);
 }
-
-static int g_fuse_rescale = 0;  // 1: emit the rescale witnesses from the tensor-core epilogue (experimental, see matmul_tc.cu)
 
 int launch_fr_matmul_rescale(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m, int P, int lb,
                              int S, int A, Fr* out_q, Fr* out_wit) {
     if (n == 0 || m == 0) return H2SVD_OK;
     rs::RescaleConsts kc;
     const int W = make_rescale_consts(P, lb, S, A, &kc);
-    if (g_fuse_rescale > 0 && W > 0 && m * (size_t)W < (1ull << 31) && n <= (1u << 30) && m <= (1u << 30) &&
-        k <= (1u << 30) && use_tensor_engine(n, k, m)) {
-        g_last_engine = 2;
+    if (ctx->tune.fuse_rescale > 0 && W > 0 && m * (size_t)W < (1ull << 31) && n <= (1u << 30) && m <= (1u << 30) &&
+        k <= (1u << 30) && use_tensor_engine(ctx, n, k, m)) {
+        ctx->last_engine = 2;
         return launch_fr_matmul_tc(ctx, a, b, c, n, k, m, &kc, out_q, out_wit);
     }
     H2SVD_TRY(launch_fr_matmul(ctx, a, b, c, n, k, m));
@@ -847,11 +819,12 @@ int launch_fr_matmul(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, 
         set_error("fr_matmul: dimension too large");
         return H2SVD_EINVAL;
     }
-    if (use_tensor_engine(n, k, m)) {
-        g_last_engine = 2;
+    if (use_tensor_engine(ctx, n, k, m)) {
+        ctx->last_engine = 2;
         return launch_fr_matmul_tc(ctx, a, b, c, n, k, m);
     }
-    g_last_engine = (g_kara >= 1 || (g_kara < 0 && k >= 64 && n * m >= 4096)) ? 1 : 0;
+    const int g_kara = ctx->tune.kara, g_variant = ctx->tune.variant;
+    ctx->last_engine = (g_kara >= 1 || (g_kara < 0 && k >= 64 && n * m >= 4096)) ? 1 : 0;
     // Karatsuba engine (48 instead of 64 IMAD.WIDE per multiply-add; measured 147 vs 129 G mul-add/s at N=1024) unless
     // the product is too small for the O(N^2) operand split and the two extra launches to pay off
     if (g_kara == 1) return launch_kara<16, 3, 2>(ctx, a, b, c, (int)n, (int)k, (int)m);
@@ -884,20 +857,3 @@ int launch_transpose(h2svd_ctx* ctx, const Fr* src, Fr* dst, size_t rows, size_t
 
 }  // namespace h2svd
 
-extern "C" int h2svd_debug_set_fuse_rescale(int v) {
-    h2svd::g_fuse_rescale = v;
-    return 0;
-}
-extern "C" int h2svd_debug_last_matmul_engine(void) { return h2svd::g_last_engine; }
-extern "C" int h2svd_debug_set_matmul_variant(int v) {
-    h2svd::g_variant = v;
-    return 0;
-}
-extern "C" int h2svd_debug_set_matmul_karatsuba(int v) {
-    h2svd::g_kara = v;
-    return 0;
-}
-extern "C" int h2svd_debug_set_matmul_streamk(int v) {
-    h2svd::g_streamk = v;
-    return 0;
-}

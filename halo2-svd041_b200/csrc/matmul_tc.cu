@@ -1,68 +1,91 @@
-// K1t: tensor-core engine of the Fr mat-mul  C = A * B  (reference src/matrix/mod.rs:507-535
+// K1t: tensor-core engines of the Fr mat-mul  C = A * B  (reference src/matrix/mod.rs:507-535
 // `honest_prover_mat_mul`; same contract as the IMAD kernels of matmul.cu, bit-exact with them).
 //
-// A field element in Montgomery form is 32 bytes.  Writing a = sum_p a_p 2^(8p), b = sum_q b_q 2^(8q),
+// FULL-WIDTH engine (TcFull).  A field element in Montgomery form is 32 bytes.  Writing a = sum_p a_p 2^(8p),
+// b = sum_q b_q 2^(8q),
 //     sum_k a_ik * b_kj  =  sum_d 2^(8d) * D_d(i,j),      D_d(i,j) = sum_{p+q=d} sum_k a_p(i,k) * b_q(k,j),
 // i.e. 63 "diagonal" sums of u8 x u8 products: exactly what the 5th-generation tensor cores compute
 // (tcgen05.mma kind::i8, unsigned 8-bit operands, 32-bit accumulators in TMEM).  For k <= 1024 every D_d is below
 // 32 * 1024 * 255^2 < 2^31, so the 32-bit accumulators are exact and the result is the same integer the IMAD
 // kernels accumulate; one Montgomery reduction per C element (fr::reduce_wide_acc) finishes it.
 //
-// Mapping (one CTA per SM, persistent over tiles of 128 rows x 8 columns of C):
-//   * MMA M = 128 rows i of A; for ONE byte plane p at a time the A operand is the 128 x K byte matrix a_p(i,k).
-//   * MMA N = 256 = 32 byte planes q x 8 columns j of B, ordered q-major: row q*8+j of the B operand is b_q(k,j).
-//   * the product for plane p is accumulated at TMEM column offset 8p: column (q*8+j) + 8p = (p+q)*8 + j = d*8 + j,
-//     so the 32 planes p overlap-add straight into the 63 diagonals (x 8 columns j = 504 of the 512 TMEM columns).
-//     Nothing but zero-initialised accumulators and `accumulate` MMAs is needed for the convolution structure.
-//   * per 128 bytes of K: one TMA load of the B operand (32 KB, shared by all p) and 32 TMA loads of A planes
-//     (16 KB each, 6-stage ring), 4 MMAs (K = 32 bytes each) per A plane: 128 x 256 x 32 MACs per instruction,
-//     the full-rate shape (128 cycles per instruction per SM).
-//   * epilogue (16 warps: thread = row i, 4 warps per TMEM lane quarter with 2 columns j each): reads the 63
-//     diagonals of one (i, j) from TMEM, carries them into an 18-limb integer, reduces, stores C; then re-zeroes
-//     its own accumulator columns for the next tile.
-// Operands are pre-split into byte planes by two O(N^2) kernels (A8[p][i][k], B8[q][j][k], both K-major so that
-// TMA with the 128-byte swizzle delivers the canonical K-major UMMA layout).
+// SMALL-OPERAND engine (TcSmall, tc_small.cuh).  Quantized fixed-point operands (ZkMatrix::new, :230-252) are small SIGNED
+// integers in standard form (|q| < 2^70 covers P = 63 and |x| < 128).  The split kernels detect this on the device; the
+// product is then taken over 9 x 10 balanced signed byte digits (s8 x s8, 10th B plane zero so that MMA N is a multiple
+// of 16) -- 90 instead of 1024 byte products per multiply-add -- and Montgomery-encoded once per C element.  Same bytes
+// out.  If any operand is out of range the full-width engine runs instead: both engines are enqueued, a device flag
+// written by the split kernels decides which one does the work (no host round trip, so the sequence is graph-capturable).
 //
-// Arithmetic per C element and k: 1024 u8 MACs on the tensor pipe (vs 48 IMAD.WIDE on the integer pipe).
+// Mapping (one CTA per SM, persistent over tiles of 128 rows x BJ columns of C; BJ = 8 full-width, 24 small):
+//   * MMA M = 128 rows i of A; for ONE byte plane p at a time the A operand is the 128 x K byte matrix a_p(i,k).
+//   * MMA N = LB byte planes q x BJ columns j of B, ordered q-major: row q*BJ+j of the B operand is b_q(k,j).
+//   * the product for plane p is accumulated at TMEM column offset BJ*p: column (q*BJ+j) + BJ*p = (p+q)*BJ + j = d*BJ + j,
+//     so the planes p overlap-add straight into the diagonals (63 x 8 = 504 / 18 x 24 = 432 of the 512 TMEM columns).
+//     Nothing but zero-initialised accumulators and `accumulate` MMAs is needed for the convolution structure.
+//   * per 128 bytes of K: one TMA load of the B operand (shared by all p) and one TMA load per A plane
+//     (16 KB each, multi-stage ring), 4 MMAs (K = 32 bytes each) per A plane.
+//   * epilogue (16 warps: thread = row i, 4 warps per TMEM lane quarter with BJ/4 columns j each): reads the
+//     diagonals of one (i, j) from TMEM, carries them into a multi-limb integer, reduces / encodes, stores C; the
+//     accumulator columns are re-zeroed and handed back before the field arithmetic, which overlaps the next tile.
+// Operands are pre-split into byte planes by O(N^2) kernels (A8[p][i][k], B8[q][j][k], both K-major so that
+// TMA with the 128-byte swizzle delivers the canonical K-major UMMA layout).
 #include <cuda.h>  // CUtensorMap and enums only; the encoder comes from cudaGetDriverEntryPoint (no -lcuda)
 
 #include "common.cuh"
 #include "rescale_dev.cuh"
+#include "tc_small.cuh"
 
 namespace h2svd {
 
 namespace {
 
 constexpr int TC_BM = 128;       // rows of C per tile = MMA M = TMEM lanes
-constexpr int TC_BJ = 8;         // columns of C per tile
 constexpr int TC_BKB = 128;      // bytes (= k values) of K per pipeline unit: one 128-byte swizzle span
-constexpr int TC_SA_PLAIN = 6;   // A-plane stages (6 x 16 KB + 2 x 32 KB leaves room for a co-resident mat-vec CTA)
 #ifndef TC_SA_FUSED_CFG
 #define TC_SA_FUSED_CFG 5
 #endif
 #ifndef TC_CH_CFG
 #define TC_CH_CFG 4
 #endif
-constexpr int TC_SA_FUSED = TC_SA_FUSED_CFG;   // one stage less when the epilogue stages rescale witnesses in shared memory
-constexpr int TC_SB = 2;         // B buffers
-constexpr int TC_KB_PASS = 8;    // K blocks per accumulation pass: 1024 k values keep every diagonal below 2^31
-constexpr uint32_t TC_A_BYTES = TC_BM * TC_BKB;        // 16 KB
-constexpr uint32_t TC_B_BYTES = 32 * TC_BJ * TC_BKB;   // 32 KB
-// Epilogue warps: 4 per TMEM lane quarter with 2 of the 8 columns j each.  (Measured for the fused-rescale variant: 3 per
-// quarter with 3/3/2 columns and 128 spill-free registers is slower, 1.03 vs 0.91 ms at N=1024 -- the code below still
-// handles MAXC = 3.)
-__host__ __device__ constexpr int tc_epi_warps(bool) { return 16; }
-__host__ __device__ constexpr int tc_threads(bool fused) { return 64 + 32 * tc_epi_warps(fused); }  // + TMA producer warp + MMA issuer warp
-// fused rescale: every epilogue warp stages 4 witnesses (128 B + 16 B skew) per lane, single-buffered
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BKB;        // 16 KB per A-plane stage
+constexpr int TC_EPI_WARPS = 16;                        // 4 per TMEM lane quarter
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;      // + TMA producer warp + MMA issuer warp
+
+// Full-width operands: 32 unsigned byte planes each; 1024 k values per accumulation pass keep every diagonal below 2^31.
+struct TcFull {
+    static constexpr int LA = 32, LB = 32, BJ = 8, SA = 6, SB = 2, KB_PASS = 8;   // 6 x 16 KB + 2 x 32 KB of stages
+    static constexpr bool SIGNED = false;
+};
+// Small signed operands: 9 (A) x 10 (B) balanced byte digits, 128 x 24 tiles (MMA N = 240); |D_d| <= 9 * k * 128^2 stays
+// below 2^31 for k <= 14563: 64 K blocks (8192 k values) per pass.  7 x 16 KB + 2 x 30 KB of stages.
+struct TcSmall {
+    static constexpr int LA = fr::SMALL_DIGITS, LB = fr::SMALL_DIGITS + 1, BJ = 24, SA = 7, SB = 2, KB_PASS = 64;
+    static constexpr bool SIGNED = true;
+};
+template <class C>
+struct TcD {
+    static constexpr int NMMA = C::LB * C::BJ;                  // MMA N
+    static constexpr int NDIAG = C::LA + C::LB - 1;             // diagonals d = p + q
+    static constexpr int TCOLS = NDIAG * C::BJ;                 // TMEM columns in use
+    static constexpr int CW = C::BJ / 4;                        // columns j per epilogue warp
+    static constexpr uint32_t B_BYTES = (uint32_t)NMMA * TC_BKB;
+    // kind::i8 instruction descriptor: D = S32, A/B = unsigned (0) or signed (1) 8-bit, both K-major, N, M = 128
+    static constexpr uint32_t IDESC = (2u << 4) | ((C::SIGNED ? 1u : 0u) << 7) | ((C::SIGNED ? 1u : 0u) << 10) |
+                                      ((uint32_t)(NMMA >> 3) << 17) | ((128u >> 4) << 24);
+    static_assert(NMMA % 16 == 0 && NMMA >= 16 && NMMA <= 256, "MMA N for M = 128");
+    static_assert(TCOLS <= 512 && C::BJ % 8 == 0 && CW % 2 == 0, "TMEM columns / epilogue mapping");
+    static_assert(B_BYTES % 1024 == 0, "B stages must keep the 1024-byte swizzle-atom alignment");
+};
+// fused rescale (full-width engine only): every epilogue warp stages 4 witnesses (128 B + 16 B skew) per lane, single-buffered
 using TcWitnessStream = rs::WitnessStreamT<TC_CH_CFG, 1>;
-constexpr uint32_t TC_STAGE_BYTES = tc_epi_warps(true) * 32 * TcWitnessStream::ROW_U4 * 16;
+constexpr uint32_t TC_STAGE_BYTES = TC_EPI_WARPS * 32 * TcWitnessStream::ROW_U4 * 16;
 static_assert((size_t)TC_SA_FUSED_CFG * 16384 + 65536 + 1280 + TC_STAGE_BYTES <= 232448, "fused kernel: shared memory");
-constexpr size_t tc_smem_bytes(bool fused) {
-    return (size_t)(fused ? TC_SA_FUSED : TC_SA_PLAIN) * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES + 256 + 1024 +
-           (fused ? TC_STAGE_BYTES : 0);
+template <class C, bool FUSE>
+__host__ __device__ constexpr int tc_sa() { return FUSE ? TC_SA_FUSED_CFG : C::SA; }
+template <class C, bool FUSE>
+constexpr size_t tc_smem_bytes() {
+    return (size_t)tc_sa<C, FUSE>() * TC_A_BYTES + (size_t)C::SB * TcD<C>::B_BYTES + 256 + 1024 + (FUSE ? TC_STAGE_BYTES : 0);
 }
-// kind::i8 instruction descriptor: D = S32, A = B = unsigned 8-bit, both K-major, N = 256, M = 128
-constexpr uint32_t TC_IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -126,14 +149,14 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
     d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
         "}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -161,26 +184,18 @@ __device__ __forceinline__ void tc_carry_diagonals(const uint32_t* dg, uint32_t*
         cy >>= 32;
     }
 }
-__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t& v0, uint32_t& v1, uint32_t& v2, uint32_t& v3) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                 : "r"(taddr));
-}
 __device__ __forceinline__ void tc_st2_zero(uint32_t taddr) {
     const uint32_t z = 0;
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(z), "r"(z) : "memory");
 }
-__device__ __forceinline__ void tc_st1_zero(uint32_t taddr) {
-    const uint32_t z = 0;
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(z) : "memory");
-}
-// this warp's accumulators (its TMEM lanes, its cnt = 2 or 3 columns j of every diagonal) := 0, then hand them (back)
+// this warp's accumulators (its TMEM lanes, its CW columns j of every diagonal) := 0, then hand them (back)
 // to the MMA warp.  Each warp zeroes only its own columns, so the warps of a lane quarter never race.
-__device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, int cnt, uint32_t bar) {
+template <class C>
+__device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, uint32_t bar) {
 #pragma unroll 9
-    for (int d = 0; d < 63; d++) {
-        tc_st2_zero(tcol0 + 8u * d);
-        if (cnt == 3) tc_st1_zero(tcol0 + 8u * d + 2);  // warp-uniform
+    for (int d = 0; d < TcD<C>::NDIAG; d++) {
+#pragma unroll
+        for (int pr = 0; pr < TcD<C>::CW / 2; pr++) tc_st2_zero(tcol0 + (uint32_t)(C::BJ * d + 2 * pr));
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
@@ -188,55 +203,112 @@ __device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, int cnt, uin
 }
 
 // ---- operand split: byte planes, K-major ---------------------------------------------------------------
+// `mode` (device int, may be null) arbitrates between the two engines without a host round trip: the small-operand
+// split kernels (SMALL) always run and raise *mode when an element is out of the small range; the full-width split
+// kernels and the two mat-mul kernels read it and return at once when the other engine is the one to run.
+// Four consecutive k values of one row / column -> one 32-bit word of every byte plane.
+template <class C>
+__device__ __forceinline__ void tc_plane_words(const Fr* e, uint32_t* words, int nplanes, bool* out_of_range) {
+    if constexpr (C::SIGNED) {
+        uint32_t t[4][3];
+        bool ok = true;
+#pragma unroll
+        for (int r = 0; r < 4; r++) ok &= fr::small_biased(e[r], t[r]);   // zero (K padding) is in range: digits 0
+        *out_of_range = !ok;
+#pragma unroll
+        for (int p = 0; p < 32; p++) {
+            if (p < nplanes) {
+                words[p] = p < fr::SMALL_DIGITS
+                               ? (fr::small_digit_bits(t[0], p) | (fr::small_digit_bits(t[1], p) << 8) |
+                                  (fr::small_digit_bits(t[2], p) << 16) | (fr::small_digit_bits(t[3], p) << 24))
+                               : 0u;   // the padding plane of B
+            }
+        }
+    } else {
+        *out_of_range = false;
+#pragma unroll
+        for (int p = 0; p < 32; p++) {
+            const int limb = p >> 2, sh = (p & 3) * 8;
+            words[p] = ((e[0].l[limb] >> sh) & 0xffu) | (((e[1].l[limb] >> sh) & 0xffu) << 8) |
+                       (((e[2].l[limb] >> sh) & 0xffu) << 16) | (((e[3].l[limb] >> sh) & 0xffu) << 24);
+        }
+    }
+}
+
 // a: n x k (row-major Fr)  ->  planes[p][i][kk], kk < ldk (bytes kk >= k are zero); one thread = 4 k values
-__global__ void tc_split_a_kernel(const Fr* __restrict__ a, uint32_t* __restrict__ planes, int n, int k, int ldk4) {
+template <class C>
+__global__ void __launch_bounds__(256)
+tc_split_a_kernel(const Fr* __restrict__ a, uint32_t* __restrict__ planes, int n, int k, int ldk4, int* mode) {
+    if (!C::SIGNED && mode && *mode == 0) return;   // the small-operand engine runs: nothing to prepare
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * ldk4) return;
     const int i = (int)(idx / ldk4), w = (int)(idx % ldk4);
     Fr e[4];
 #pragma unroll
     for (int t = 0; t < 4; t++) e[t] = (4 * w + t < k) ? ldg_fr(a + (size_t)i * k + 4 * w + t) : fr::zero();
+    uint32_t words[32];
+    bool bad;
+    tc_plane_words<C>(e, words, C::LA, &bad);
+    if (C::SIGNED && bad) atomicOr(mode, 1);
 #pragma unroll
-    for (int p = 0; p < 32; p++) {
-        const int limb = p >> 2, sh = (p & 3) * 8;
-        const uint32_t word = ((e[0].l[limb] >> sh) & 0xffu) | (((e[1].l[limb] >> sh) & 0xffu) << 8) |
-                              (((e[2].l[limb] >> sh) & 0xffu) << 16) | (((e[3].l[limb] >> sh) & 0xffu) << 24);
-        planes[((size_t)p * n + i) * ldk4 + w] = word;
-    }
+    for (int p = 0; p < C::LA; p++) planes[((size_t)p * n + i) * ldk4 + w] = words[p];
 }
-// b: k x m (row-major Fr)  ->  planes[q][j][kk]  (the transposed operand: K-major rows per column j of B)
-__global__ void tc_split_b_kernel(const Fr* __restrict__ b, uint32_t* __restrict__ planes, int k, int m, int ldk4) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)m * ldk4) return;
-    const int j = (int)(idx / ldk4), w = (int)(idx % ldk4);
+
+// b: k x m (row-major Fr)  ->  planes[q][j][kk]  (the transposed operand: K-major rows per column j of B).
+// One CTA = 128 k values x 8 columns: the loads walk B along its rows (8 x 32 B = 256 contiguous bytes per k), the
+// words go through a padded shared-memory tile, and every plane row leaves as one coalesced 128-byte store.
+constexpr int TC_SPLIT_ROW_W = 36;   // words per (plane, column) tile row: 32 + 4 of skew (conflict-free both ways)
+template <class C>
+__global__ void __launch_bounds__(256)
+tc_split_b_kernel(const Fr* __restrict__ b, uint32_t* __restrict__ planes, int k, int m, int ldk4, int* mode) {
+    if (!C::SIGNED && mode && *mode == 0) return;
+    __shared__ uint32_t tile[C::LB * 8 * TC_SPLIT_ROW_W];
+    const int k0 = blockIdx.x * 128, j0 = blockIdx.y * 8;
+    const int j = threadIdx.x & 7, kq = threadIdx.x >> 3;       // kq: 0..31 -> k values k0 + 4*kq .. +3
     Fr e[4];
 #pragma unroll
-    for (int t = 0; t < 4; t++) e[t] = (4 * w + t < k) ? ldg_fr(b + (size_t)(4 * w + t) * m + j) : fr::zero();
+    for (int t = 0; t < 4; t++) {
+        const int kk = k0 + 4 * kq + t;
+        e[t] = (kk < k && j0 + j < m) ? ldg_fr(b + (size_t)kk * m + j0 + j) : fr::zero();
+    }
+    uint32_t words[32];
+    bool bad;
+    tc_plane_words<C>(e, words, C::LB, &bad);
+    if (C::SIGNED && bad) atomicOr(mode, 1);
 #pragma unroll
-    for (int q = 0; q < 32; q++) {
-        const int limb = q >> 2, sh = (q & 3) * 8;
-        const uint32_t word = ((e[0].l[limb] >> sh) & 0xffu) | (((e[1].l[limb] >> sh) & 0xffu) << 8) |
-                              (((e[2].l[limb] >> sh) & 0xffu) << 16) | (((e[3].l[limb] >> sh) & 0xffu) << 24);
-        planes[((size_t)q * m + j) * ldk4 + w] = word;
+    for (int q = 0; q < C::LB; q++) tile[(q * 8 + j) * TC_SPLIT_ROW_W + kq] = words[q];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w0 = k0 / 4;
+    for (int row = warp; row < C::LB * 8; row += 8) {
+        const int q = row >> 3, jj = row & 7;
+        if (j0 + jj < m && w0 + lane < ldk4)
+            planes[((size_t)q * m + j0 + jj) * ldk4 + w0 + lane] = tile[row * TC_SPLIT_ROW_W + lane];
     }
 }
 
 // ---- the tensor-core kernel ----------------------------------------------------------------------------
-// FUSE (experimental, off by default -- h2svd_debug_set_fuse_rescale): the epilogue also emits the rescale_matrix
-// witnesses (K4, rescale_dev.cuh) of every C element it produces, so that the witness stream (2 KB per element) is
-// written under the MMAs of the next tile instead of after the mat-mul.  Bit-identical, but measured NOT to pay: the
-// MMAs read their operands from shared memory at 96 of the SM's 128 B/clk, and staging the witnesses for the bulk
-// stores needs another ~60 B/clk, so a fused tile takes 126 us against 69 us (MMAs) + 58 us (stand-alone rescale):
-// N=1024 0.91 ms fused vs 1.01 ms as two kernels (a wave-rounding gain only), slower on 1-4 wave slabs.  Direct 32-byte
-// global stores instead of staging: 1.37 ms.  It would need the A operand in TMEM or 2-CTA MMAs (halved B reads).
-template <bool FUSE>
-__global__ void __launch_bounds__(tc_threads(FUSE), 1)
+// FUSE (experimental, off by default -- tuning switch "fuse_rescale", full-width engine only): the epilogue also emits
+// the rescale_matrix witnesses (K4, rescale_dev.cuh) of every C element it produces, so that the witness stream (2 KB per
+// element) is written under the MMAs of the next tile instead of after the mat-mul.  Bit-identical, but measured NOT to
+// pay: the MMAs read their operands from shared memory at 96 of the SM's 128 B/clk, and staging the witnesses for the
+// bulk stores needs another ~60 B/clk, so a fused tile takes 126 us against 69 us (MMAs) + 58 us (stand-alone rescale).
+template <class C, bool FUSE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     Fr* __restrict__ c, int n, int k, int m, int tiles_j, int num_tiles, int* err,
+                    const int* __restrict__ mode, int run_if_mode,
                     const __grid_constant__ rs::RescaleConsts kc, Fr* __restrict__ out_q, Fr* __restrict__ out_wit) {
-    constexpr int TC_SA = FUSE ? TC_SA_FUSED : TC_SA_PLAIN;
-    constexpr int EPI_WARPS = 16;
-    constexpr int MAXC = TC_BJ / (EPI_WARPS / 4);  // columns j per epilogue warp (the last warp of a quarter may own fewer)
+    using D = TcD<C>;
+    constexpr int TC_SA = tc_sa<C, FUSE>();
+    constexpr int TC_SB = C::SB;
+    constexpr int EPI_WARPS = TC_EPI_WARPS;
+    constexpr int CW = D::CW;
+    constexpr int BJ = C::BJ;
+    constexpr uint32_t TC_B_BYTES = D::B_BYTES;
+    static_assert(!FUSE || !C::SIGNED, "the fused rescale epilogue exists for the full-width engine only");
+    // engine arbitration (uniform over the grid): the split kernels earlier in the stream decided which engine runs
+    if (mode != nullptr && (*mode != 0) != (run_if_mode != 0)) return;
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = tc_smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
@@ -275,7 +347,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     const int kblocks = (k + TC_BKB - 1) / TC_BKB;
-    const int passes = (kblocks + TC_KB_PASS - 1) / TC_KB_PASS;
+    const int passes = (kblocks + C::KB_PASS - 1) / C::KB_PASS;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -287,9 +359,9 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const uint32_t sb = ub % TC_SB;
                     tc_mbar_wait(empty_b + 8 * sb, ((ub / TC_SB) & 1) ^ 1, err);
                     tc_mbar_expect_tx(full_b + 8 * sb, TC_B_BYTES);
-                    tc_tma_3d(s_b + sb * TC_B_BYTES, &tm_b, kb * TC_BKB, jb * TC_BJ, 0, full_b + 8 * sb);
+                    tc_tma_3d(s_b + sb * TC_B_BYTES, &tm_b, kb * TC_BKB, jb * BJ, 0, full_b + 8 * sb);
                     ub++;
-                    for (int p = 0; p < 32; p++) {
+                    for (int p = 0; p < C::LA; p++) {
                         const uint32_t sa = ua % TC_SA;
                         tc_mbar_wait(empty_a + 8 * sa, ((ua / TC_SA) & 1) ^ 1, err);
                         tc_mbar_expect_tx(full_a + 8 * sa, TC_A_BYTES);
@@ -306,12 +378,12 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_empty, round & 1, err);  // accumulators zeroed by the epilogue warps
                 tc_fence_after();
-                const int kb_end = min(kblocks, (pass + 1) * TC_KB_PASS);
-                for (int kb = pass * TC_KB_PASS; kb < kb_end; kb++) {
+                const int kb_end = min(kblocks, (pass + 1) * C::KB_PASS);
+                for (int kb = pass * C::KB_PASS; kb < kb_end; kb++) {
                     const uint32_t sb = ub % TC_SB;
                     tc_mbar_wait(full_b + 8 * sb, (ub / TC_SB) & 1, err);
                     const uint64_t bdesc = tc_smem_desc(s_b + sb * TC_B_BYTES);
-                    for (int p = 0; p < 32; p++) {
+                    for (int p = 0; p < C::LA; p++) {
                         const uint32_t sa = ua % TC_SA;
                         tc_mbar_wait(full_a + 8 * sa, (ua / TC_SA) & 1, err);
                         tc_fence_after();
@@ -319,7 +391,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                             const uint64_t adesc = tc_smem_desc(s_a + sa * TC_A_BYTES);
 #pragma unroll
                             for (int s = 0; s < TC_BKB / 32; s++)  // 32 bytes of K per instruction: +2 in 16-byte units
-                                tc_mma_i8(tmem_base + 8u * p, adesc + 2u * s, bdesc + 2u * s, 1u);
+                                tc_mma_i8(tmem_base + (uint32_t)(BJ * p), adesc + 2u * s, bdesc + 2u * s, D::IDESC, 1u);
                             tc_commit(empty_a + 8 * sa);  // frees the A stage once these MMAs have read it
                         }
                         __syncwarp();
@@ -338,12 +410,10 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ===== epilogue: thread = row of the tile =====
         const uint32_t quarter = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int il = quarter * 32 + lane;
-        // this warp's columns j0 .. j0+cnt-1 of the tile: 2 each with 16 warps, 3/3/2 with 12 warps
-        const int jg = (warp - 2) >> 2;
-        const int j0 = jg * MAXC;
-        const int cnt = TC_BJ - j0 < MAXC ? TC_BJ - j0 : MAXC;
+        const int jg = (warp - 2) >> 2;     // this warp's columns j0 .. j0+CW-1 of the tile
+        const int j0 = jg * CW;
         const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
-        tc_zero_and_release(tlane + j0, cnt, tmem_empty);
+        tc_zero_and_release<C>(tlane + j0, tmem_empty);
         TcWitnessStream ws;
         if (FUSE) {
             ws.warp_row0 = stage + (size_t)(warp - 2) * 32 * TcWitnessStream::ROW_U4;
@@ -359,42 +429,45 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_full, round & 1, err);
                 tc_fence_after();
-                // Phase 1 (on the critical path of the next tile): read this warp's columns of all 63 diagonals and
-                // carry them into 18-limb integers.  T = sum_d dg[d] * 2^(8d): diagonals d = 4g + r sit at whole-word
-                // offsets g for fixed r, so T = Y0 + (Y1 << 8) + (Y2 << 16) + (Y3 << 24) with Y_r[g] = dg[4g + r].
-                uint32_t dg[MAXC][64];
+                // Phase 1 (on the critical path of the next tile): read this warp's columns of all diagonals and carry
+                // them into multi-limb integers T = sum_d dg[d] * 2^(8d).
+                constexpr int TW = C::SIGNED ? 6 : 18;
+                uint32_t T[CW][TW];
 #pragma unroll
-                for (int d = 0; d < 63; d++) {
-                    if (MAXC == 2) {
-                        tc_ld2(tlane + 8u * d + j0, dg[0][d], dg[1][d]);
-                    } else {
-                        uint32_t unused;  // 4-column load; a 2-column warp reads (and ignores) its neighbours' columns
-                        tc_ld4(tlane + 8u * d + j0, dg[0][d], dg[1][d], dg[MAXC - 1][d], unused);
+                for (int pr = 0; pr < CW / 2; pr++) {
+                    uint32_t dg[2][64];
+#pragma unroll
+                    for (int d = 0; d < D::NDIAG; d++) tc_ld2(tlane + (uint32_t)(BJ * d + j0 + 2 * pr), dg[0][d], dg[1][d]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // pin the loaded registers behind the wait (the compiler must not read them earlier)
+#pragma unroll
+                    for (int d = 0; d < D::NDIAG; d++)
+#pragma unroll
+                        for (int q = 0; q < 2; q++) asm volatile("" : "+r"(dg[q][d]));
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        if constexpr (C::SIGNED) {
+                            fr::carry_signed<D::NDIAG>(dg[q], T[2 * pr + q]);
+                        } else {
+                            // diagonals d = 4g + r sit at whole-word offsets g for fixed r:
+                            // T = Y0 + (Y1 << 8) + (Y2 << 16) + (Y3 << 24) with Y_r[g] = dg[4g + r]
+                            dg[q][63] = 0;
+                            tc_carry_diagonals(dg[q], T[2 * pr + q]);
+                        }
                     }
-                }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // pin the loaded registers behind the wait (the compiler must not read them earlier)
-#pragma unroll
-                for (int d = 0; d < 63; d++)
-#pragma unroll
-                    for (int q = 0; q < MAXC; q++) asm volatile("" : "+r"(dg[q][d]));
-                uint32_t T[MAXC][18];
-#pragma unroll
-                for (int q = 0; q < MAXC; q++) {
-                    dg[q][63] = 0;
-                    tc_carry_diagonals(dg[q], T[q]);
                 }
                 // the accumulators are free again: zero them and let the MMA warp start the next tile while the
                 // Montgomery reductions (and the rescale witnesses) below run
                 tc_fence_before();  // order the TMEM reads above before the zeroing stores / the next MMAs
-                tc_zero_and_release(tlane + j0, cnt, tmem_empty);
+                tc_zero_and_release<C>(tlane + j0, tmem_empty);
                 // Phase 2 (overlaps the next tile's MMAs)
-                Fr res[MAXC];
+                Fr res[CW];
 #pragma unroll
-                for (int q = 0; q < MAXC; q++) {
-                    res[q] = fr::reduce_wide_acc(T[q]);
-                    const int gj = jb * TC_BJ + j0 + q;
-                    if (q < cnt && gi < n && gj < m) {
+                for (int q = 0; q < CW; q++) {
+                    if constexpr (C::SIGNED) res[q] = fr::signed6_to_mont(T[q]);
+                    else res[q] = fr::reduce_wide_acc(T[q]);
+                    const int gj = jb * BJ + j0 + q;
+                    if (gi < n && gj < m) {
                         Fr* dst = c + (size_t)gi * m + gj;
                         if (pass > 0) res[q] = fr::add(ld_fr(dst), res[q]);
                         st_fr(dst, res[q]);
@@ -405,9 +478,9 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const int row0 = ib * TC_BM + (int)quarter * 32;
                     const int valid = n - row0 < 32 ? n - row0 : 32;
 #pragma unroll
-                    for (int q = 0; q < MAXC; q++) {
-                        const int gj = jb * TC_BJ + j0 + q;
-                        if (q < cnt && gj < m && valid > 0) {  // warp-uniform
+                    for (int q = 0; q < CW; q++) {
+                        const int gj = jb * BJ + j0 + q;
+                        if (gj < m && valid > 0) {  // warp-uniform
                             ws.valid = valid;
                             ws.gwarp = out_wit + ((size_t)row0 * m + gj) * (size_t)kc.p.W;
                             const Fr qv = rs::rescale_element(ws, kc, gi < n ? res[q] : fr::zero());
@@ -444,9 +517,79 @@ tc_encode_fn tc_encoder() {
     return fn;
 }
 
-}  // namespace
+size_t tc_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-int g_matmul_tc = -1;  // -1 auto, 0 off, 1 force (triage hook; see launch_fr_matmul)
+// split kernels + mat-mul kernel of ONE engine on pre-carved plane buffers
+template <class C>
+int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m,
+                     size_t ldk, uint8_t* a8, uint8_t* b8, int* mode, int run_if_mode, bool split_only, bool mm_only,
+                     const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit) {
+    using D = TcD<C>;
+    const int ldk4 = (int)(ldk / 4);
+    if (!mm_only) {
+        const size_t ta = n * (size_t)ldk4;
+        tc_split_a_kernel<C><<<(unsigned)((ta + 255) / 256), 256, 0, ctx->stream>>>(a, reinterpret_cast<uint32_t*>(a8), (int)n,
+                                                                                   (int)k, ldk4, mode);
+        H2SVD_LAUNCH_CHECK(ctx);
+        const dim3 gb((unsigned)((ldk + 127) / 128), (unsigned)((m + 7) / 8));
+        tc_split_b_kernel<C><<<gb, 256, 0, ctx->stream>>>(b, reinterpret_cast<uint32_t*>(b8), (int)k, (int)m, ldk4, mode);
+        H2SVD_LAUNCH_CHECK(ctx);
+    }
+    if (split_only) return H2SVD_OK;
+    CUtensorMap tm_a, tm_b;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)(C::LA * n)};
+        const cuuint64_t strides[1] = {(cuuint64_t)ldk};
+        const cuuint32_t box[2] = {(cuuint32_t)TC_BKB, (cuuint32_t)TC_BM};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, a8, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("fr_matmul (tensor-core engine): tensor map for A failed (CUresult %d)", (int)r);
+            return H2SVD_ECUDA;
+        }
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)m, (cuuint64_t)C::LB};
+        const cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)(m * ldk)};
+        const cuuint32_t box[3] = {(cuuint32_t)TC_BKB, (cuuint32_t)C::BJ, (cuuint32_t)C::LB};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&tm_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, b8, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("fr_matmul (tensor-core engine): tensor map for B failed (CUresult %d)", (int)r);
+            return H2SVD_ECUDA;
+        }
+    }
+    const int tiles_i = (int)((n + TC_BM - 1) / TC_BM), tiles_j = (int)((m + C::BJ - 1) / C::BJ);
+    const long long tiles = (long long)tiles_i * tiles_j;
+    if (tiles >= (1LL << 31)) {
+        set_error("fr_matmul (tensor-core engine): too many tiles");
+        return H2SVD_EINVAL;
+    }
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    if (fuse) {
+        if constexpr (!C::SIGNED) {
+            H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, true>), (tc_smem_bytes<C, true>()));
+            fr_matmul_tc_kernel<C, true><<<grid, TC_THREADS, tc_smem_bytes<C, true>(), ctx->stream>>>(
+                tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, *fuse, out_q,
+                out_wit);
+        }
+    } else {
+        static const rs::RescaleConsts none{};
+        H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, false>), (tc_smem_bytes<C, false>()));
+        fr_matmul_tc_kernel<C, false><<<grid, TC_THREADS, tc_smem_bytes<C, false>(), ctx->stream>>>(
+            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, none, nullptr,
+            nullptr);
+    }
+    H2SVD_LAUNCH_CHECK(ctx);
+    (void)D::NMMA;
+    return H2SVD_OK;
+}
+
+}  // namespace
 
 bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
     // p * n + ib * 128 and the plane sizes are 32-bit TMA coordinates / comfortably below 2^31
@@ -461,80 +604,34 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
         set_error("fr_matmul (tensor-core engine): cuTensorMapEncodeTiled is not available from this driver");
         return H2SVD_ECUDA;
     }
+    const bool try_small = ctx->tune.matmul_small != 0 && fuse == nullptr;
     const size_t ldk = (k + 15) & ~(size_t)15;  // TMA row pitch: multiple of 16 bytes
-    const size_t bytes_a = 32 * n * ldk, bytes_b = 32 * m * ldk;
-    const size_t need = ((bytes_a + 255) & ~(size_t)255) + bytes_b;
-    if (ctx->kara_ws_bytes < need) {  // the operand workspace is shared with the Karatsuba engine (never both at once)
-        H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->kara_ws) H2SVD_CUDA(cudaFree(ctx->kara_ws));
-        ctx->kara_ws = nullptr;
-        ctx->kara_ws_bytes = 0;
-        H2SVD_CUDA(cudaMalloc(&ctx->kara_ws, need));
-        ctx->kara_ws_bytes = need;
+    const size_t full_a = tc_align256(TcFull::LA * n * ldk), full_b = tc_align256(TcFull::LB * m * ldk);
+    const size_t small_a = tc_align256(TcSmall::LA * n * ldk), small_b = tc_align256(TcSmall::LB * m * ldk);
+    const size_t need = full_a + full_b + (try_small ? small_a + small_b : 0);
+    // the operand workspace is shared with the Karatsuba engine (never both at once)
+    H2SVD_TRY(ws_grow(ctx, &ctx->kara_ws, &ctx->kara_ws_bytes, need));
+    uint8_t* fa8 = reinterpret_cast<uint8_t*>(ctx->kara_ws);
+    uint8_t* fb8 = fa8 + full_a;
+    uint8_t* sa8 = fb8 + full_b;
+    uint8_t* sb8 = sa8 + small_a;
+    if (!try_small) {
+        ctx->last_engine = 2;
+        return tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, nullptr, 0, false, false, fuse, out_q,
+                                        out_wit);
     }
-    uint8_t* a8 = reinterpret_cast<uint8_t*>(ctx->kara_ws);
-    uint8_t* b8 = a8 + ((bytes_a + 255) & ~(size_t)255);
-    const int ldk4 = (int)(ldk / 4);
-    {
-        const size_t ta = n * (size_t)ldk4, tb = m * (size_t)ldk4;
-        tc_split_a_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, ctx->stream>>>(a, reinterpret_cast<uint32_t*>(a8),
-                                                                                 (int)n, (int)k, ldk4);
-        H2SVD_LAUNCH_CHECK(ctx);
-        tc_split_b_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(b, reinterpret_cast<uint32_t*>(b8),
-                                                                                 (int)k, (int)m, ldk4);
-        H2SVD_LAUNCH_CHECK(ctx);
-    }
-    CUtensorMap tm_a, tm_b;
-    {
-        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)(32 * n)};
-        const cuuint64_t strides[1] = {(cuuint64_t)ldk};
-        const cuuint32_t box[2] = {(cuuint32_t)TC_BKB, (cuuint32_t)TC_BM};
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, a8, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("fr_matmul (tensor-core engine): tensor map for A failed (CUresult %d)", (int)r);
-            return H2SVD_ECUDA;
-        }
-    }
-    {
-        const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)m, 32};
-        const cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)(m * ldk)};
-        const cuuint32_t box[3] = {(cuuint32_t)TC_BKB, (cuuint32_t)TC_BJ, 32};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult r = encode(&tm_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, b8, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("fr_matmul (tensor-core engine): tensor map for B failed (CUresult %d)", (int)r);
-            return H2SVD_ECUDA;
-        }
-    }
-    const int tiles_i = (int)((n + TC_BM - 1) / TC_BM), tiles_j = (int)((m + TC_BJ - 1) / TC_BJ);
-    const long long tiles = (long long)tiles_i * tiles_j;
-    if (tiles >= (1LL << 31)) {
-        set_error("fr_matmul (tensor-core engine): too many tiles");
-        return H2SVD_EINVAL;
-    }
-    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    if (fuse) {
-        H2SVD_SET_SMEM(ctx, fr_matmul_tc_kernel<true>, tc_smem_bytes(true));
-        fr_matmul_tc_kernel<true><<<grid, tc_threads(true), tc_smem_bytes(true), ctx->stream>>>(
-            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, *fuse, out_q, out_wit);
-    } else {
-        static const rs::RescaleConsts none{};
-        H2SVD_SET_SMEM(ctx, fr_matmul_tc_kernel<false>, tc_smem_bytes(false));
-        fr_matmul_tc_kernel<false><<<grid, tc_threads(false), tc_smem_bytes(false), ctx->stream>>>(
-            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, none, nullptr, nullptr);
-    }
-    H2SVD_LAUNCH_CHECK(ctx);
-    return H2SVD_OK;
+    // Both engines are enqueued; *d_mode (0 = every operand is a small signed integer, else 1), written by the
+    // small-operand split kernels, decides on the device which of them does the work.
+    ctx->last_engine = 3;
+    H2SVD_CUDA(cudaMemsetAsync(ctx->d_mode, 0, sizeof(int), ctx->stream));
+    H2SVD_TRY(tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, true, false, nullptr,
+                                        nullptr, nullptr));
+    H2SVD_TRY(tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, true, false, nullptr,
+                                       nullptr, nullptr));
+    H2SVD_TRY(tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, true, nullptr,
+                                        nullptr, nullptr));
+    return tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, false, true, nullptr,
+                                    nullptr, nullptr);
 }
 
 }  // namespace h2svd
-
-extern "C" int h2svd_debug_set_matmul_tc(int v) {
-    h2svd::g_matmul_tc = v;
-    return 0;
-}

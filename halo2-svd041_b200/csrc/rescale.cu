@@ -133,8 +133,10 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
         const Fr q = rescale_element(ws, k, am);
         if (live) st_fr(out_q + e, q);
     }
-    // shared memory must outlive every bulk read, and the writes must be complete at kernel end
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // shared memory must outlive every bulk read, and the writes must be complete at kernel end.  Bulk async-groups
+    // belong to the thread that committed them and elect.sync need not pick lane 0: every lane waits (a no-op for lanes
+    // that never committed a group).
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // check_abs_less_than(x, bnd) (reference src/matrix/mod.rs:425-437), optionally of a difference x - y
@@ -166,7 +168,7 @@ abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __r
         stream_cbls(ws, k.lc, fr::from_mont_fast(tm), tm, k.n, k.i_pow, k.i_bound, k.m_pow, k.m_bound);
         ws.flush();
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every lane: see rescale_kernel
 }
 
 // RangeChip::range_check(x, range_bits) with n = ceil(range_bits / lb) limbs: limbs + running sums (none when
@@ -201,7 +203,7 @@ range_check_kernel(const Fr* __restrict__ x, Fr* __restrict__ out_wit, size_t co
         }
         ws.flush();
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every lane: see rescale_kernel
 }
 
 // mat_times_diag_mat (reference :610-627): out[i][j] = a[i][j] * v[j], j < cols_v <= lda
@@ -230,8 +232,6 @@ int rescale_params(int P, int lb, int S, int A, int* n_d, int* n_r) {
     // per check_big_less_than_safe: range_check (2n-1) + chk, xp + range_check (2n-1) = 4n; only chk, xp when n == 1
     return 4 + (nd >= 2 ? 4 * nd : 2) + (nr >= 2 ? 4 * nr : 2);
 }
-
-static int g_force_generic = 0;
 
 static void fill_limb_consts(LimbConsts& lc, int lb, int npos) {
     lc.lb = lb;
@@ -283,7 +283,7 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
         return H2SVD_EINVAL;
     }
     if (count == 0) return H2SVD_OK;
-    if (p.n_d > MAX_POS || p.n_r > MAX_POS || g_force_generic) {
+    if (p.n_d > MAX_POS || p.n_r > MAX_POS || ctx->tune.rescale_generic) {
         rescale_generic_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(cs, out_q, out_wit, count, p);
         H2SVD_LAUNCH_CHECK(ctx);
         return H2SVD_OK;
@@ -385,7 +385,3 @@ int launch_mat_times_diag(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows,
 
 }  // namespace h2svd
 
-extern "C" int h2svd_debug_set_rescale_generic(int v) {
-    h2svd::g_force_generic = v;
-    return 0;
-}

@@ -64,8 +64,11 @@ __global__ void quantize_kernel(const double* __restrict__ x, Fr* __restrict__ o
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         const double v = x[i];
-        // floor(|x| * 2^P + 0.5); the scaling by a power of two is exact
-        const double mag = floor(fabs(v) * scalbn(1.0, P) + 0.5);
+        // round-half-away-from-zero of |x| * 2^P (PDF Eq. 11, Rust f64::round).  The scaling by a power of two is exact and
+        // so is y - floor(y); forming y + 0.5 instead would tie-to-even for odd y in [2^52, 2^53) and round 0.49999999999999994 up.
+        const double y = fabs(v) * scalbn(1.0, P);
+        double mag = floor(y);
+        if (y - mag >= 0.5) mag += 1.0;
         Fr q = fr::zero();
         if (!(mag < scalbn(1.0, 127))) {
             atomicExch(flag, 1);  // NaN / inf / out of range

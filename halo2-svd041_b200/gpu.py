@@ -103,6 +103,20 @@ class Handle:
     def sync(self) -> None:
         _ffi.check(self._lib.h2svd_sync(self._h))
 
+    # ---- triage / tuning switches (per handle; not part of the public header) ----
+    TUNE_KEYS = ("matmul_tc", "matmul_small", "matmul_karatsuba", "matmul_streamk", "matmul_variant", "fuse_rescale",
+                 "rescale_generic", "matvec_warp_kernel")
+
+    def tune(self, key: str, value: int) -> None:
+        """matmul_tc / matmul_small: -1 auto, 0 never, 1 always; matmul_karatsuba: -1 auto, 0 schoolbook, 1..3 variants;
+        matmul_streamk: -1 auto, 0 never, 1 always; fuse_rescale, rescale_generic, matvec_warp_kernel: 0/1."""
+        _ffi.check(self._lib.h2svd_debug_tune(self._h, key.encode(), int(value)))
+
+    def last_matmul_engine(self) -> str:
+        """Which engine the last fr_matmul launch of THIS handle used (bench.py reports the matching roofline)."""
+        return {0: "schoolbook", 1: "karatsuba", 2: "tensor", 3: "tensor-small"}.get(
+            self._lib.h2svd_debug_last_matmul_engine(self._h), "none")
+
     # ---- host-pointer entry points (numpy) ----
     def fr_matmul(self, a: np.ndarray, b: np.ndarray, b_transposed: bool = False,
                   out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -322,6 +336,32 @@ class Handle:
                                                         lookup_bits, shift_bits, a_num_bits, self._tp(c_s),
                                                         self._tp(out_q), self._tp(out_wit)))
 
+    def zkmatrix_mul_witness_dev(self, a, b, gamma, precision_bits: int, lookup_bits: int, c_s, q, wit, powers,
+                                 prefix_cv, prefix_bv, prefix_abv, diff, is_zero, inv, bv_rows: Optional[tuple] = None,
+                                 shift_bits: int = -1, a_num_bits: int = -1) -> None:
+        """honest_prover_mat_mul -> rescale_matrix -> verify_mul for the rows of `a`, device tensors, asynchronous; the
+        Freivalds mat-vecs are forked onto the handle's side stream inside the call (h2svd_zkmatrix_mul_witness_dev)."""
+        rows, k, m = a.shape[0], a.shape[1], b.shape[1]
+        r0, r1 = bv_rows if bv_rows is not None else (0, k)
+        _ffi.check(self._lib.h2svd_zkmatrix_mul_witness_dev(
+            self._h, self._tp(a), self._tp(b), self._tp(gamma), rows, k, m, precision_bits, lookup_bits, shift_bits,
+            a_num_bits, r0, r1, self._tp(c_s), self._tp(q), self._tp(wit), self._tp(powers), self._tp(prefix_cv),
+            self._tp(prefix_bv) if r1 > r0 else ct.c_void_p(0), self._tp(prefix_abv), self._tp(diff), self._tp(is_zero),
+            self._tp(inv)))
+
+    def mat_vec_totals_dev(self, a, v, totals) -> None:
+        rows, ln = a.shape[0], a.shape[1]
+        _ffi.check(self._lib.h2svd_mat_vec_totals_dev(self._h, self._tp(a), self._tp(v), rows, ln, self._tp(totals)))
+
+    # ---- CUDA-graph capture of *_dev call sequences ----
+    def graph_begin(self) -> None:
+        _ffi.check(self._lib.h2svd_graph_begin(self._h))
+
+    def graph_end(self) -> "Graph":
+        g = ct.c_void_p()
+        _ffi.check(self._lib.h2svd_graph_end(self._h, ct.byref(g)))
+        return Graph(self, g)
+
     def zkvec_inner_prefix_dev(self, x, self_, out) -> None:
         batch, ln = x.shape[0], x.shape[1]
         _ffi.check(self._lib.h2svd_zkvec_inner_prefix_dev(self._h, self._tp(x), self._tp(self_), batch, ln,
@@ -343,41 +383,82 @@ class Handle:
         _ffi.check(self._lib.h2svd_check_canonical_dev(self._h, self._tp(x), x.numel() // 4))
 
 
-def set_rescale_generic(v: bool) -> None:
-    """Triage hook: force the generic (unstaged) rescale kernel."""
-    _ffi.load().h2svd_debug_set_rescale_generic(int(v))
+class Graph:
+    """A recorded sequence of *_dev calls (h2svd_graph); launch() replays it on the handle's stream."""
+
+    def __init__(self, handle: Handle, g) -> None:
+        self._handle, self._g = handle, g
+
+    def launch(self) -> None:
+        _ffi.check(self._handle._lib.h2svd_graph_launch(self._handle._h, self._g))
+
+    def close(self) -> None:
+        if self._g:
+            self._handle._lib.h2svd_graph_destroy(self._g)
+            self._g = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def set_matvec_warp_kernel(v: bool) -> None:
-    """Triage hook: force the warp-per-segment mat-vec prefix kernel instead of the tile kernel."""
-    _ffi.load().h2svd_debug_set_matvec_warp_kernel(int(v))
+class MultiHandle:
+    """h2svd_multi: one handle per GPU in ONE process; rows of A / C partitioned, B replicated, no exchange step."""
 
+    def __init__(self, devices) -> None:
+        self._lib = _ffi.load()
+        devs = (ct.c_int * len(devices))(*devices)
+        h = ct.c_void_p()
+        _ffi.check(self._lib.h2svd_multi_create(ct.byref(h), devs, len(devices)))
+        self._h = h
 
-def set_matmul_karatsuba(v: int) -> None:
-    """Triage hook: 0 schoolbook kernels, 1..3 Karatsuba kernel variants."""
-    _ffi.load().h2svd_debug_set_matmul_karatsuba(v)
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.h2svd_multi_destroy(self._h)
+            self._h = None
 
+    def __enter__(self) -> "MultiHandle":
+        return self
 
-def last_matmul_engine() -> str:
-    """Which engine the last fr_matmul launch of this process used (bench.py reports the matching roofline)."""
-    return {0: "schoolbook", 1: "karatsuba", 2: "tensor"}.get(_ffi.load().h2svd_debug_last_matmul_engine(), "none")
+    def __exit__(self, *exc) -> None:
+        self.close()
 
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
-def set_fuse_rescale(v: int) -> None:
-    """Tuning hook: 1 = emit the rescale witnesses from the tensor-core mat-mul epilogue (experimental), 0 = off (default)."""
-    _ffi.load().h2svd_debug_set_fuse_rescale(v)
+    @property
+    def count(self) -> int:
+        return self._lib.h2svd_multi_count(self._h)
 
+    def launch_count(self) -> int:
+        return sum(int(self._lib.h2svd_launch_count(self._lib.h2svd_multi_ctx(self._h, i))) for i in range(self.count))
 
-def set_matmul_tc(v: int) -> None:
-    """Triage hook: -1 auto, 0 never, 1 always use the tensor-core (tcgen05 kind::i8) mat-mul engine."""
-    _ffi.load().h2svd_debug_set_matmul_tc(v)
-
-
-def set_matmul_streamk(v: int) -> None:
-    """Triage hook: -1 auto (default), 0 never, 1 always use the stream-K mat-mul schedule."""
-    _ffi.load().h2svd_debug_set_matmul_streamk(v)
-
-
-def set_matmul_variant(v: int) -> None:
-    """Triage/tuning hook (not part of the public header)."""
-    _ffi.load().h2svd_debug_set_matmul_variant(v)
+    def zkmatrix_mul_witness(self, a: np.ndarray, b: np.ndarray, gamma: np.ndarray, precision_bits: int,
+                             lookup_bits: int, shift_bits: int = -1, a_num_bits: int = -1,
+                             out: Optional[dict] = None) -> dict:
+        n, k = _fr_shape(a, 2)
+        k2, m = _fr_shape(b, 2)
+        if k != k2:
+            raise ValueError("zkmatrix_mul_witness: inner dimensions differ")
+        W = self._lib.h2svd_rescale_witness_count(precision_bits, lookup_bits, shift_bits, a_num_bits)
+        if W < 0:
+            _ffi.check(W)
+        shapes = dict(c_s=(n, m), q=(n, m), wit=(n * m, W), powers=(m,), prefix_cv=(n, m), prefix_bv=(k, m),
+                      prefix_abv=(n, k), diff=(n,), is_zero=(n,), inv=(n,))
+        res = {}
+        for key, shp in shapes.items():
+            arr = out[key] if out is not None and key in out else _np_fr(*shp)
+            if tuple(arr.shape) != shp + (4,):
+                raise ValueError(f"zkmatrix_mul_witness: out[{key!r}] has shape {arr.shape}, expected {shp + (4,)}")
+            res[key] = arr
+        g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
+        _ffi.check(self._lib.h2svd_multi_zkmatrix_mul_witness(
+            self._h, _np_ptr(a), _np_ptr(b), _np_ptr(g), n, k, m, precision_bits, lookup_bits, shift_bits, a_num_bits,
+            *[_np_ptr(res[key]) for key in ("c_s", "q", "wit", "powers", "prefix_cv", "prefix_bv", "prefix_abv", "diff",
+                                            "is_zero", "inv")]))
+        return res

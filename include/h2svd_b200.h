@@ -13,8 +13,10 @@
  *    row-major and contiguous.  No conversion happens on either side of the boundary.
  *  - Every function returns 0 on success or a negative H2SVD_E* code; nothing unwinds, nothing
  *    aborts.  h2svd_last_error() returns a static/thread-local description of the last failure.
- *  - A handle owns one CUDA device, one stream and a grow-only device workspace.  It is NOT
- *    thread-safe (it mirrors the reference's `&mut Context`): one handle per thread / per GPU.
+ *  - A handle owns one CUDA device, one stream (plus two internal side streams) and grow-only device workspaces.  It
+ *    is NOT thread-safe (it mirrors the reference's `&mut Context`): one handle per thread / per GPU.  There is no
+ *    process-global mutable state: two handles never influence each other.  h2svd_multi (below) bundles one handle
+ *    per GPU for single-process multi-GPU callers.
  *  - Functions without suffix take HOST pointers (pageable or pinned) and do H2D + kernels + D2H
  *    before returning.  Functions ending in _dev take DEVICE pointers on the handle's device, are
  *    asynchronous on the handle's stream (h2svd_sync to wait) and never touch host memory.
@@ -63,9 +65,11 @@ uint64_t h2svd_launch_count(h2svd_ctx *ctx);
  * b_transposed != 0, `b` holds the m x k matrix B^T (what ZkMatrix::transpose_matrix, :408, would
  * have been called on), so callers such as check_svd_phase0 (src/svd/mod.rs:96,109,112) need not
  * materialise the transpose.  Asserts of the reference (:515) become H2SVD_EINVAL.
- * Two engines compute the same bytes: from 64^3 on (and k >= 32) the product runs on the tensor cores as exact u8 x u8
- * integer MMAs over the 32 byte planes of each operand (csrc/matmul_tc.cu), smaller products on the integer pipe
- * (csrc/matmul.cu).  The choice is internal; results do not depend on it. */
+ * Several engines compute the same bytes: from 64^3 on (and k >= 32) the product runs on the tensor cores as exact 8-bit
+ * integer MMAs (csrc/matmul_tc.cu) -- over 9 x 10 signed byte digits when every operand is a small signed integer in
+ * standard form (|x| < 2^70: what ZkMatrix::new's quantization produces; detected on the device), else over the 32 x 32
+ * byte planes of the full-width Montgomery representation -- smaller products on the integer pipe (csrc/matmul.cu).  The
+ * choice is internal; results do not depend on it. */
 int h2svd_fr_matmul(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *c, size_t n,
                     size_t k, size_t m, int b_transposed);
 int h2svd_fr_matmul_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *c,
@@ -108,6 +112,10 @@ int h2svd_mat_vec_prefix_pair_dev(h2svd_ctx *ctx, const h2svd_fr *a0, size_t row
                                   h2svd_fr *out_prefix0, h2svd_fr *out_totals0, const h2svd_fr *a1,
                                   size_t rows1, h2svd_fr *out_prefix1, h2svd_fr *out_totals1,
                                   const h2svd_fr *v, size_t len);
+/* Row totals only: out_totals[i] = sum_t a[i*len + t] * v[t] -- the value field_mat_vec_mul returns per row (:597) without
+ * the running-sum witnesses (lazy accumulation, one reduction per row).  Row-sharded callers use it for (b v). */
+int h2svd_mat_vec_totals_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *v, size_t rows, size_t len,
+                             h2svd_fr *out_totals);
 /* out[i] = src[i*stride + offset]  (gathers the last running sum of every row) */
 int h2svd_gather_dev(h2svd_ctx *ctx, const h2svd_fr *src, size_t count, size_t stride,
                      size_t offset, h2svd_fr *out);
@@ -190,6 +198,50 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr
                                h2svd_fr *q, h2svd_fr *wit, h2svd_fr *powers, h2svd_fr *prefix_cv,
                                h2svd_fr *prefix_bv, h2svd_fr *prefix_abv, h2svd_fr *diff, h2svd_fr *is_zero,
                                h2svd_fr *inv);
+
+/* Device-pointer form of the same sequence (what h2svd_zkmatrix_mul_witness runs per slab, and what a caller that keeps
+ * its matrices on the GPU uses): asynchronous on the handle's stream.  Internally the C-independent half of verify_mul
+ * (gamma powers :316-326, b . v :336, a . (b v) :337 -- integer-pipe work) is forked onto a side stream under the mat-mul
+ * (tensor pipe), and c_s . v (:335) + is_equal (:339-341) run next to the rescale kernel (HBM writes); the side stream is
+ * joined before the call returns to the caller's stream order.  prefix_bv receives rows [bv_row0, bv_row1) of b . v; every
+ * handle derives all k row totals itself, so row-sharded callers need no exchange step. */
+int h2svd_zkmatrix_mul_witness_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2svd_fr *b, const h2svd_fr *gamma,
+                                   size_t rows, size_t k, size_t m, int precision_bits, int lookup_bits,
+                                   int shift_bits, int a_num_bits, size_t bv_row0, size_t bv_row1, h2svd_fr *c_s,
+                                   h2svd_fr *q, h2svd_fr *wit, h2svd_fr *powers, h2svd_fr *prefix_cv,
+                                   h2svd_fr *prefix_bv, h2svd_fr *prefix_abv, h2svd_fr *diff, h2svd_fr *is_zero,
+                                   h2svd_fr *inv);
+
+/* ---- CUDA-graph capture -------------------------------------------------------------------------------------------
+ * Any sequence of *_dev calls on one handle between h2svd_graph_begin and h2svd_graph_end is recorded instead of run
+ * (cudaStreamBeginCapture on the handle's stream) and can then be replayed with ONE launch: a row slab on one of 8 GPUs
+ * is ~20 kernels of 2-70 us each, where launch gaps are a visible share of the step.  Rules: run the same calls once
+ * un-captured first (workspaces only grow outside a capture); the recorded pointers and shapes are baked in;
+ * host-pointer entry points cannot be captured.  h2svd_launch_count advances by the recorded kernel count per replay. */
+typedef struct h2svd_graph h2svd_graph;
+int h2svd_graph_begin(h2svd_ctx *ctx);
+int h2svd_graph_end(h2svd_ctx *ctx, h2svd_graph **out);
+int h2svd_graph_launch(h2svd_ctx *ctx, h2svd_graph *graph);
+void h2svd_graph_destroy(h2svd_graph *graph);
+
+/* ---- one process, several GPUs (north_star: rows of A and C shard across the GPUs of one box, B replicated) ---------
+ * h2svd_multi owns one handle per entry of devices[] (an index may repeat: two handles on one GPU exercise the same
+ * partitioning).  h2svd_multi_zkmatrix_mul_witness is h2svd_zkmatrix_mul_witness for ALL n rows: handle g gets the
+ * contiguous row range g of A / C (first n % parts ranges one row longer) and the matching range of the rows of b . v,
+ * the per-handle calls run concurrently (one host thread per GPU, each bound by its own PCIe link), results land in the
+ * caller's arrays at the right offsets.  No data-path exchange between GPUs: every handle derives (b v) itself, and
+ * field addition is exact, so the output is byte-identical to the single-GPU call.  This is what a caller of
+ * ZkMatrix::verify_mul (src/matrix/mod.rs:299) binds to use the whole box. */
+typedef struct h2svd_multi h2svd_multi;
+int h2svd_multi_create(h2svd_multi **out, const int *devices, int n_dev);
+void h2svd_multi_destroy(h2svd_multi *mh);
+int h2svd_multi_count(h2svd_multi *mh);
+h2svd_ctx *h2svd_multi_ctx(h2svd_multi *mh, int i);
+int h2svd_multi_zkmatrix_mul_witness(h2svd_multi *mh, const h2svd_fr *a, const h2svd_fr *b, const h2svd_fr *gamma,
+                                     size_t n, size_t k, size_t m, int precision_bits, int lookup_bits, int shift_bits,
+                                     int a_num_bits, h2svd_fr *c_s, h2svd_fr *q, h2svd_fr *wit, h2svd_fr *powers,
+                                     h2svd_fr *prefix_cv, h2svd_fr *prefix_bv, h2svd_fr *prefix_abv, h2svd_fr *diff,
+                                     h2svd_fr *is_zero, h2svd_fr *inv);
 
 /* Pinned (page-locked) host memory for the host-pointer entry points. */
 int h2svd_host_alloc(size_t bytes, void **out);

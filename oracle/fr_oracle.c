@@ -425,7 +425,10 @@ int orc_mat_times_diag(const orc_fr *a, const orc_fr *v, size_t rows, size_t lda
 int orc_quantize(const double *x, size_t count, int P, orc_fr *out) {
     if (P < 1 || P > 63) return -1;
     for (size_t i = 0; i < count; i++) {
-        double mag = floor(fabs(x[i]) * ldexp(1.0, P) + 0.5);
+        /* round half away from zero WITHOUT forming y + 0.5 (which ties-to-even once y >= 2^52) */
+        const double y = fabs(x[i]) * ldexp(1.0, P);
+        double mag = floor(y);
+        if (y - mag >= 0.5) mag += 1.0;
         if (!(mag < ldexp(1.0, 127))) return -2;
         u128 q = (u128)mag;
         uint64_t v[4] = {(uint64_t)q, (uint64_t)(q >> 64), 0, 0};

@@ -116,7 +116,10 @@ def mat_vec_prefix(a: Sequence[Sequence[int]], v: Sequence[int]) -> List[List[in
 def quantize(x: float, precision_bits: int) -> int:
     """FixedPointChip041::quantization (A.5; PDF Eq. 11): sign-magnitude
     round-half-up of |x|*2^P, negatives as r - q."""
-    q = int(math.floor(abs(x) * float(1 << precision_bits) + 0.5))
+    y = abs(x) * float(1 << precision_bits)      # exact: scaling by a power of two
+    q = int(math.floor(y))
+    if y - math.floor(y) >= 0.5:                  # exact: Rust's f64::round (half away from zero), no y + 0.5 tie-to-even
+        q += 1
     return q % R_MOD if x >= 0 else (R_MOD - q) % R_MOD
 
 

@@ -7,6 +7,7 @@
 #include "../../halo2-svd041_b200/csrc/fr_acc.cuh"
 #include "../../halo2-svd041_b200/csrc/fr_fast.cuh"
 #include "../../halo2-svd041_b200/csrc/fr_kara.cuh"
+#include "../../halo2-svd041_b200/csrc/tc_small.cuh"
 
 using fr::Fr;
 
@@ -28,6 +29,25 @@ void hs_add_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0;
 void hs_sub_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::sub_fast(a[i], b[i]); }
 void hs_to_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::to_mont_fast(a[i]); }
 void hs_from_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::from_mont_fast(a[i]); }
+void hs_mont_reduce_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::mont_reduce_fast(a[i]); }
+// Small-operand tensor-core engine, arithmetic only (tc_small.cuh): balanced digits of every operand, the 17 signed
+// diagonal sums a tile of s8 x s8 MMAs would leave in TMEM, signed carry, one Montgomery encode.  Returns 0 when an
+// operand is out of the small range (|x| >= 2^70), else 1.
+int hs_small_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {
+    int32_t D[2 * fr::SMALL_DIGITS - 1] = {0};
+    for (size_t i = 0; i < k; i++) {
+        uint32_t ta[3], tb[3];
+        if (!fr::small_biased(a[i], ta) || !fr::small_biased(b[i], tb)) return 0;
+        for (int p = 0; p < fr::SMALL_DIGITS; p++)
+            for (int q = 0; q < fr::SMALL_DIGITS; q++)
+                D[p + q] += (int32_t)(int8_t)fr::small_digit_bits(ta, p) * (int32_t)(int8_t)fr::small_digit_bits(tb, q);
+    }
+    uint32_t T[6];
+    fr::carry_signed<2 * fr::SMALL_DIGITS - 1>(reinterpret_cast<const uint32_t*>(D), T);
+    *o = fr::signed6_to_mont(T);
+    return 1;
+}
+int hs_small_ok(const Fr* a) { uint32_t t[3]; return fr::small_biased(*a, t) ? 1 : 0; }
 // Karatsuba lazy dot product exactly as the Karatsuba mat-mul accumulates it (fr_kara.cuh)
 void hs_kara_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {
     fr::KAcc p0, p1, p2;

@@ -162,3 +162,40 @@ def test_karatsuba_accumulator_headroom(shim):
     for k in (1, 4096, 100000):
         shim.hs_kara_repeat(P(a), P(a), k, P(o))
         assert unraw(o) == [k * (R - 1) * (R - 1) * po.MONT_RINV % R]
+
+
+def test_mont_reduce_fast_matches_bigint(shim):
+    vals = _vals()
+    a = raw_limbs(vals)
+    o = np.zeros_like(a)
+    shim.hs_mont_reduce_fast(P(a), P(o), len(vals))
+    assert unraw(o) == [po.from_mont(x) for x in vals]
+
+
+def _mont_signed(vals):
+    return raw_limbs([po.to_mont(v % R) for v in vals])
+
+
+@pytest.mark.parametrize("k", [1, 7, 64, 1024])
+def test_small_operand_engine_arithmetic(shim, k):
+    """tc_small.cuh: balanced signed byte digits -> 17 diagonal sums -> signed carry -> one Montgomery encode gives the
+    same canonical element as sum a*b over the field, incl. the extremes +-(2^70 - 1), 0, +-1 and mixed signs."""
+    rng = random.Random(k)
+    lim = (1 << 70) - 1
+    edge = [0, 1, -1, lim, -lim, 127, 128, -128, -129, 255, 256, -255, -256, (1 << 63), -(1 << 63), (1 << 64) - 1]
+    av = [rng.choice(edge) if rng.random() < 0.3 else rng.randrange(-lim, lim + 1) for _ in range(k)]
+    bv = [rng.choice(edge) if rng.random() < 0.3 else rng.randrange(-lim, lim + 1) for _ in range(k)]
+    o = np.zeros((1, 4), dtype=np.uint64)
+    assert shim.hs_small_dot(P(_mont_signed(av)), P(_mont_signed(bv)), k, P(o)) == 1
+    assert unraw(o) == [po.to_mont(sum(x * y for x, y in zip(av, bv)) % R)]
+    # worst case for the accumulators: every product +-(2^70-1)^2
+    av, bv = [lim] * k, [-lim if i % 2 else lim for i in range(k)]
+    assert shim.hs_small_dot(P(_mont_signed(av)), P(_mont_signed(bv)), k, P(o)) == 1
+    assert unraw(o) == [po.to_mont(sum(x * y for x, y in zip(av, bv)) % R)]
+
+
+def test_small_operand_range_detection(shim):
+    lim = 1 << 70
+    for v, ok in [(0, 1), (lim - 1, 1), (-(lim - 1), 1), (lim, 0), (-lim, 0), (lim + 5, 0), (R // 2, 0), (-(R // 2), 0),
+                  ((1 << 200) + 3, 0), (1 << 96, 0), (-(1 << 96), 0)]:
+        assert shim.hs_small_ok(P(_mont_signed([v]))) == ok, v

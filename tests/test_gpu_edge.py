@@ -85,6 +85,6 @@ def test_two_handles_on_two_devices_in_one_process(pkg):
         with pkg.Handle(dev) as h:
             res = h.zkmatrix_mul_witness(a, b, gamma, 63, 19)
             assert _eq(res["c_s"], want) and _eq(res["wit"], ew) and not res["diff"].any()
-            assert _eq(h.fr_matmul(a2, b2), want2) and pkg.last_matmul_engine() == "tensor"
+            assert _eq(h.fr_matmul(a2, b2), want2) and h.last_matmul_engine() == "tensor"
             x, s = random_fr(rng, 700, 300), random_fr(rng, 700, 300)
             assert _eq(h.zkvec_inner_prefix(x, s), corac.zkvec_inner_prefix(x, s))

@@ -37,20 +37,20 @@ def test_fuzz_matmul_shapes_engines_schedules(handle, pkg, seed):
         try:
             for kara in (-1, 0, 1, 3):
                 for sk in (-1, 0, 1):
-                    pkg.set_matmul_karatsuba(kara)
-                    pkg.set_matmul_streamk(sk)
+                    handle.tune("matmul_karatsuba", kara)
+                    handle.tune("matmul_streamk", sk)
                     assert _eq(handle.fr_matmul(a, b), want), (n, k, m, kara, sk)
-            pkg.set_matmul_karatsuba(-1)
-            pkg.set_matmul_streamk(-1)
-            pkg.set_matmul_tc(1)             # tensor-core engine forced, whatever the shape
+            handle.tune("matmul_karatsuba", -1)
+            handle.tune("matmul_streamk", -1)
+            handle.tune("matmul_tc", 1)             # tensor-core engine forced, whatever the shape
             assert _eq(handle.fr_matmul(a, b), want), (n, k, m, "tensor-core")
-            pkg.set_matmul_tc(-1)
+            handle.tune("matmul_tc", -1)
             bt = np.ascontiguousarray(b.transpose(1, 0, 2))
             assert _eq(handle.fr_matmul(a, bt, b_transposed=True), want), (n, k, m, "transposed")
         finally:
-            pkg.set_matmul_karatsuba(-1)
-            pkg.set_matmul_streamk(-1)
-            pkg.set_matmul_tc(-1)
+            handle.tune("matmul_karatsuba", -1)
+            handle.tune("matmul_streamk", -1)
+            handle.tune("matmul_tc", -1)
 
 
 @pytest.mark.parametrize("seed", range(4))

@@ -30,12 +30,12 @@ def test_fr_matmul_all_tile_variants(handle, pkg, variant):
     rng = np.random.default_rng(variant)
     a, b = random_fr(rng, 70, 50, ), random_fr(rng, 50, 45)
     try:
-        pkg.set_matmul_karatsuba(0)      # tile variants of the schoolbook engine
-        pkg.set_matmul_variant(variant)
+        handle.tune("matmul_karatsuba", 0)      # tile variants of the schoolbook engine
+        handle.tune("matmul_variant", variant)
         c = handle.fr_matmul(a, b)
     finally:
-        pkg.set_matmul_variant(0)
-        pkg.set_matmul_karatsuba(-1)
+        handle.tune("matmul_variant", 0)
+        handle.tune("matmul_karatsuba", -1)
     assert _eq(c, corac.field_mat_mul(a, b, threads=0))
 
 
@@ -46,14 +46,14 @@ def test_fr_matmul_streamk_schedule(handle, pkg, n, k, m):
     rng = np.random.default_rng(n * 7 + k)
     a, b = random_fr(rng, n, k), random_fr(rng, k, m)
     try:
-        pkg.set_matmul_karatsuba(0)      # schoolbook engine: this test is about the schedule
-        pkg.set_matmul_streamk(1)
+        handle.tune("matmul_karatsuba", 0)      # schoolbook engine: this test is about the schedule
+        handle.tune("matmul_streamk", 1)
         got = handle.fr_matmul(a, b)
-        pkg.set_matmul_streamk(0)
+        handle.tune("matmul_streamk", 0)
         plain = handle.fr_matmul(a, b)
     finally:
-        pkg.set_matmul_streamk(-1)
-        pkg.set_matmul_karatsuba(-1)
+        handle.tune("matmul_streamk", -1)
+        handle.tune("matmul_karatsuba", -1)
     assert _eq(got, plain)
     if n * k * m <= 1 << 22:
         assert _eq(got, corac.field_mat_mul(a, b))
@@ -74,12 +74,12 @@ def test_fr_matmul_karatsuba_engine(handle, pkg, kara, streamk, n, k, m):
     a.reshape(-1, 4)[: min(len(adv), n * k)] = adv[: n * k]
     b.reshape(-1, 4)[-min(len(adv), k * m):] = adv[: min(len(adv), k * m)]
     try:
-        pkg.set_matmul_karatsuba(kara)
-        pkg.set_matmul_streamk(streamk)
+        handle.tune("matmul_karatsuba", kara)
+        handle.tune("matmul_streamk", streamk)
         got = handle.fr_matmul(a, b)
     finally:
-        pkg.set_matmul_karatsuba(-1)
-        pkg.set_matmul_streamk(-1)
+        handle.tune("matmul_karatsuba", -1)
+        handle.tune("matmul_streamk", -1)
     assert _eq(got, corac.field_mat_mul(a, b))
 
 
@@ -95,12 +95,12 @@ def test_fr_matmul_tensor_core_engine(handle, pkg, n, k, m):
     a.reshape(-1, 4)[: min(len(adv), n * k)] = adv[: n * k]
     b.reshape(-1, 4)[-min(len(adv), k * m):] = adv[: min(len(adv), k * m)]
     try:
-        pkg.set_matmul_tc(1)
+        handle.tune("matmul_tc", 1)
         got = handle.fr_matmul(a, b)
-        pkg.set_matmul_tc(0)
+        handle.tune("matmul_tc", 0)
         imad = handle.fr_matmul(a, b)
     finally:
-        pkg.set_matmul_tc(-1)
+        handle.tune("matmul_tc", -1)
     assert _eq(got, imad)
     if n * k * m <= 1 << 22:
         assert _eq(got, corac.field_mat_mul(a, b))
@@ -113,7 +113,7 @@ def test_fr_matmul_tensor_core_worst_case_accumulation(handle, pkg):
     """Every product (r-1)^2 and every byte of one operand 0xff-heavy, k = 4096 (four accumulation passes):
     the per-diagonal sums stay below 2^31 by construction (32 * 1024 * 255^2), so this must be exact."""
     try:
-        pkg.set_matmul_tc(1)
+        handle.tune("matmul_tc", 1)
         big = np.ascontiguousarray(np.broadcast_to(raw_limbs([po.R_MOD - 1])[0], (3, 4096, 4)))
         bigt = np.ascontiguousarray(np.broadcast_to(raw_limbs([po.R_MOD - 1])[0], (4096, 5, 4)))
         c = handle.fr_matmul(big, bigt)
@@ -128,7 +128,7 @@ def test_fr_matmul_tensor_core_worst_case_accumulation(handle, pkg):
         exp = 1024 * ff * ff * po.MONT_RINV % po.R_MOD
         assert [int(v) for v in c[1, 1]] == [int(v) for v in raw_limbs([exp])[0]]
     finally:
-        pkg.set_matmul_tc(-1)
+        handle.tune("matmul_tc", -1)
 
 
 def test_fr_matmul_adversarial_operands(handle):
@@ -351,6 +351,10 @@ def test_quantize_matches_oracle(handle):
                                                         -0.5 / (1 << 32), 99.99999999, -99.99999999]])
     for P in (32, 42, 63):
         assert _eq(handle.quantize(xs, P), corac.quantize(xs, P))
+        # ties and near-ties: odd y = |x|*2^P in [2^52, 2^53), 0.49999999999999994, exact halves
+        from tests.test_oracle import quantize_tie_cases
+        ties = quantize_tie_cases(P)
+        assert _eq(handle.quantize(ties, P), corac.quantize(ties, P))
 
 
 def test_isqrt_matches_oracle(handle):
@@ -402,11 +406,11 @@ def test_fr_matmul_rescale_one_call(handle, pkg, fuse, n, k, m, P, lb):
     tw = torch.full((n * m, W, 4), -1, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
     try:
-        pkg.set_fuse_rescale(fuse)
+        handle.tune("fuse_rescale", fuse)
         handle.fr_matmul_rescale_dev(ta, tb, tc, P, lb, tq, tw)
         handle.sync()
     finally:
-        pkg.set_fuse_rescale(0)
+        handle.tune("fuse_rescale", 0)
     c = corac.field_mat_mul(a, b)
     q, _rem, wit = corac.rescale_witness(c.reshape(-1, 4), P, lb, threads=0)
     assert _eq(tc.cpu().numpy().view(np.uint64), c)

@@ -84,6 +84,34 @@ def test_quantize_and_isqrt():
     assert po.unpack_mont(corac.isqrt_fixed(po.pack_mont(vals), 32)) == [po.isqrt_fixed(x, 32) for x in vals]
 
 
+def quantize_tie_cases(P):
+    """Inputs on which floor(y + 0.5) and round-half-away-from-zero differ or nearly do: odd integers
+    y = |x| * 2^P in [2^52, 2^53) (y + 0.5 ties to even), the largest double below 0.5, exact .5 fractions."""
+    ys = [float((1 << 52) + 1), float((1 << 52) + 3), float((1 << 53) - 1), float(1 << 52), 0.49999999999999994, 0.5,
+          1.5, 2.5, 4503599627370495.5, 1.0 + 2.0 ** -52]
+    xs = []
+    for y in ys:
+        x = y * 2.0 ** -P          # exact (power of two), never subnormal for P <= 63
+        xs += [x, -x]
+    return np.array(xs)
+
+
+def test_quantize_rounds_half_away_from_zero_exactly():
+    """PDF Eq. 11 / Rust f64::round, checked against exact rational arithmetic (not against a float formula)."""
+    from fractions import Fraction
+    for P in (32, 42, 63):
+        xs = quantize_tie_cases(P)
+        want = []
+        for x in xs:
+            y = Fraction(abs(float(x))) * (1 << P)
+            q = y.numerator // y.denominator
+            if y - q >= Fraction(1, 2):
+                q += 1
+            want.append(q % po.R_MOD if x >= 0 else (po.R_MOD - q) % po.R_MOD)
+        assert [po.quantize(float(x), P) for x in xs] == want
+        assert po.unpack_mont(corac.quantize(xs, P)) == want
+
+
 def _svd_circuit(inputs, P, lb, err_size):
     fp = po.FixedPointChip(P, lb)
     ctx = po.Context()

@@ -14,11 +14,25 @@ R_LIMBS = np.array([(po.R_MOD >> (64 * i)) & po.MASK64 for i in range(4)], dtype
 
 
 def random_fr(rng: np.random.Generator, *shape) -> np.ndarray:
-    """Uniform-ish canonical field elements as raw limbs (any canonical limb pattern is a valid
-    Montgomery-form element, so no conversion is needed)."""
-    a = rng.integers(0, 1 << 64, size=shape + (4,), dtype=np.uint64)
-    a[..., 3] &= np.uint64((1 << 60) - 1)  # < 2^252 < r
-    return a
+    """Uniform canonical field elements over the WHOLE range [0, r) as raw limbs (any canonical limb pattern is a valid
+    Montgomery-form element, so no conversion is needed).  Rejection sampling below 2^254 (r ~ 0.76 * 2^254)."""
+    n = int(np.prod(shape)) if shape else 1
+    a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 62) - 1)
+    while True:
+        bad = np.zeros(n, dtype=bool)       # bad = (a >= r), compared limb by limb from the top
+        undecided = np.ones(n, dtype=bool)
+        for limb in (3, 2, 1, 0):
+            bad |= undecided & (a[:, limb] > R_LIMBS[limb])
+            undecided &= a[:, limb] == R_LIMBS[limb]
+        bad |= undecided                    # equal to r
+        nb = int(bad.sum())
+        if nb == 0:
+            break
+        fresh = rng.integers(0, 1 << 64, size=(nb, 4), dtype=np.uint64)
+        fresh[:, 3] &= np.uint64((1 << 62) - 1)
+        a[bad] = fresh
+    return a.reshape(shape + (4,))
 
 
 def adversarial_fr() -> np.ndarray:

@@ -32,7 +32,7 @@ def main():
             outs = []
             times = []
             for fuse in (0, 1):
-                pkg.set_fuse_rescale(fuse)
+                h.tune("fuse_rescale", fuse)
                 c = torch.full((n, m, 4), -1, dtype=torch.int64, device="cuda")
                 q = torch.full((n, m, 4), -1, dtype=torch.int64, device="cuda")
                 wit = torch.full((n * m, W, 4), -1, dtype=torch.int64, device="cuda")
@@ -50,10 +50,10 @@ def main():
                 times.append(min(ts))
             same = all(bool((x == y).all()) for x, y in zip(outs[0], outs[1]))
             nbad = int((outs[0][2] != outs[1][2]).any(dim=-1).sum())
-            print(f"P={P} lb={lb} W={W} {n}x{k}x{m}: same={same} bad_wit={nbad} engine={pkg.last_matmul_engine()} "
+            print(f"P={P} lb={lb} W={W} {n}x{k}x{m}: same={same} bad_wit={nbad} engine={h.last_matmul_engine()} "
                   f"separate {times[0]:.4f} ms fused {times[1]:.4f} ms", flush=True)
             del outs
-    pkg.set_fuse_rescale(0)
+    h.tune("fuse_rescale", 0)
     h.close()
 
 

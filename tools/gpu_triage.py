@@ -53,9 +53,9 @@ def main():
         a, b = rand_fr(gen, N, N), rand_fr(gen, N, N)
         c = torch.empty_like(a)
         ref = None
-        pkg.set_matmul_karatsuba(0)          # tile variants of the schoolbook engine
+        h.tune("matmul_karatsuba", 0)          # tile variants of the schoolbook engine
         for variant in (0, 1, 2, 3):
-            pkg.set_matmul_variant(variant)
+            h.tune("matmul_variant", variant)
             best, med = timeit(lambda: h.fr_matmul_dev(a, b, c), stream)
             h.sync()
             if ref is None:
@@ -65,8 +65,8 @@ def main():
             out[f"matmul_N{N}_v{variant}"] = dict(ms_best=best, ms_med=med, gmuladd_s=rate / 1e9, same_as_v0=same)
             print(f"matmul N={N} variant {variant}: best {best:.3f} ms med {med:.3f} ms -> {rate/1e9:.1f} G mul-add/s"
                   f" same={same}", flush=True)
-        pkg.set_matmul_variant(0)
-        pkg.set_matmul_karatsuba(-1)
+        h.tune("matmul_variant", 0)
+        h.tune("matmul_karatsuba", -1)
         best, med = timeit(lambda: h.fr_matmul_dev(a, b, c), stream)
         h.sync()
         out[f"matmul_N{N}_default"] = dict(ms_best=best, ms_med=med, gmuladd_s=N ** 3 / (best * 1e-3) / 1e9, same_as_v0=bool((ref == c).all()))
@@ -96,9 +96,9 @@ def main():
     out["rescale_N1024"] = dict(ms_best=best, ms_med=med, gbps=rs_bytes / (best * 1e-3) / 1e9, W=W)
     print("rescale N=1024:", out["rescale_N1024"], flush=True)
     wit_ref, q_ref = torch.empty_like(wit), torch.empty_like(q)
-    pkg.set_rescale_generic(True)
+    h.tune("rescale_generic", True)
     best, med = timeit(lambda: h.rescale_witness_dev(cs, N * N, P, lb, q_ref, wit_ref), stream, reps=2, warm=1)
-    pkg.set_rescale_generic(False)
+    h.tune("rescale_generic", False)
     h.sync()
     out["rescale_N1024_generic"] = dict(ms_best=best, same_as_staged=bool((wit_ref == wit).all() and (q_ref == q).all()))
     print("rescale generic:", out["rescale_N1024_generic"], flush=True)

@@ -23,11 +23,11 @@ for (n, k, m) in shapes:
     c = torch.empty((n, m, 4), dtype=torch.int64, device="cuda")
     ref = None
     for variant in variants:
-        pkg.set_matmul_variant(variant)
+        h.tune("matmul_variant", variant)
         modes = [("sk", 0), ("sk", 1), ("sk", -1)] + [("kara", x) for x in kara_modes]
         for kind, sk in modes:
-            pkg.set_matmul_karatsuba(sk if kind == "kara" else 0)
-            pkg.set_matmul_streamk(sk if kind == "sk" else -1)
+            h.tune("matmul_karatsuba", sk if kind == "kara" else 0)
+            h.tune("matmul_streamk", sk if kind == "sk" else -1)
             ts = []
             for i in range(7):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,5 +39,5 @@ for (n, k, m) in shapes:
             same = bool((ref == c).all())
             t = min(ts[2:])
             print(f"{n}x{k}x{m} variant {variant} {kind}={sk:2d}: {t:.4f} ms  {n*k*m/t/1e6:.1f} G mul-add/s  same={same}", flush=True)
-pkg.set_matmul_streamk(-1); pkg.set_matmul_variant(0); pkg.set_matmul_karatsuba(-1)
+h.tune("matmul_streamk", -1); h.tune("matmul_variant", 0); h.tune("matmul_karatsuba", -1)
 h.close()

@@ -47,9 +47,9 @@ def main():
     for rows, ln in shapes:
         x, s = rand_fr(gen, rows, ln), rand_fr(gen, rows, ln)
         o, o_ref = torch.empty_like(x), torch.empty_like(x)
-        pkg.set_matvec_warp_kernel(True)
+        h.tune("matvec_warp_kernel", True)
         h.zkvec_inner_prefix_dev(x, s, o_ref)
-        pkg.set_matvec_warp_kernel(False)
+        h.tune("matvec_warp_kernel", False)
         best, med = timeit(lambda: h.zkvec_inner_prefix_dev(x, s, o), stream)
         h.sync()
         same = bool((o == o_ref).all())
@@ -58,9 +58,9 @@ def main():
         # shared-vector mat-vec with row totals
         v = rand_fr(gen, ln)
         tot, tot_ref = torch.empty((rows, 4), dtype=torch.int64, device="cuda"), torch.empty((rows, 4), dtype=torch.int64, device="cuda")
-        pkg.set_matvec_warp_kernel(True)
+        h.tune("matvec_warp_kernel", True)
         h.mat_vec_prefix_dev(x, v, o_ref, tot_ref)
-        pkg.set_matvec_warp_kernel(False)
+        h.tune("matvec_warp_kernel", False)
         best, med = timeit(lambda: h.mat_vec_prefix_dev(x, v, o, tot), stream)
         h.sync()
         same = bool((o == o_ref).all() and (tot == tot_ref).all())

@@ -25,12 +25,12 @@ def main():
         a, b = rfr(rng, n, k), rfr(rng, k, m)
         for kara in (0, 3):
             for sk in (0, 1):
-                pkg.set_matmul_karatsuba(kara)
-                pkg.set_matmul_streamk(sk)
+                h.tune("matmul_karatsuba", kara)
+                h.tune("matmul_streamk", sk)
                 c = h.fr_matmul(a, b)
                 assert (c == corac.field_mat_mul(a, b)).all(), (n, k, m, kara, sk)
-        pkg.set_matmul_karatsuba(-1)
-        pkg.set_matmul_streamk(-1)
+        h.tune("matmul_karatsuba", -1)
+        h.tune("matmul_streamk", -1)
         g = rfr(rng, 1)
         fw = h.freivalds_witness(a, b, c, g)
         ew = corac.freivalds_witness(a, b, c, g)

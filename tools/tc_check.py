@@ -35,10 +35,10 @@ def main():
             b[1, 1] = 0
             a[1, :] = 0
         ref, out = torch.empty((n, m, 4), dtype=torch.int64, device="cuda"), torch.empty((n, m, 4), dtype=torch.int64, device="cuda")
-        pkg.set_matmul_tc(0)
+        h.tune("matmul_tc", 0)
         h.fr_matmul_dev(a, b, ref)
         h.sync()
-        pkg.set_matmul_tc(1)
+        h.tune("matmul_tc", 1)
         out.fill_(-1)
         h.fr_matmul_dev(a, b, out)
         h.sync()
@@ -60,12 +60,12 @@ def main():
                 ts.append(e0.elapsed_time(e1) / inner)
             return min(ts)
         best = bench()
-        pkg.set_matmul_tc(0)
+        h.tune("matmul_tc", 0)
         imad = bench()
         msg += (f"  tc {best:.4f} ms -> {n*k*m/(best*1e-3)/1e9:.1f} G mul-add/s ({2*1024*n*k*m/(best*1e-3)/1e12:.0f} T int8 op/s)"
                 f"  imad {imad:.4f} ms")
         print(msg, flush=True)
-    pkg.set_matmul_tc(0)
+    h.tune("matmul_tc", 0)
     h.close()
 
 
