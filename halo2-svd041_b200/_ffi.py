@@ -86,6 +86,7 @@ SIGNATURES = {
     "h2svd_quantize_dev": (_I, [_P, _P, _Z, _I, _P]),
     "h2svd_check_canonical_dev": (_I, [_P, _P, _Z]),
     "h2svd_microbench_imad": (_I, [_P, _I, _I, ct.POINTER(ct.c_double)]),
+    "h2svd_microbench_tensor_i8": (_I, [_P, _I, ct.c_double, ct.POINTER(ct.c_double)]),
 }
 # not part of the public header: triage helpers
 DEBUG_SIGNATURES = {

@@ -1034,6 +1034,12 @@ int h2svd_microbench_imad(h2svd_ctx* ctx, int kind, int iters, double* ops_per_s
     return launch_microbench(ctx, kind, iters, ops_per_s);
 }
 
+int h2svd_microbench_tensor_i8(h2svd_ctx* ctx, int kind, double min_seconds, double* ops_per_s) {
+    REQUIRE(ctx, "microbench_tensor_i8: null handle");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_microbench_i8(ctx, kind, min_seconds, ops_per_s);
+}
+
 /* debug / triage only (not in the public header): per-handle tuning switches and the engine of the last mat-mul */
 int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
     REQUIRE(ctx && key, "debug_tune: null argument");

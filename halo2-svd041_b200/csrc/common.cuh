@@ -156,5 +156,6 @@ int launch_isqrt(h2svd_ctx* ctx, const Fr* a, size_t count, int P, Fr* out);
 int launch_quantize(h2svd_ctx* ctx, const double* x, size_t count, int P, Fr* out);
 int launch_check_canonical(h2svd_ctx* ctx, const Fr* x, size_t count, int* d_flag);
 int launch_microbench(h2svd_ctx* ctx, int kind, int iters, double* ops_per_s);
+int launch_microbench_i8(h2svd_ctx* ctx, int kind, double min_seconds, double* ops_per_s);
 
 }  // namespace h2svd

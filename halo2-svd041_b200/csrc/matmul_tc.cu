@@ -517,6 +517,87 @@ tc_encode_fn tc_encoder() {
     return fn;
 }
 
+// ---- tensor-pipe micro-benchmark: the measured denominator of the mat-mul roofline --------------------------------
+// One CTA per SM, operands resident in shared memory (pseudo-random bytes, the layouts of the real kernel), one elected
+// thread issues back-to-back kind::i8 MMAs of the real kernel's shape (M = 128, K = 32, N = NMMA) into TMEM; batches of 32
+// instructions are committed to two alternating mbarriers so that the next batch is always queued before the previous
+// one is waited for.  Nothing else runs: this is what the pipe delivers when operand delivery and epilogues cost nothing.
+template <int NMMA, bool SIGNED>
+__global__ void __launch_bounds__(128, 1) tc_peak_kernel(int batches, int* err) {
+    extern __shared__ uint8_t tc_smem_raw[];
+    const uint32_t raw = tc_smem_u32(tc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = tc_smem_raw + (base - raw);
+    const uint32_t s_a = base, s_b = base + TC_A_BYTES, bars = s_b + NMMA * TC_BKB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars + 16 - base));
+    constexpr uint32_t IDESC = (2u << 4) | ((SIGNED ? 1u : 0u) << 7) | ((SIGNED ? 1u : 0u) << 10) |
+                               ((uint32_t)(NMMA >> 3) << 17) | ((128u >> 4) << 24);
+    for (uint32_t i = threadIdx.x; i < (TC_A_BYTES + NMMA * TC_BKB) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+    if (threadIdx.x == 0) {
+        tc_mbar_init(bars, 1);
+        tc_mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    if (threadIdx.x == 0) {
+        const uint64_t adesc = tc_smem_desc(s_a), bdesc = tc_smem_desc(s_b);
+        for (int b = 0; b < batches; b++) {
+            if (b >= 2) tc_mbar_wait(bars + 8 * (b & 1), ((b >> 1) - 1) & 1, err);   // batch b-2 has drained
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                tc_mma_i8(tmem_base + (uint32_t)(i & 1) * (512 - NMMA), adesc + 2u * (i & 3), bdesc + 2u * (i & 3), IDESC, 1u);
+            tc_commit(bars + 8 * (b & 1));
+        }
+        for (int b = batches > 2 ? batches - 2 : 0; b < batches; b++) tc_mbar_wait(bars + 8 * (b & 1), (b >> 1) & 1, err);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+template <int NMMA, bool SIGNED>
+int tc_peak_run(h2svd_ctx* ctx, double min_seconds, double* ops_per_s) {
+    const size_t smem = TC_A_BYTES + (size_t)NMMA * TC_BKB + 1024 + 64;
+    H2SVD_SET_SMEM(ctx, (tc_peak_kernel<NMMA, SIGNED>), smem);
+    const int batches = 2048;   // 65536 MMAs per CTA: ~4 ms at N = 256
+    cudaEvent_t e0, e1;
+    H2SVD_CUDA(cudaEventCreate(&e0));
+    H2SVD_CUDA(cudaEventCreate(&e1));
+    tc_peak_kernel<NMMA, SIGNED><<<ctx->sm_count, 128, smem, ctx->stream>>>(batches, ctx->d_flag);   // warm-up
+    H2SVD_LAUNCH_CHECK(ctx);
+    double best = 0, total_ms = 0;
+    long launches = 0;
+    do {
+        H2SVD_CUDA(cudaEventRecord(e0, ctx->stream));
+        tc_peak_kernel<NMMA, SIGNED><<<ctx->sm_count, 128, smem, ctx->stream>>>(batches, ctx->d_flag);
+        H2SVD_LAUNCH_CHECK(ctx);
+        H2SVD_CUDA(cudaEventRecord(e1, ctx->stream));
+        H2SVD_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        H2SVD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = 2.0 * 128 * NMMA * 32 * 32.0 * batches * ctx->sm_count / (ms * 1e-3);
+        if (min_seconds <= 0 && rate > best) best = rate;
+        total_ms += ms;
+        launches++;
+    } while (min_seconds > 0 ? total_ms < min_seconds * 1e3 : launches < 3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // burst: best single launch; sustained: everything issued over >= min_seconds, back to back
+    *ops_per_s = min_seconds > 0 ? 2.0 * 128 * NMMA * 32 * 32.0 * batches * ctx->sm_count * launches / (total_ms * 1e-3) : best;
+    return H2SVD_OK;
+}
+
 size_t tc_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // split kernels + mat-mul kernel of ONE engine on pre-carved plane buffers
@@ -590,6 +671,15 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
 }
 
 }  // namespace
+
+int launch_microbench_i8(h2svd_ctx* ctx, int kind, double min_seconds, double* ops_per_s) {
+    if (!ops_per_s || kind < 0 || kind > 1) {
+        set_error("microbench_tensor_i8: bad arguments");
+        return H2SVD_EINVAL;
+    }
+    return kind == 0 ? tc_peak_run<TcD<TcFull>::NMMA, false>(ctx, min_seconds, ops_per_s)
+                     : tc_peak_run<TcD<TcSmall>::NMMA, true>(ctx, min_seconds, ops_per_s);
+}
 
 bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
     // p * n + ib * 128 and the plane sizes are 32-bit TMA coordinates / comfortably below 2^31

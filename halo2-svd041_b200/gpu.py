@@ -267,6 +267,11 @@ class Handle:
         _ffi.check(self._lib.h2svd_microbench_imad(self._h, kind, iters, ct.byref(v)))
         return v.value
 
+    def microbench_tensor_i8(self, kind: int = 0, min_seconds: float = 0.0) -> float:
+        v = ct.c_double()
+        _ffi.check(self._lib.h2svd_microbench_tensor_i8(self._h, kind, float(min_seconds), ct.byref(v)))
+        return v.value
+
     # ---- device-pointer entry points (torch CUDA tensors, int64[..., 4]) ----
     @staticmethod
     def _tp(t) -> ct.c_void_p:

@@ -1,10 +1,16 @@
 """The hot path as one "step": honest_prover_mat_mul -> rescale_matrix -> verify_mul witnesses for
-one (A, B) pair, row-sharded over `world` GPUs (one process per GPU).
+one (A, B) pair, row-sharded over `world` GPUs (one process per GPU), spelled out in building-block calls.
 
 Sharding: rank g owns rows [r0, r1) of A and of C (mat-mul, rescale, C.v and A.(Bv)
-witnesses are row-local); B is replicated; the k rows of B are split for the B.v running sums and the
-k row totals (B v) are exchanged with ONE all-gather (NCCL over NVLink) -- the only collective on the
-path.  Field addition is exact, so the sharded witnesses are byte-identical to the single-GPU ones.
+witnesses are row-local); B is replicated; the k rows of B are split for the B.v running-sum witnesses.
+Every rank needs all k row totals (B v) as the second operand of A.(Bv); two ways to get them:
+  exchange="redundant" (default, what h2svd_zkmatrix_mul_witness[_dev] and bench.py do): every rank
+      recomputes the totals itself (h2svd_mat_vec_totals_dev: lazily accumulated, no running sums) --
+      NO collective on the data path; measured in round 1, the all-gather below cost a 66 us tail at 8 ranks;
+  exchange="allgather": the totals of the local rows are exchanged with ONE all-gather (NCCL over NVLink).
+Field addition is exact, so either way the sharded witnesses are byte-identical to the single-GPU ones.
+The C library's own h2svd_zkmatrix_mul_witness_dev runs the same schedule inside one call (and is what
+bench.py records into a CUDA graph); this module is the readable, testable statement of the sharding.
 
 `backend` is any object with the `*_dev` methods of gpu.Handle (the tests inject a CPU stand-in to
 cover the sharding logic under gloo); `comm` is a torch.distributed process group or None.
@@ -106,14 +112,17 @@ def step_rescale(backend, plan: ShardPlan, bufs: StepBuffers, precision_bits: in
                                 bufs.wit_slab)
 
 
-def _bv_running_sums(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None):
+def _bv_running_sums(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None, exchange: str = "redundant"):
     """gamma powers (reference src/matrix/mod.rs:316-326), the B.v running sums of this rank's rows of B (:336) and
-    the one exchange step, the all-gather of the k row totals.  Returns the tensor holding (B v)."""
+    the k row totals (B v): recomputed on every rank, or all-gathered.  Returns the tensor holding (B v)."""
     b0, b1 = plan.brows
     brows = b1 - b0
     backend.gamma_powers_dev(bufs.gamma, plan.m, bufs.powers)
     if brows > 0:
         backend.mat_vec_prefix_dev(bufs.b[b0:b1], bufs.powers, bufs.prefix_bv[:brows], bufs.bv_local[:brows])
+    if plan.world > 1 and exchange == "redundant":
+        backend.mat_vec_totals_dev(bufs.b, bufs.powers, bufs.bv)                      # all k totals, no exchange step
+        return bufs.bv
     if plan.world > 1:
         dist.all_gather_into_tensor(bufs.bv_all, bufs.bv_local, group=comm)          # the one exchange step
         if bufs.bv_index is not None:
@@ -134,11 +143,11 @@ def step_matmul_rescale(backend, plan: ShardPlan, bufs: StepBuffers, precision_b
     fused(bufs.a_slab, bufs.b, bufs.c_slab, precision_bits, lookup_bits, bufs.q_slab, bufs.wit_slab)
 
 
-def step_freivalds_pre(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None):
+def step_freivalds_pre(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None, exchange: str = "redundant"):
     """The part of ZkMatrix::verify_mul (:299) that does not need C: gamma powers (:316-326), the B.v
     running sums of this rank's rows of B (:336), the one exchange step (the all-gather of the k row
     totals) and A.(Bv) for this rank's rows (:337).  Returns the tensor holding (B v)."""
-    bv = _bv_running_sums(backend, plan, bufs, dist, comm)
+    bv = _bv_running_sums(backend, plan, bufs, dist, comm, exchange)
     backend.mat_vec_prefix_dev(bufs.a_slab, bv, bufs.prefix_abv, bufs.abv)
     return bv
 
@@ -170,20 +179,20 @@ class SideStream:
         self.main.wait_event(self.ev_join)
 
 
-def step_freivalds(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None) -> None:
-    """ZkMatrix::verify_mul (:299) witnesses, row-sharded, one all-gather of (B v)."""
-    bv = step_freivalds_pre(backend, plan, bufs, dist, comm)
+def step_freivalds(backend, plan: ShardPlan, bufs: StepBuffers, dist=None, comm=None, exchange: str = "redundant") -> None:
+    """ZkMatrix::verify_mul (:299) witnesses, row-sharded."""
+    bv = step_freivalds_pre(backend, plan, bufs, dist, comm, exchange)
     step_freivalds_post(backend, plan, bufs, bv)
 
 
 def run_step(backend, plan: ShardPlan, bufs: StepBuffers, precision_bits: int, lookup_bits: int, dist=None,
-             comm=None, side: Optional[SideStream] = None) -> None:
+             comm=None, side: Optional[SideStream] = None, exchange: str = "redundant") -> None:
     if side is None:
         step_matmul(backend, plan, bufs)
         step_rescale(backend, plan, bufs, precision_bits, lookup_bits)
-        step_freivalds(backend, plan, bufs, dist, comm)
+        step_freivalds(backend, plan, bufs, dist, comm, exchange)
         return
-    bv = side.run(lambda be: step_freivalds_pre(be, plan, bufs, dist, comm))
+    bv = side.run(lambda be: step_freivalds_pre(be, plan, bufs, dist, comm, exchange))
     step_matmul(backend, plan, bufs)
     side.run(lambda be: step_freivalds_post(be, plan, bufs, bv))   # stream order on the side stream: after the pre part
     step_rescale(backend, plan, bufs, precision_bits, lookup_bits)

@@ -1,7 +1,7 @@
 """Row-sharded hot path (halo2-svd041_b200/workload.py) at world_size 2 on CPU: two processes, gloo backend,
 the `*_dev` backend replaced by a stand-in that computes values with the C oracle on CPU tensors.  Checks
 that the sharded witnesses, gathered, are byte-identical to the single-rank ones (field addition is exact;
-the only exchange is the all-gather of the k row totals of B.v), including uneven splits (n, k not divisible
+the k row totals of B.v are either recomputed on every rank -- the default, no collective -- or all-gathered), including uneven splits (n, k not divisible
 by the world size, which exercises the padded all-gather + compaction)."""
 import importlib
 import os
@@ -49,6 +49,9 @@ class OracleBackend:
         if totals is not None:
             _put(totals, pre[:, -1])
 
+    def mat_vec_totals_dev(self, a, v, totals):
+        _put(totals, corac.mat_vec_prefix(_np(a), _np(v)[: a.shape[1]])[:, -1])
+
     def mat_vec_prefix_pair_dev(self, a0, out0, tot0, a1, out1, tot1, v):
         self.mat_vec_prefix_dev(a0, v, out0, tot0)
         self.mat_vec_prefix_dev(a1, v, out1, tot1)
@@ -69,7 +72,7 @@ def _inputs(n, k, m, P):
     return a, b, gamma
 
 
-def _run_rank(rank, world, port, n, k, m, P, lb, outdir):
+def _run_rank(rank, world, port, n, k, m, P, lb, outdir, exchange="redundant"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     comm = None
     if world > 1:
@@ -83,7 +86,7 @@ def _run_rank(rank, world, port, n, k, m, P, lb, outdir):
     _put(bufs.a_slab, a[r0:r1])
     _put(bufs.b, b)
     _put(bufs.gamma, gamma)
-    wl.run_step(OracleBackend(), plan, bufs, P, lb, dist if world > 1 else None, comm)
+    wl.run_step(OracleBackend(), plan, bufs, P, lb, dist if world > 1 else None, comm, exchange=exchange)
     b0, b1 = plan.brows
     np.savez(os.path.join(outdir, f"rank{rank}of{world}.npz"), c=_np(bufs.c_slab), q=_np(bufs.q_slab), wit=_np(bufs.wit_slab),
              powers=_np(bufs.powers), pcv=_np(bufs.prefix_cv), pbv=_np(bufs.prefix_bv)[: b1 - b0], pabv=_np(bufs.prefix_abv),
@@ -99,12 +102,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("exchange", ["redundant", "allgather"])
 @pytest.mark.parametrize("n,k,m", [(10, 7, 9), (8, 8, 8)])
-def test_row_sharded_step_matches_single_rank_and_oracle(tmp_path, n, k, m):
+def test_row_sharded_step_matches_single_rank_and_oracle(tmp_path, n, k, m, exchange):
     P, lb = 42, 19
     outdir = str(tmp_path)
     _run_rank(0, 1, _free_port(), n, k, m, P, lb, outdir)                       # single rank, in-process
-    mp.spawn(_run_rank, args=(2, _free_port(), n, k, m, P, lb, outdir), nprocs=2, join=True)   # world_size 2, gloo
+    mp.spawn(_run_rank, args=(2, _free_port(), n, k, m, P, lb, outdir, exchange), nprocs=2, join=True)   # world_size 2, gloo
     one = np.load(os.path.join(outdir, "rank0of1.npz"))
     two = [np.load(os.path.join(outdir, f"rank{r}of2.npz")) for r in range(2)]
     for key in ("c", "q", "wit", "pcv", "pbv", "pabv", "diff", "is_zero", "inv"):
