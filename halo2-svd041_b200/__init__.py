@@ -7,6 +7,8 @@ Importing the package does NOT load the CUDA library (so CPU-only tooling can in
 """
 from . import _ffi  # noqa: F401
 from ._ffi import H2svdError  # noqa: F401
-from .gpu import Graph, Handle, MultiHandle, PinnedBuffer  # noqa: F401
+from .gpu import (CellsLayout, Graph, Handle, MultiHandle, PinnedBuffer, expand_gamma_power_cells,  # noqa: F401
+                  expand_inner_product_cells, expand_is_equal_cells)
 
-__all__ = ["Handle", "MultiHandle", "Graph", "PinnedBuffer", "H2svdError"]
+__all__ = ["Handle", "MultiHandle", "Graph", "PinnedBuffer", "H2svdError", "CellsLayout", "expand_inner_product_cells",
+           "expand_gamma_power_cells", "expand_is_equal_cells"]

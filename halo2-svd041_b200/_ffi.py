@@ -85,6 +85,15 @@ SIGNATURES = {
     "h2svd_quantize": (_I, [_P, _P, _Z, _I, _P]),
     "h2svd_quantize_dev": (_I, [_P, _P, _Z, _I, _P]),
     "h2svd_check_canonical_dev": (_I, [_P, _P, _Z]),
+    "h2svd_rescale_cells_layout": (_I, [_I, _I, _I, _I, ct.POINTER(_P)]),
+    "h2svd_abs_less_than_cells_layout": (_I, [_P, _I, _I, ct.POINTER(_P)]),
+    "h2svd_range_check_cells_layout": (_I, [_I, _I, ct.POINTER(_P)]),
+    "h2svd_is_equal_cells_layout": (_I, [ct.POINTER(_P)]),
+    "h2svd_cells_layout_destroy": (None, [_P]),
+    "h2svd_expand_cells": (_I, [_P, _P, _P, _Z, _P, _I]),
+    "h2svd_expand_inner_product_cells": (_I, [_P, _P, _Z, _P, _Z, _Z, _P, _I]),
+    "h2svd_expand_gamma_power_cells": (_I, [_P, _P, _Z, _P]),
+    "h2svd_expand_is_equal_cells": (_I, [_P, _P, _P, _P, _P, _Z, _P]),
     "h2svd_microbench_imad": (_I, [_P, _I, _I, ct.POINTER(ct.c_double)]),
     "h2svd_microbench_tensor_i8": (_I, [_P, _I, ct.c_double, ct.POINTER(ct.c_double)]),
 }

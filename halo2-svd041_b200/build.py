@@ -15,7 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libh2svd_b200.so")
-SOURCES = ["api.cu", "matmul.cu", "matmul_tc.cu", "freivalds.cu", "rescale.cu", "zkvec.cu", "microbench.cu"]
+# one list for every build of the library: this script and rust/h2svd-b200/build.rs both read csrc/SOURCES.txt
+with open(os.path.join(CSRC, "SOURCES.txt")) as _fh:
+    SOURCES = [ln.strip() for ln in _fh if ln.strip() and not ln.startswith("#")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

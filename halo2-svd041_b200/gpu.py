@@ -467,3 +467,96 @@ class MultiHandle:
             *[_np_ptr(res[key]) for key in ("c_s", "q", "wit", "powers", "prefix_cv", "prefix_bv", "prefix_abv", "diff",
                                             "is_zero", "inv")]))
         return res
+
+
+# ---- bulk hand-off: cell layouts + value expansion (host functions of the library, no GPU) ----
+class _LayoutStruct(ct.Structure):
+    _fields_ = [("cells", ct.c_uint32), ("witnesses", ct.c_uint32), ("inputs", ct.c_uint32), ("n_gates", ct.c_uint32),
+                ("n_lookups", ct.c_uint32), ("n_copies", ct.c_uint32), ("n_constants", ct.c_uint32),
+                ("kind", ct.POINTER(ct.c_uint8)), ("source", ct.POINTER(ct.c_int32)), ("gates", ct.POINTER(ct.c_uint32)),
+                ("lookups", ct.POINTER(ct.c_int32)), ("copies", ct.POINTER(ct.c_int32)), ("constants", ct.c_void_p)]
+
+
+class CellsLayout:
+    """h2svd_cells_layout: the static advice-cell structure of ONE unit of an operation (kinds, sources, gate offsets,
+    lookup cells, constrain_equal pairs, constants) + expand(): the values of all units in assignment order."""
+    WITNESS, CONSTANT, EXISTING = 0, 1, 2
+
+    def __init__(self, ptr) -> None:
+        self._lib = _ffi.load()
+        self._ptr = ptr
+        s = ct.cast(ptr, ct.POINTER(_LayoutStruct)).contents
+        self.cells, self.witnesses, self.inputs = s.cells, s.witnesses, s.inputs
+        self.kind = [s.kind[i] for i in range(s.cells)]
+        self.source = [s.source[i] for i in range(s.cells)]
+        self.gates = [s.gates[i] for i in range(s.n_gates)]
+        self.lookups = [s.lookups[i] for i in range(s.n_lookups)]
+        self.copies = [(s.copies[2 * i], s.copies[2 * i + 1]) for i in range(s.n_copies)]
+        buf = (ct.c_uint64 * (4 * s.n_constants)).from_address(s.constants) if s.n_constants else []
+        self.constants = np.array(list(buf), dtype=np.uint64).reshape(-1, 4)
+
+    @classmethod
+    def _make(cls, fn, *args) -> "CellsLayout":
+        p = ct.c_void_p()
+        _ffi.check(fn(*args, ct.byref(p)))
+        return cls(p)
+
+    @classmethod
+    def rescale(cls, precision_bits: int, lookup_bits: int, shift_bits: int = -1, a_num_bits: int = -1) -> "CellsLayout":
+        return cls._make(_ffi.load().h2svd_rescale_cells_layout, precision_bits, lookup_bits, shift_bits, a_num_bits)
+
+    @classmethod
+    def abs_less_than(cls, bnd: int, lookup_bits: int, with_diff: bool) -> "CellsLayout":
+        b = Handle._bnd_limbs(bnd)
+        return cls._make(_ffi.load().h2svd_abs_less_than_cells_layout, _np_ptr(b), lookup_bits, int(with_diff))
+
+    @classmethod
+    def range_check(cls, range_bits: int, lookup_bits: int) -> "CellsLayout":
+        return cls._make(_ffi.load().h2svd_range_check_cells_layout, range_bits, lookup_bits)
+
+    @classmethod
+    def is_equal(cls) -> "CellsLayout":
+        return cls._make(_ffi.load().h2svd_is_equal_cells_layout)
+
+    def expand(self, inputs: Optional[np.ndarray], wit: Optional[np.ndarray], units: int, threads: int = 0) -> np.ndarray:
+        out = _np_fr(units, self.cells)
+        null = ct.c_void_p(0)
+        _ffi.check(self._lib.h2svd_expand_cells(self._ptr, _np_ptr(inputs) if inputs is not None else null,
+                                               _np_ptr(wit) if wit is not None else null, units, _np_ptr(out), threads))
+        return out
+
+    def close(self) -> None:
+        if self._ptr:
+            self._lib.h2svd_cells_layout_destroy(self._ptr)
+            self._ptr = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def expand_inner_product_cells(a: np.ndarray, v: np.ndarray, prefix: np.ndarray, per_row_v: bool = False,
+                               threads: int = 0) -> np.ndarray:
+    rows, ln = _fr_shape(a, 2)
+    out = _np_fr(rows, 1 + 3 * ln)
+    _ffi.check(_ffi.load().h2svd_expand_inner_product_cells(_np_ptr(a), _np_ptr(v), ln if per_row_v else 0, _np_ptr(prefix),
+                                                           rows, ln, _np_ptr(out), threads))
+    return out
+
+
+def expand_gamma_power_cells(gamma: np.ndarray, powers: np.ndarray) -> np.ndarray:
+    m = powers.shape[0]
+    out = _np_fr(1 + 4 * (m - 1))
+    g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
+    _ffi.check(_ffi.load().h2svd_expand_gamma_power_cells(_np_ptr(g), _np_ptr(powers), m, _np_ptr(out)))
+    return out
+
+
+def expand_is_equal_cells(x: np.ndarray, y: np.ndarray, diff: np.ndarray, is_zero: np.ndarray, inv: np.ndarray) -> np.ndarray:
+    n = x.shape[0]
+    out = _np_fr(n, 12)
+    _ffi.check(_ffi.load().h2svd_expand_is_equal_cells(_np_ptr(x), _np_ptr(y), _np_ptr(diff), _np_ptr(is_zero), _np_ptr(inv),
+                                                      n, _np_ptr(out)))
+    return out

@@ -278,6 +278,55 @@ int h2svd_quantize(h2svd_ctx *ctx, const double *x, size_t count, int precision_
 int h2svd_quantize_dev(h2svd_ctx *ctx, const double *x, size_t count, int precision_bits,
                        h2svd_fr *out);
 
+/* ---- bulk hand-off of the witnesses into halo2-base ---------------------------------------------------
+ * The reference assigns ~100 advice cells per rescaled element one ctx.assign_region at a time (src/matrix/mod.rs:364-373
+ * -> signed_div_scale -> RangeChip), and the proving backend then walks the Context's advice vector
+ * (src/utils/executor.rs:100,116).  Every unit (element / row) of one operation has the same cell structure, so:
+ *   h2svd_*_cells_layout     the static structure of ONE unit: per cell its kind and where its value comes from, the
+ *                            offsets with the gate selector on, the cells pushed to the lookup table (in push order), the
+ *                            extra constrain_equal pairs, the constants.  Offsets >= 0 are cells of the unit,
+ *                            -1 - i is the unit's i-th input cell (an AssignedValue the caller already holds).
+ *   h2svd_expand_cells       the VALUES of all units in assignment order, out_values[u * cells + c], produced from the
+ *                            Witness-only array of the matching h2svd_*_witness call (and the inputs) in one pass of
+ *                            32-byte copies on `threads` host threads (0 = all).
+ * A binding appends out_values to Context::advice with one extend and replays the layout per unit for selectors, lookups
+ * and copy constraints.  Host functions: no GPU, no handle. */
+enum { H2SVD_CELL_WITNESS = 0, H2SVD_CELL_CONSTANT = 1, H2SVD_CELL_EXISTING = 2 };
+typedef struct h2svd_cells_layout {
+    uint32_t cells;        /* advice cells per unit */
+    uint32_t witnesses;    /* Witness values per unit == W of the matching h2svd_*_witness call */
+    uint32_t inputs;       /* input cells per unit */
+    uint32_t n_gates, n_lookups, n_copies, n_constants;
+    const uint8_t *kind;          /* [cells] H2SVD_CELL_* */
+    const int32_t *source;        /* [cells] Witness: index into the unit's witness stripe; Constant: index into constants;
+                                     Existing: cell of the unit (>= 0, always earlier) or input (-1 - i) */
+    const uint32_t *gates;        /* [n_gates] offsets q with the vertical gate a + b*c - d == 0 on cells q .. q+3 */
+    const int32_t *lookups;       /* [n_lookups] cells constrained to [0, 2^lookup_bits), in push order */
+    const int32_t *copies;        /* [2 * n_copies] constrain_equal(a, b) pairs beyond those implied by Existing cells */
+    const h2svd_fr *constants;    /* [n_constants] */
+} h2svd_cells_layout;
+/* FixedPointChip041::signed_div_scale per element (rescale_matrix :354-375, inner_product :104); input 0 = the element */
+int h2svd_rescale_cells_layout(int precision_bits, int lookup_bits, int shift_bits, int a_num_bits,
+                               h2svd_cells_layout **out);
+/* check_abs_less_than(x [- y], bnd) (:425-459); input 0 = x, input 1 = y when with_diff */
+int h2svd_abs_less_than_cells_layout(const uint64_t bnd[4], int lookup_bits, int with_diff, h2svd_cells_layout **out);
+/* RangeChip::range_check(x, range_bits) (:185-216); input 0 = x */
+int h2svd_range_check_cells_layout(int range_bits, int lookup_bits, h2svd_cells_layout **out);
+/* gate.is_equal(a, b) of verify_mul (:339-341); inputs a, b; witness stripe diff, is_zero, inv */
+int h2svd_is_equal_cells_layout(h2svd_cells_layout **out);
+void h2svd_cells_layout_destroy(h2svd_cells_layout *layout);
+int h2svd_expand_cells(const h2svd_cells_layout *layout, const h2svd_fr *inputs, const h2svd_fr *wit, size_t units,
+                       h2svd_fr *out_values, int threads);
+/* field_mat_vec_mul rows (:574-599): [0, a_0, v_0, s_0, a_1, v_1, s_1, ...], 1 + 3*len cells per row, gates at 3*j;
+ * v_row_stride = 0 for one shared vector, len for a vector per row (ZkVector::inner_product, u = x, v = self). */
+int h2svd_expand_inner_product_cells(const h2svd_fr *a, const h2svd_fr *v, size_t v_row_stride, const h2svd_fr *prefix,
+                                     size_t rows, size_t len, h2svd_fr *out_values, int threads);
+/* the challenge powers of verify_mul (:316-326): [one] + (m-1) x [0, v_{i-1}, gamma, v_i]; 1 + 4*(m-1) cells */
+int h2svd_expand_gamma_power_cells(const h2svd_fr *gamma, const h2svd_fr *powers, size_t m, h2svd_fr *out_values);
+/* gate.is_equal per row from the separate arrays of h2svd_freivalds_witness: 12 cells per row */
+int h2svd_expand_is_equal_cells(const h2svd_fr *x, const h2svd_fr *y, const h2svd_fr *diff, const h2svd_fr *is_zero,
+                                const h2svd_fr *inv, size_t count, h2svd_fr *out_values);
+
 /* ---- input validation ----------------------------------------------------------------------------------------
  * Returns H2SVD_OK if all `count` device-resident elements are canonical (< r), else H2SVD_ERANGE. */
 int h2svd_check_canonical_dev(h2svd_ctx *ctx, const h2svd_fr *x, size_t count);
