@@ -102,6 +102,7 @@ DEBUG_SIGNATURES = {
     "h2svd_debug_fr_matmul_naive_dev": (_I, [_P, _P, _P, _P, _Z, _Z, _Z]),
     "h2svd_debug_tune": (_I, [_P, ct.c_char_p, _I]),          # per-handle tuning switches
     "h2svd_debug_last_matmul_engine": (_I, [_P]),
+    "h2svd_debug_matmul_timeline": (_I, [_P, _I, _P]),
 }
 
 _LIB = None

@@ -203,6 +203,7 @@ void h2svd_destroy(h2svd_ctx* ctx) {
     if (ctx->sk_ws) cudaFree(ctx->sk_ws);
     if (ctx->kara_ws) cudaFree(ctx->kara_ws);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->d_timeline) cudaFree(ctx->d_timeline);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1048,6 +1049,7 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
         {"matmul_karatsuba", &ctx->tune.kara},     {"matmul_streamk", &ctx->tune.streamk},
         {"matmul_variant", &ctx->tune.variant},    {"fuse_rescale", &ctx->tune.fuse_rescale},
         {"rescale_generic", &ctx->tune.rescale_generic}, {"matvec_warp_kernel", &ctx->tune.matvec_warp},
+        {"matvec_seg", &ctx->tune.matvec_seg},
     };
     for (const auto& e : keys)
         if (strcmp(e.name, key) == 0) {
@@ -1057,6 +1059,23 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
     set_error("debug_tune: unknown key '%s'", key);
     return H2SVD_EINVAL;
 }
+/* enable != 0: allocate (and zero) the 128-slot timeline the tensor-core mat-mul kernels stamp; out (may be null): copy it
+ * to the host after synchronising.  enable == 0: switch it off again. */
+int h2svd_debug_matmul_timeline(h2svd_ctx* ctx, int enable, unsigned long long* out) {
+    REQUIRE(ctx, "debug_matmul_timeline: null handle");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    H2SVD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out && ctx->d_timeline) H2SVD_CUDA(cudaMemcpy(out, ctx->d_timeline, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (enable) {
+        if (!ctx->d_timeline) H2SVD_CUDA(cudaMalloc((void**)&ctx->d_timeline, 128 * sizeof(unsigned long long)));
+        H2SVD_CUDA(cudaMemset(ctx->d_timeline, 0, 128 * sizeof(unsigned long long)));
+    } else if (ctx->d_timeline) {
+        cudaFree(ctx->d_timeline);
+        ctx->d_timeline = nullptr;
+    }
+    return H2SVD_OK;
+}
+
 int h2svd_debug_last_matmul_engine(h2svd_ctx* ctx) {
     if (!ctx) return -1;
     if (ctx->last_engine != 3) return ctx->last_engine;

@@ -29,6 +29,7 @@ struct h2svd_ctx {
     int* d_flag = nullptr;  // device flag for validation kernels
     int* d_mode = nullptr;  // device flag of the tensor-core mat-mul: 0 = small-operand engine, 1 = full-width engine (d_flag + 1)
     uint64_t launches = 0;
+    unsigned long long* d_timeline = nullptr;  // triage: phase timestamps of the tensor-core mat-mul (h2svd_debug_matmul_timeline)
     // Triage / tuning switches (h2svd_debug_tune).  Per handle: two handles on two streams never see each other's settings.
     struct Tuning {
         int matmul_tc = -1;       // tensor-core mat-mul engines: -1 auto, 0 never, 1 always
@@ -39,6 +40,7 @@ struct h2svd_ctx {
         int fuse_rescale = 0;     // 1: rescale witnesses from the tensor-core epilogue (experimental)
         int rescale_generic = 0;  // 1: force the generic (unstaged) rescale kernel
         int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel
+        int matvec_seg = -1;      // several-warps-per-row mat-vec prefix kernel: -1 auto (few long rows), 0 never, 1 always
     } tune;
     int last_engine = -1;         // engine of the last mat-mul launch: 0 schoolbook, 1 Karatsuba, 2 tensor core, 3 small-operand
 };

@@ -259,6 +259,87 @@ mat_vec_prefix_tile_kernel(const __grid_constant__ MvJobs jobs, const Fr* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Few-rows version of the tile kernel (the Freivalds mat-vecs of one N = 1024 product, or a 128-row slab of it: 1024 /
+// 128 rows leave one-warp-per-row with 7 / 1 warps per SM -- measured 10.7 % warps active, 33 % issue active).  A CTA of
+// SEGS warps takes ONE row: warp w owns the 128-element tiles w, w + SEGS, ... of it and computes their products and
+// tile-local running sums exactly like the tile kernel; the SEGS tile totals of a round meet in shared memory (one
+// __syncthreads per round, double-buffered by round parity), every warp adds the totals of the tiles before its own to
+// its lane offsets, and the second, coalesced pass stores.  Same arithmetic per element, SEGS times the parallelism.
+template <int SEGS>
+__global__ void __launch_bounds__(SEGS * 32)
+mat_vec_prefix_seg_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len, size_t v_row_stride) {
+    extern __shared__ __align__(128) uint4 mt_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint4* sa = mt_smem + (size_t)w * MT_WARP_U4;
+    uint4* sv = sa + MT_SEG_U4;
+    Fr* soff = reinterpret_cast<Fr*>(sv + MT_SEG_U4);
+    Fr* stot = reinterpret_cast<Fr*>(mt_smem + (size_t)SEGS * MT_WARP_U4);   // [2][SEGS] tile totals
+    size_t total_rows = 0;
+#pragma unroll
+    for (int q = 0; q < MV_MAX_JOBS; q++) total_rows += q < jobs.njobs ? jobs.job[q].rows : 0;
+    const size_t rounds = (len + (size_t)SEGS * MT_SEG - 1) / ((size_t)SEGS * MT_SEG);
+
+    for (size_t grow = blockIdx.x; grow < total_rows; grow += gridDim.x) {   // CTA-uniform: barriers inside are safe
+        size_t row = grow;
+        int jq = 0;
+        if (jobs.njobs > 1 && row >= jobs.job[0].rows) {
+            row -= jobs.job[0].rows;
+            jq = 1;
+        }
+        const Fr* a = jobs.job[jq].a + row * len;
+        Fr* out = jobs.job[jq].out + row * len;
+        const Fr* vr = v + row * v_row_stride;
+        Fr carry = fr::zero();  // sum of all tiles of the previous rounds (identical in every warp)
+        for (size_t rd = 0; rd < rounds; rd++) {
+            const size_t t0 = (rd * SEGS + w) * (size_t)MT_SEG;
+            const int nseg = t0 >= len ? 0 : (int)(len - t0 < (size_t)MT_SEG ? len - t0 : (size_t)MT_SEG);   // warp-uniform
+            Fr incl = fr::zero(), off = fr::zero();
+            if (nseg > 0) {
+                mt_stage(sa, a + t0, nseg, lane);
+                mt_stage(sv, vr + t0, nseg, lane);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                Fr run = fr::zero();
+#pragma unroll
+                for (int i = 0; i < MT_EPL; i++) {
+                    const int e = MT_EPL * lane + i;
+                    if (e < nseg) {
+                        run = fr::add_fast(run, fr::mont_mul_fast(mt_ld(sa, e), mt_ld(sv, e)));
+                        mt_st(sa, e, run);
+                    }
+                }
+                incl = warp_scan_fr<32>(run, lane);
+                off = shfl_up_fr(incl, 1);  // exclusive over the lanes
+                if (lane == 0) off = fr::zero();
+            }
+            Fr* tot = stot + (rd & 1) * SEGS;
+            if (lane == 31) st_fr(&tot[w], incl);   // tile total (zero for a tile past the end of the row)
+            __syncthreads();
+            // totals of the tiles before this warp's own, and of the whole round
+            Fr before = carry;
+#pragma unroll
+            for (int q = 0; q < SEGS; q++) {
+                const Fr t = ld_fr(&tot[q]);
+                if (q < w) before = fr::add_fast(before, t);
+                carry = fr::add_fast(carry, t);
+            }
+            if (nseg > 0) {
+                st_fr(&soff[lane], fr::add_fast(off, before));
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < MT_EPL; r++) {
+                    const int e = lane + 32 * r;
+                    if (e < nseg) st_fr_cs(out + t0 + e, fr::add_fast(mt_ld(sa, e), ld_fr(&soff[e / MT_EPL])));
+                }
+                __syncwarp();  // the buffers are restaged by the next round
+            }
+        }
+        if (threadIdx.x == 0 && jobs.job[jq].totals) st_fr(jobs.job[jq].totals + row, carry);
+    }
+}
+
 // Row totals only (no running sums): totals[row] = sum_t a[row][t] * v[t].  Used by row-sharded callers for (B v): every
 // rank needs all k totals as the second operand of A.(Bv) (reference src/matrix/mod.rs:337) but emits the running-sum
 // witnesses of its own rows of B only -- computing the totals redundantly is cheaper than a collective.  No canonical
@@ -353,10 +434,29 @@ static int launch_mv(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, cons
     return H2SVD_OK;
 }
 
+template <int SEGS>
+static int launch_mv_seg(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, const Fr* v, size_t len, size_t vs) {
+    constexpr size_t smem = (size_t)SEGS * MT_WARP_U4 * sizeof(uint4) + 2 * SEGS * sizeof(Fr);
+    H2SVD_SET_SMEM(ctx, mat_vec_prefix_seg_kernel<SEGS>, smem);
+    size_t blocks = total_rows;
+    const size_t cap = (size_t)ctx->sm_count * 16;   // grid-stride beyond a few waves of resident CTAs
+    if (blocks > cap) blocks = cap;
+    mat_vec_prefix_seg_kernel<SEGS><<<(unsigned)blocks, SEGS * 32, smem, ctx->stream>>>(jobs, v, len, vs);
+    H2SVD_LAUNCH_CHECK(ctx);
+    return H2SVD_OK;
+}
+
 static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_t len, size_t vs) {
     size_t total_rows = 0;
     for (int q = 0; q < jobs.njobs; q++) total_rows += jobs.job[q].rows;
     if (total_rows == 0 || len == 0) return H2SVD_OK;
+    // few long rows: several warps per row (mat_vec_prefix_seg_kernel); "matvec_seg": -1 auto, 0 never, 1 whenever len >= 256
+    const bool few_rows = total_rows < (size_t)ctx->sm_count * 16;
+    if (len >= 256 && ctx->tune.matvec_warp == 0 && (ctx->tune.matvec_seg > 0 || (ctx->tune.matvec_seg < 0 && few_rows))) {
+        if (len >= 1024) return launch_mv_seg<8>(ctx, jobs, total_rows, v, len, vs);
+        if (len >= 512) return launch_mv_seg<4>(ctx, jobs, total_rows, v, len, vs);
+        return launch_mv_seg<2>(ctx, jobs, total_rows, v, len, vs);
+    }
     if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && ctx->tune.matvec_warp == 0) {
         // one warp per row, consecutive elements per lane (mat_vec_prefix_tile_kernel); needs enough rows to
         // give every SM a few warps, otherwise the row-splitting kernel below is the better fit

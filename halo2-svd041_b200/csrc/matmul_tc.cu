@@ -188,6 +188,15 @@ __device__ __forceinline__ void tc_st2_zero(uint32_t taddr) {
     const uint32_t z = 0;
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(z), "r"(z) : "memory");
 }
+// debug timeline (triage switch "matmul_timeline"): CTA 0 stamps %globaltimer at the phase boundaries of its first 16 rounds
+__device__ __forceinline__ void tc_stamp(unsigned long long* tl, uint32_t round, int slot) {
+    if (tl != nullptr && blockIdx.x == 0 && round < 16) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tl[8 * round + slot] = t;
+    }
+}
+
 // this warp's accumulators (its TMEM lanes, its CW columns j of every diagonal) := 0, then hand them (back)
 // to the MMA warp.  Each warp zeroes only its own columns, so the warps of a lane quarter never race.
 template <class C>
@@ -235,35 +244,35 @@ __device__ __forceinline__ void tc_plane_words(const Fr* e, uint32_t* words, int
     }
 }
 
-// a: n x k (row-major Fr)  ->  planes[p][i][kk], kk < ldk (bytes kk >= k are zero); one thread = 4 k values
-template <class C>
-__global__ void __launch_bounds__(256)
-tc_split_a_kernel(const Fr* __restrict__ a, uint32_t* __restrict__ planes, int n, int k, int ldk4, int* mode) {
-    if (!C::SIGNED && mode && *mode == 0) return;   // the small-operand engine runs: nothing to prepare
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)n * ldk4) return;
-    const int i = (int)(idx / ldk4), w = (int)(idx % ldk4);
-    Fr e[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) e[t] = (4 * w + t < k) ? ldg_fr(a + (size_t)i * k + 4 * w + t) : fr::zero();
-    uint32_t words[32];
-    bool bad;
-    tc_plane_words<C>(e, words, C::LA, &bad);
-    if (C::SIGNED && bad) atomicOr(mode, 1);
-#pragma unroll
-    for (int p = 0; p < C::LA; p++) planes[((size_t)p * n + i) * ldk4 + w] = words[p];
-}
-
-// b: k x m (row-major Fr)  ->  planes[q][j][kk]  (the transposed operand: K-major rows per column j of B).
-// One CTA = 128 k values x 8 columns: the loads walk B along its rows (8 x 32 B = 256 contiguous bytes per k), the
-// words go through a padded shared-memory tile, and every plane row leaves as one coalesced 128-byte store.
+// ONE launch splits both operands: the first blocks_a CTAs take A, the others B.
+//   a: n x k (row-major Fr)  ->  planes_a[p][i][kk], kk < ldk (bytes kk >= k are zero); one thread = 4 k values of a row.
+//   b: k x m (row-major Fr)  ->  planes_b[q][j][kk]  (the transposed operand: K-major rows per column j of B).  One CTA =
+//      128 k values x 8 columns: the loads walk B along its rows (8 x 32 B = 256 contiguous bytes per k), the words go
+//      through a padded shared-memory tile, and every plane row leaves as one coalesced 128-byte store.
 constexpr int TC_SPLIT_ROW_W = 36;   // words per (plane, column) tile row: 32 + 4 of skew (conflict-free both ways)
 template <class C>
 __global__ void __launch_bounds__(256)
-tc_split_b_kernel(const Fr* __restrict__ b, uint32_t* __restrict__ planes, int k, int m, int ldk4, int* mode) {
-    if (!C::SIGNED && mode && *mode == 0) return;
+tc_split_kernel(const Fr* __restrict__ a, uint32_t* __restrict__ planes_a, int n, const Fr* __restrict__ b,
+                uint32_t* __restrict__ planes_b, int k, int m, int ldk4, int* mode, unsigned blocks_a, unsigned tiles_k) {
+    if (!C::SIGNED && mode && *mode == 0) return;   // the small-operand engine runs: nothing to prepare
     __shared__ uint32_t tile[C::LB * 8 * TC_SPLIT_ROW_W];
-    const int k0 = blockIdx.x * 128, j0 = blockIdx.y * 8;
+    uint32_t words[32];
+    bool bad;
+    if (blockIdx.x < blocks_a) {
+        const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx >= (size_t)n * ldk4) return;
+        const int i = (int)(idx / ldk4), w = (int)(idx % ldk4);
+        Fr e[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) e[t] = (4 * w + t < k) ? ldg_fr(a + (size_t)i * k + 4 * w + t) : fr::zero();
+        tc_plane_words<C>(e, words, C::LA, &bad);
+        if (C::SIGNED && bad) atomicOr(mode, 1);
+#pragma unroll
+        for (int p = 0; p < C::LA; p++) planes_a[((size_t)p * n + i) * ldk4 + w] = words[p];
+        return;
+    }
+    const unsigned bb = blockIdx.x - blocks_a;
+    const int k0 = (int)(bb % tiles_k) * 128, j0 = (int)(bb / tiles_k) * 8;
     const int j = threadIdx.x & 7, kq = threadIdx.x >> 3;       // kq: 0..31 -> k values k0 + 4*kq .. +3
     Fr e[4];
 #pragma unroll
@@ -271,8 +280,6 @@ tc_split_b_kernel(const Fr* __restrict__ b, uint32_t* __restrict__ planes, int k
         const int kk = k0 + 4 * kq + t;
         e[t] = (kk < k && j0 + j < m) ? ldg_fr(b + (size_t)kk * m + j0 + j) : fr::zero();
     }
-    uint32_t words[32];
-    bool bad;
     tc_plane_words<C>(e, words, C::LB, &bad);
     if (C::SIGNED && bad) atomicOr(mode, 1);
 #pragma unroll
@@ -283,7 +290,7 @@ tc_split_b_kernel(const Fr* __restrict__ b, uint32_t* __restrict__ planes, int k
     for (int row = warp; row < C::LB * 8; row += 8) {
         const int q = row >> 3, jj = row & 7;
         if (j0 + jj < m && w0 + lane < ldk4)
-            planes[((size_t)q * m + j0 + jj) * ldk4 + w0 + lane] = tile[row * TC_SPLIT_ROW_W + lane];
+            planes_b[((size_t)q * m + j0 + jj) * ldk4 + w0 + lane] = tile[row * TC_SPLIT_ROW_W + lane];
     }
 }
 
@@ -297,7 +304,7 @@ template <class C, bool FUSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     Fr* __restrict__ c, int n, int k, int m, int tiles_j, int num_tiles, int* err,
-                    const int* __restrict__ mode, int run_if_mode,
+                    const int* __restrict__ mode, int run_if_mode, unsigned long long* __restrict__ tl,
                     const __grid_constant__ rs::RescaleConsts kc, Fr* __restrict__ out_q, Fr* __restrict__ out_wit) {
     using D = TcD<C>;
     constexpr int TC_SA = tc_sa<C, FUSE>();
@@ -352,9 +359,10 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            uint32_t ua = 0, ub = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            uint32_t ua = 0, ub = 0, ptile = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ptile++) {
                 const int ib = tile / tiles_j, jb = tile % tiles_j;
+                tc_stamp(tl, ptile * passes, 6);
                 for (int kb = 0; kb < kblocks; kb++) {
                     const uint32_t sb = ub % TC_SB;
                     tc_mbar_wait(empty_b + 8 * sb, ((ub / TC_SB) & 1) ^ 1, err);
@@ -369,6 +377,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         ua++;
                     }
                 }
+                tc_stamp(tl, ptile * passes, 7);
             }
         }
     } else if (warp == 1) {
@@ -378,6 +387,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_empty, round & 1, err);  // accumulators zeroed by the epilogue warps
                 tc_fence_after();
+                if (lane == 0) tc_stamp(tl, round, 0);
                 const int kb_end = min(kblocks, (pass + 1) * C::KB_PASS);
                 for (int kb = pass * C::KB_PASS; kb < kb_end; kb++) {
                     const uint32_t sb = ub % TC_SB;
@@ -401,7 +411,10 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     __syncwarp();
                     ub++;
                 }
-                if (lane == 0) tc_commit(tmem_full);
+                if (lane == 0) {
+                    tc_commit(tmem_full);
+                    tc_stamp(tl, round, 1);
+                }
                 __syncwarp();
                 round++;
             }
@@ -419,6 +432,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             ws.warp_row0 = stage + (size_t)(warp - 2) * 32 * TcWitnessStream::ROW_U4;
             ws.row0 = ws.warp_row0 + (size_t)lane * TcWitnessStream::ROW_U4;
             ws.W = m * kc.p.W;
+            ws.buf_stride = 0;   // single-buffered
             ws.buf = 0;
             ws.fill = 0;
         }
@@ -429,6 +443,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_full, round & 1, err);
                 tc_fence_after();
+                if (threadIdx.x == 64) tc_stamp(tl, round, 2);
                 // Phase 1 (on the critical path of the next tile): read this warp's columns of all diagonals and carry
                 // them into multi-limb integers T = sum_d dg[d] * 2^(8d).
                 constexpr int TW = C::SIGNED ? 6 : 18;
@@ -459,7 +474,9 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 // the accumulators are free again: zero them and let the MMA warp start the next tile while the
                 // Montgomery reductions (and the rescale witnesses) below run
                 tc_fence_before();  // order the TMEM reads above before the zeroing stores / the next MMAs
+                if (threadIdx.x == 64) tc_stamp(tl, round, 3);
                 tc_zero_and_release<C>(tlane + j0, tmem_empty);
+                if (threadIdx.x == 64) tc_stamp(tl, round, 4);
                 // Phase 2 (overlaps the next tile's MMAs)
                 Fr res[CW];
 #pragma unroll
@@ -488,6 +505,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         }
                     }
                 }
+                if (threadIdx.x == 64) tc_stamp(tl, round, 5);
                 round++;
             }
         }
@@ -608,12 +626,14 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
     using D = TcD<C>;
     const int ldk4 = (int)(ldk / 4);
     if (!mm_only) {
-        const size_t ta = n * (size_t)ldk4;
-        tc_split_a_kernel<C><<<(unsigned)((ta + 255) / 256), 256, 0, ctx->stream>>>(a, reinterpret_cast<uint32_t*>(a8), (int)n,
-                                                                                   (int)k, ldk4, mode);
-        H2SVD_LAUNCH_CHECK(ctx);
-        const dim3 gb((unsigned)((ldk + 127) / 128), (unsigned)((m + 7) / 8));
-        tc_split_b_kernel<C><<<gb, 256, 0, ctx->stream>>>(b, reinterpret_cast<uint32_t*>(b8), (int)k, (int)m, ldk4, mode);
+        const size_t blocks_a = (n * (size_t)ldk4 + 255) / 256, tiles_k = (ldk + 127) / 128, blocks_b = tiles_k * ((m + 7) / 8);
+        if (blocks_a + blocks_b >= (1ull << 31)) {
+            set_error("fr_matmul (tensor-core engine): operands too large for the split kernel's grid");
+            return H2SVD_EINVAL;
+        }
+        tc_split_kernel<C><<<(unsigned)(blocks_a + blocks_b), 256, 0, ctx->stream>>>(
+            a, reinterpret_cast<uint32_t*>(a8), (int)n, b, reinterpret_cast<uint32_t*>(b8), (int)k, (int)m, ldk4, mode,
+            (unsigned)blocks_a, (unsigned)tiles_k);
         H2SVD_LAUNCH_CHECK(ctx);
     }
     if (split_only) return H2SVD_OK;
@@ -655,14 +675,14 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         if constexpr (!C::SIGNED) {
             H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, true>), (tc_smem_bytes<C, true>()));
             fr_matmul_tc_kernel<C, true><<<grid, TC_THREADS, tc_smem_bytes<C, true>(), ctx->stream>>>(
-                tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, *fuse, out_q,
+                tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, *fuse, out_q,
                 out_wit);
         }
     } else {
         static const rs::RescaleConsts none{};
         H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, false>), (tc_smem_bytes<C, false>()));
         fr_matmul_tc_kernel<C, false><<<grid, TC_THREADS, tc_smem_bytes<C, false>(), ctx->stream>>>(
-            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, none, nullptr,
+            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, none, nullptr,
             nullptr);
     }
     H2SVD_LAUNCH_CHECK(ctx);

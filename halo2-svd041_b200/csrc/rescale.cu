@@ -116,8 +116,9 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
     WitnessStream ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_NBUF * RS_ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_NBUF * RS_ROW_U4;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_ROW_U4;
+    ws.buf_stride = RS_THREADS * RS_ROW_U4;
     ws.W = k.p.W;
     ws.buf = 0;
     ws.fill = 0;
@@ -147,8 +148,9 @@ abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __r
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
     WitnessStream ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_NBUF * RS_ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_NBUF * RS_ROW_U4;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_ROW_U4;
+    ws.buf_stride = RS_THREADS * RS_ROW_U4;
     ws.W = k.W;
     ws.buf = 0;
     ws.fill = 0;
@@ -178,8 +180,9 @@ range_check_kernel(const Fr* __restrict__ x, Fr* __restrict__ out_wit, size_t co
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
     WitnessStream ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_NBUF * RS_ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_NBUF * RS_ROW_U4;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_ROW_U4;
+    ws.buf_stride = RS_THREADS * RS_ROW_U4;
     ws.W = k.W;
     ws.buf = 0;
     ws.fill = 0;

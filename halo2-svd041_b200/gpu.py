@@ -105,12 +105,20 @@ class Handle:
 
     # ---- triage / tuning switches (per handle; not part of the public header) ----
     TUNE_KEYS = ("matmul_tc", "matmul_small", "matmul_karatsuba", "matmul_streamk", "matmul_variant", "fuse_rescale",
-                 "rescale_generic", "matvec_warp_kernel")
+                 "rescale_generic", "matvec_warp_kernel", "matvec_seg")
 
     def tune(self, key: str, value: int) -> None:
         """matmul_tc / matmul_small: -1 auto, 0 never, 1 always; matmul_karatsuba: -1 auto, 0 schoolbook, 1..3 variants;
         matmul_streamk: -1 auto, 0 never, 1 always; fuse_rescale, rescale_generic, matvec_warp_kernel: 0/1."""
         _ffi.check(self._lib.h2svd_debug_tune(self._h, key.encode(), int(value)))
+
+    def matmul_timeline(self, enable: bool = True) -> np.ndarray:
+        """Triage: returns the [16, 8] %globaltimer stamps CTA 0 of the last tensor-core mat-mul left (rounds x slots:
+        0 MMA start, 1 MMAs issued, 2 epilogue sees the accumulators, 3 TMEM read + carry done, 4 accumulators zeroed and
+        released, 5 field arithmetic + stores done, 6/7 TMA producer first/last load of the tile) and re-arms (or disarms)."""
+        out = np.zeros((16, 8), dtype=np.uint64)
+        _ffi.check(self._lib.h2svd_debug_matmul_timeline(self._h, int(enable), _np_ptr(out)))
+        return out
 
     def last_matmul_engine(self) -> str:
         """Which engine the last fr_matmul launch of THIS handle used (bench.py reports the matching roofline)."""

@@ -301,3 +301,56 @@ def test_multi_handle_more_handles_than_rows_and_errors(pkg):
         assert _eq(res2["c_s"], c)
     with pytest.raises(pkg.H2svdError):
         pkg.MultiHandle([ngpu + 7])
+
+
+# ---------------------------------------------------------------- several-warps-per-row mat-vec prefix kernel
+@pytest.mark.parametrize("rows,ln", [(1, 256), (3, 300), (5, 512), (7, 1000), (16, 1024), (2, 2100), (3, 4099), (130, 1024)])
+@pytest.mark.parametrize("per_row_v", [False, True])
+def test_mat_vec_prefix_seg_kernel_matches_oracle(handle, rows, ln, per_row_v):
+    """mat_vec_prefix_seg_kernel (SEGS warps per row, tile totals exchanged through shared memory) forced on: every
+    running sum bit-exact with the oracle, shared vector (field_mat_vec_mul) and per-row vectors (ZkVector::inner_product),
+    ragged last tiles, rows longer than one round of SEGS tiles."""
+    import torch
+    rng = np.random.default_rng(rows * 7 + ln)
+    a = random_fr(rng, rows, ln)
+    dev = torch.device("cuda", handle.device)
+    ta = torch.from_numpy(a.view(np.int64)).to(dev)
+    out = torch.full((rows, ln, 4), -1, dtype=torch.int64, device=dev)
+    try:
+        handle.tune("matvec_seg", 1)
+        if per_row_v:
+            s = random_fr(rng, rows, ln)
+            ts = torch.from_numpy(s.view(np.int64)).to(dev)
+            torch.cuda.synchronize()
+            handle.zkvec_inner_prefix_dev(ta, ts, out)
+            want = corac.zkvec_inner_prefix(a, s, threads=0)
+        else:
+            v = random_fr(rng, ln)
+            tv = torch.from_numpy(v.view(np.int64)).to(dev)
+            tot = torch.full((rows, 4), -1, dtype=torch.int64, device=dev)
+            torch.cuda.synchronize()
+            handle.mat_vec_prefix_dev(ta, tv, out, tot)
+            want = corac.mat_vec_prefix(a, v, threads=0)
+        handle.sync()
+    finally:
+        handle.tune("matvec_seg", -1)
+    assert _eq(out.cpu().numpy().view(np.uint64), want)
+    if not per_row_v:
+        assert _eq(tot.cpu().numpy().view(np.uint64), want[:, -1])
+
+
+def test_freivalds_witness_with_seg_kernel_two_jobs(handle):
+    """verify_mul's paired launch (c_s . v and b . v in one grid: two jobs) through the several-warps-per-row kernel."""
+    rng = np.random.default_rng(21)
+    n, k, m = 40, 70, 600
+    a, b = quantized_matrix(rng, n, k, 63), quantized_matrix(rng, k, m, 63)
+    c = corac.field_mat_mul(a, b, threads=0)
+    gamma = random_fr(rng, 1)
+    try:
+        handle.tune("matvec_seg", 1)
+        fw = handle.freivalds_witness(a, b, c, gamma)
+    finally:
+        handle.tune("matvec_seg", -1)
+    want = corac.freivalds_witness(a, b, c, gamma, threads=0)
+    for key, val in want.items():
+        assert _eq(fw[key], val), key
