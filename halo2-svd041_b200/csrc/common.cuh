@@ -34,11 +34,13 @@ struct h2svd_ctx {
     struct Tuning {
         int matmul_tc = -1;       // tensor-core mat-mul engines: -1 auto, 0 never, 1 always
         int matmul_small = -1;    // small-operand tensor-core engine: -1 auto (range-detected on the device), 0 never
+        int matmul_small_width = 0;  // tile width of the small-operand engine: 0 auto (cost model), 8 / 16 / 24 forced
         int kara = -1;            // IMAD engines: -1 auto, 0 schoolbook kernels only, 1..3 force a Karatsuba variant
         int streamk = -1;         // IMAD engines: -1 auto, 0 never, 1 always use the stream-K schedule
         int variant = 0;          // schoolbook tile variant
         int fuse_rescale = 0;     // 1: rescale witnesses from the tensor-core epilogue (experimental)
         int rescale_generic = 0;  // 1: force the generic (unstaged) rescale kernel
+        int rescale_ch = 8;       // witnesses per bulk store of the staged rescale kernel: 4, 6 or 8
         int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel
         int matvec_seg = -1;      // several-warps-per-row mat-vec prefix kernel: -1 auto (few long rows), 0 never, 1 always
     } tune;

@@ -56,12 +56,18 @@ struct TcFull {
     static constexpr int LA = 32, LB = 32, BJ = 8, SA = 6, SB = 2, KB_PASS = 8;   // 6 x 16 KB + 2 x 32 KB of stages
     static constexpr bool SIGNED = false;
 };
-// Small signed operands: 9 (A) x 10 (B) balanced byte digits, 128 x 24 tiles (MMA N = 240); |D_d| <= 9 * k * 128^2 stays
-// below 2^31 for k <= 14563: 64 K blocks (8192 k values) per pass.  7 x 16 KB + 2 x 30 KB of stages.
-struct TcSmall {
-    static constexpr int LA = fr::SMALL_DIGITS, LB = fr::SMALL_DIGITS + 1, BJ = 24, SA = 7, SB = 2, KB_PASS = 64;
+// Small signed operands: 9 (A) x 9 or 10 (B) balanced byte digits (a zero 10th plane where MMA N = LB * BJ would not be a
+// multiple of 16 otherwise); |D_d| <= 9 * k * 128^2 stays below 2^31 for k <= 14563: 64 K blocks (8192 k values) per pass.
+// Three tile widths: 128 x 24 (MMA N = 240: the fewest operand bytes per multiply-add, for products with at least a
+// wave of such tiles), 128 x 16 and 128 x 8 (N = 144 / 80: more, shorter tiles for the row slabs of a sharded job).
+template <int BJ_, int LB_, int SA_>
+struct TcSmallT {
+    static constexpr int LA = fr::SMALL_DIGITS, LB = LB_, BJ = BJ_, SA = SA_, SB = 2, KB_PASS = 64;
     static constexpr bool SIGNED = true;
 };
+using TcSmall = TcSmallT<24, fr::SMALL_DIGITS + 1, 7>;     // 7 x 16 KB + 2 x 30 KB of stages
+using TcSmall16 = TcSmallT<16, fr::SMALL_DIGITS, 8>;       // 8 x 16 KB + 2 x 18 KB
+using TcSmall8 = TcSmallT<8, fr::SMALL_DIGITS + 1, 8>;     // 8 x 16 KB + 2 x 10 KB
 template <class C>
 struct TcD {
     static constexpr int NMMA = C::LB * C::BJ;                  // MMA N
@@ -706,6 +712,33 @@ bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
     return k >= 1 && n * 32 < (1ull << 31) && m * 32 < (1ull << 31) && k < (1ull << 30);
 }
 
+// Tile width of the small-operand engine for one product: estimated time = waves of tiles x time per tile, a tile being
+// bound by its MMAs (LA * 4 instructions of N / 2 cycles per K block) or by the L2 -> shared-memory delivery of its
+// operands (~6000 B/clk for the whole chip, ~100 B/clk for one SM), plus the field arithmetic of the last tile's columns.
+static int tc_small_tile_width(const h2svd_ctx* ctx, size_t n, size_t k, size_t m) {
+    if (ctx->tune.matmul_small_width == 8 || ctx->tune.matmul_small_width == 16 || ctx->tune.matmul_small_width == 24)
+        return ctx->tune.matmul_small_width;
+    const double sms = ctx->sm_count, kblocks = (double)((k + TC_BKB - 1) / TC_BKB);
+    const int widths[3] = {24, 16, 8}, planes_b[3] = {10, 9, 10};
+    int best = 24;
+    double best_t = 1e300;
+    for (int i = 0; i < 3; i++) {
+        const double bj = widths[i], lb = planes_b[i];
+        const double tiles = (double)((n + TC_BM - 1) / TC_BM) * (double)((m + widths[i] - 1) / widths[i]);
+        const double active = tiles < sms ? tiles : sms;
+        const double waves = (double)(long long)((tiles + sms - 1) / sms);
+        const double bw = 6000.0 / active < 100.0 ? 6000.0 / active : 100.0;                 // bytes per clock per busy SM
+        const double mma = 9.0 * 4.0 * (lb * bj / 2.0), bytes = 9.0 * 16384.0 + lb * bj * 128.0;
+        const double tile = kblocks * (mma > bytes / bw ? mma : bytes / bw) + 700.0;          // + accumulator hand-over
+        const double t = waves * tile + 2900.0 * (bj / 4.0);                                  // + the last tile's field arithmetic
+        if (t < best_t) {
+            best_t = t;
+            best = widths[i];
+        }
+    }
+    return best;
+}
+
 int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m,
                         const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit) {
     if (n == 0 || m == 0) return H2SVD_OK;
@@ -717,7 +750,7 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
     const bool try_small = ctx->tune.matmul_small != 0 && fuse == nullptr;
     const size_t ldk = (k + 15) & ~(size_t)15;  // TMA row pitch: multiple of 16 bytes
     const size_t full_a = tc_align256(TcFull::LA * n * ldk), full_b = tc_align256(TcFull::LB * m * ldk);
-    const size_t small_a = tc_align256(TcSmall::LA * n * ldk), small_b = tc_align256(TcSmall::LB * m * ldk);
+    const size_t small_a = tc_align256(TcSmall::LA * n * ldk), small_b = tc_align256(TcSmall::LB * m * ldk);   // LB = 10: the largest
     const size_t need = full_a + full_b + (try_small ? small_a + small_b : 0);
     // the operand workspace is shared with the Karatsuba engine (never both at once)
     H2SVD_TRY(ws_grow(ctx, &ctx->kara_ws, &ctx->kara_ws_bytes, need));
@@ -731,15 +764,21 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
                                         out_wit);
     }
     // Both engines are enqueued; *d_mode (0 = every operand is a small signed integer, else 1), written by the
-    // small-operand split kernels, decides on the device which of them does the work.
+    // small-operand split kernel, decides on the device which of them does the work.
     ctx->last_engine = 3;
     H2SVD_CUDA(cudaMemsetAsync(ctx->d_mode, 0, sizeof(int), ctx->stream));
-    H2SVD_TRY(tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, true, false, nullptr,
-                                        nullptr, nullptr));
+    const int width = tc_small_tile_width(ctx, n, k, m);
+    auto small = [&](bool split_only, bool mm_only) -> int {
+        switch (width) {
+            case 8: return tc_launch_engine<TcSmall8>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
+            case 16: return tc_launch_engine<TcSmall16>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
+            default: return tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
+        }
+    };
+    H2SVD_TRY(small(true, false));
     H2SVD_TRY(tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, true, false, nullptr,
                                        nullptr, nullptr));
-    H2SVD_TRY(tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, true, nullptr,
-                                        nullptr, nullptr));
+    H2SVD_TRY(small(false, true));
     return tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, false, true, nullptr,
                                     nullptr, nullptr);
 }

@@ -109,16 +109,26 @@ constexpr int RS_ROW_U4 = RS_CH * 2 + 1;      // staging row in 16-byte units: 2
 constexpr size_t RS_SMEM = (size_t)RS_THREADS * RS_NBUF * RS_ROW_U4 * sizeof(uint4);
 constexpr int RS_CTAS_PER_SM = (int)((227 * 1024) / (RS_SMEM + 1024)) > 0 ? (int)((227 * 1024) / (RS_SMEM + 1024)) : 1;
 using WitnessStream = WitnessStreamT<RS_CH, RS_NBUF>;   // 256-byte bursts, double-buffered rows
+// the rescale kernel itself is instantiated for several burst sizes (tuning switch "rescale_ch"): fewer witnesses per
+// burst = a smaller staging area = more resident CTAs per SM (the kernel is latency-, not bandwidth-limited)
+template <int CH>
+struct RsCfg {
+    static constexpr int ROW_U4 = CH * 2 + 1;
+    static constexpr size_t SMEM = (size_t)RS_THREADS * RS_NBUF * ROW_U4 * sizeof(uint4);
+    static constexpr int CTAS_PER_SM_SMEM = (int)((227 * 1024) / (SMEM + 1024));
+    static constexpr int CTAS_PER_SM = CTAS_PER_SM_SMEM < 4 ? CTAS_PER_SM_SMEM : 4;   // 128 threads x 120 registers: 4 by registers
+};
 
-__global__ void __launch_bounds__(RS_THREADS)
+template <int CH>
+__global__ void __launch_bounds__(RS_THREADS, RsCfg<CH>::CTAS_PER_SM)
 rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
                const __grid_constant__ RescaleConsts k) {
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
-    WitnessStream ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * RS_ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RS_ROW_U4;
-    ws.buf_stride = RS_THREADS * RS_ROW_U4;
+    WitnessStreamT<CH, RS_NBUF> ws;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RsCfg<CH>::ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RsCfg<CH>::ROW_U4;
+    ws.buf_stride = RS_THREADS * RsCfg<CH>::ROW_U4;
     ws.W = k.p.W;
     ws.buf = 0;
     ws.fill = 0;
@@ -167,7 +177,7 @@ abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __r
         }
         const Fr tm = fr::add_fast(dm, k.m_add);     // gate.add(x, Constant(bnd - 1))
         ws.put(tm);
-        stream_cbls(ws, k.lc, fr::from_mont_fast(tm), tm, k.n, k.i_pow, k.i_bound, k.m_pow, k.m_bound);
+        stream_cbls(ws, k.lc, fr::mont_reduce_fast(tm), tm, k.n, k.i_pow, k.i_bound, k.m_pow, k.m_bound);
         ws.flush();
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every lane: see rescale_kernel
@@ -193,7 +203,7 @@ range_check_kernel(const Fr* __restrict__ x, Fr* __restrict__ out_wit, size_t co
         ws.gwarp = out_wit + e0 * (size_t)k.W;
         const size_t e = lane < ws.valid ? e0 + lane : count - 1;
         const Fr xm = ldg_fr(x + e);
-        const Fr xi = fr::from_mont_fast(xm);
+        const Fr xi = fr::mont_reduce_fast(xm);
         stream_range_check(ws, k.lc, xi, k.n);
         if (k.rem > 1) {
             if (k.n == 1) {
@@ -274,6 +284,17 @@ int make_rescale_consts(int P, int lb, int S, int A, rs::RescaleConsts* out) {
     return p.W;
 }
 
+template <int CH>
+static int launch_rescale_ch(h2svd_ctx* ctx, const Fr* cs, size_t count, const rs::RescaleConsts& k, Fr* out_q, Fr* out_wit) {
+    H2SVD_SET_SMEM(ctx, rescale_kernel<CH>, RsCfg<CH>::SMEM);
+    size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
+    const size_t cap = (size_t)ctx->sm_count * RsCfg<CH>::CTAS_PER_SM;  // resident CTAs, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    rescale_kernel<CH><<<(unsigned)blocks, RS_THREADS, RsCfg<CH>::SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
+    H2SVD_LAUNCH_CHECK(ctx);
+    return H2SVD_OK;
+}
+
 int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, int S, int A, Fr* out_q,
                    Fr* out_wit) {
     if (S < 0) S = 3 * P;
@@ -293,13 +314,11 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     }
     RescaleConsts k;
     make_rescale_consts(P, lb, S, A, &k);
-    H2SVD_SET_SMEM(ctx, rescale_kernel, RS_SMEM);
-    size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
-    const size_t cap = (size_t)ctx->sm_count * RS_CTAS_PER_SM;  // resident CTAs (staging-limited), grid-stride beyond
-    if (blocks > cap) blocks = cap;
-    rescale_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
-    H2SVD_LAUNCH_CHECK(ctx);
-    return H2SVD_OK;
+    switch (ctx->tune.rescale_ch) {
+        case 4: return launch_rescale_ch<4>(ctx, cs, count, k, out_q, out_wit);
+        case 6: return launch_rescale_ch<6>(ctx, cs, count, k, out_q, out_wit);
+        default: return launch_rescale_ch<8>(ctx, cs, count, k, out_q, out_wit);
+    }
 }
 
 // W of check_abs_less_than for bound `bnd` (canonical integer): [diff] + t + cbls(2*bnd - 1)

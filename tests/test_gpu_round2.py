@@ -354,3 +354,21 @@ def test_freivalds_witness_with_seg_kernel_two_jobs(handle):
     want = corac.freivalds_witness(a, b, c, gamma, threads=0)
     for key, val in want.items():
         assert _eq(fw[key], val), key
+
+
+@pytest.mark.parametrize("width", [8, 16, 24])
+@pytest.mark.parametrize("n,k,m", [(129, 130, 50), (300, 257, 47), (128, 1024, 100), (40, 8300, 30)])
+def test_small_operand_engine_every_tile_width(handle, width, n, k, m):
+    """The three tile widths of the small-operand engine (128 x 8 / 16 / 24: MMA N = 80 / 144 / 240) forced in turn on ragged
+    shapes (m not a multiple of any width, n not a multiple of 128, k tails, two accumulation passes): same bytes."""
+    rng = np.random.default_rng(n + k + m)
+    a, b = _signed_matrix(rng, n, k, 69), _signed_matrix(rng, k, m, 69)
+    try:
+        handle.tune("matmul_tc", 1)
+        handle.tune("matmul_small_width", width)
+        got = handle.fr_matmul(a, b)
+        assert handle.last_matmul_engine() == "tensor-small"
+    finally:
+        handle.tune("matmul_tc", -1)
+        handle.tune("matmul_small_width", 0)
+    assert _eq(got, corac.field_mat_mul(a, b, threads=0))
