@@ -95,6 +95,7 @@ SIGNATURES = {
     "h2svd_expand_gamma_power_cells": (_I, [_P, _P, _Z, _P]),
     "h2svd_expand_is_equal_cells": (_I, [_P, _P, _P, _P, _P, _Z, _P]),
     "h2svd_microbench_imad": (_I, [_P, _I, _I, ct.POINTER(ct.c_double)]),
+    "h2svd_microbench_hbm": (_I, [_P, _I, _Z, ct.POINTER(ct.c_double)]),
     "h2svd_microbench_tensor_i8": (_I, [_P, _I, ct.c_double, ct.POINTER(ct.c_double)]),
 }
 # not part of the public header: triage helpers

@@ -1035,6 +1035,12 @@ int h2svd_microbench_imad(h2svd_ctx* ctx, int kind, int iters, double* ops_per_s
     return launch_microbench(ctx, kind, iters, ops_per_s);
 }
 
+int h2svd_microbench_hbm(h2svd_ctx* ctx, int kind, size_t bytes, double* gb_per_s) {
+    REQUIRE(ctx, "microbench_hbm: null handle");
+    H2SVD_CUDA(cudaSetDevice(ctx->device));
+    return launch_microbench_hbm(ctx, kind, bytes, gb_per_s);
+}
+
 int h2svd_microbench_tensor_i8(h2svd_ctx* ctx, int kind, double min_seconds, double* ops_per_s) {
     REQUIRE(ctx, "microbench_tensor_i8: null handle");
     H2SVD_CUDA(cudaSetDevice(ctx->device));
@@ -1051,6 +1057,7 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
         {"matmul_variant", &ctx->tune.variant},    {"fuse_rescale", &ctx->tune.fuse_rescale},
         {"rescale_generic", &ctx->tune.rescale_generic}, {"matvec_warp_kernel", &ctx->tune.matvec_warp},
         {"matvec_seg", &ctx->tune.matvec_seg},       {"rescale_ch", &ctx->tune.rescale_ch},
+        {"rescale_tma", &ctx->tune.rescale_tma},
     };
     for (const auto& e : keys)
         if (strcmp(e.name, key) == 0) {

@@ -40,6 +40,7 @@ struct h2svd_ctx {
         int variant = 0;          // schoolbook tile variant
         int fuse_rescale = 0;     // 1: rescale witnesses from the tensor-core epilogue (experimental)
         int rescale_generic = 0;  // 1: force the generic (unstaged) rescale kernel
+        int rescale_tma = 1;      // witness stream of the rescale kernel through TMA tensor stores (0: per-row bulk copies)
         int rescale_ch = 8;       // witnesses per bulk store of the staged rescale kernel: 4, 6 or 8
         int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel
         int matvec_seg = -1;      // several-warps-per-row mat-vec prefix kernel: -1 auto (few long rows), 0 never, 1 always
@@ -160,6 +161,7 @@ int launch_isqrt(h2svd_ctx* ctx, const Fr* a, size_t count, int P, Fr* out);
 int launch_quantize(h2svd_ctx* ctx, const double* x, size_t count, int P, Fr* out);
 int launch_check_canonical(h2svd_ctx* ctx, const Fr* x, size_t count, int* d_flag);
 int launch_microbench(h2svd_ctx* ctx, int kind, int iters, double* ops_per_s);
+int launch_microbench_hbm(h2svd_ctx* ctx, int kind, size_t bytes, double* gb_per_s);
 int launch_microbench_i8(h2svd_ctx* ctx, int kind, double min_seconds, double* ops_per_s);
 
 }  // namespace h2svd

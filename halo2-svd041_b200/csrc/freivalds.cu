@@ -345,18 +345,23 @@ mat_vec_prefix_seg_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restr
 // witnesses of its own rows of B only -- computing the totals redundantly is cheaper than a collective.  No canonical
 // intermediate is needed, so the products are accumulated lazily (fr_acc.cuh: 64 IMAD.WIDE per element, one reduction
 // per lane) -- the same value as the last running sum of mat_vec_prefix, since the canonical representative is unique.
-constexpr int MVT_WARPS = 8;
-__global__ void __launch_bounds__(MVT_WARPS * 32)
+constexpr int MVT_WPR = 4;      // warps per row: 1024 rows of one N = 1024 operand would otherwise leave 7 warps per SM
+constexpr int MVT_ROWS = 2;     // rows per CTA
+__global__ void __launch_bounds__(MVT_WPR * MVT_ROWS * 32)
 mat_vec_totals_kernel(const Fr* __restrict__ a, const Fr* __restrict__ v, Fr* __restrict__ totals, size_t rows, size_t len) {
-    const int lane = threadIdx.x & 31;
-    const size_t warps_total = (size_t)gridDim.x * MVT_WARPS;
-    for (size_t row = (size_t)blockIdx.x * MVT_WARPS + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    __shared__ Fr part[MVT_ROWS][MVT_WPR];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = warp / MVT_WPR, wr = warp % MVT_WPR;
+    for (size_t row0 = (size_t)blockIdx.x * MVT_ROWS; row0 < rows; row0 += (size_t)gridDim.x * MVT_ROWS) {   // CTA-uniform
+        const size_t row = row0 + rl;
         fr::WideAcc w;
         fr::acc_clear(w);
-        const Fr* ar = a + row * len;
-        for (size_t j = lane; j < len; j += 32) {
-            const Fr x = ldg_fr(ar + j), y = ldg_fr(v + j);
-            fr::mul_acc(w, x.l, y.l);
+        if (row < rows) {
+            const Fr* ar = a + row * len;
+            for (size_t j = (size_t)wr * 32 + lane; j < len; j += MVT_WPR * 32) {
+                const Fr x = ldg_fr(ar + j), y = ldg_fr(v + j);
+                fr::mul_acc(w, x.l, y.l);
+            }
         }
         Fr p = fr::acc_finalize(w);
 #pragma unroll
@@ -366,7 +371,15 @@ mat_vec_totals_kernel(const Fr* __restrict__ a, const Fr* __restrict__ v, Fr* __
             for (int i = 0; i < 8; i++) t.l[i] = __shfl_down_sync(0xffffffffu, p.l[i], d);
             p = fr::add_fast(p, t);
         }
-        if (lane == 0) st_fr(totals + row, p);
+        if (lane == 0) st_fr(&part[rl][wr], p);
+        __syncthreads();
+        if (wr == 0 && lane == 0 && row < rows) {
+            Fr s = ld_fr(&part[rl][0]);
+#pragma unroll
+            for (int q = 1; q < MVT_WPR; q++) s = fr::add_fast(s, ld_fr(&part[rl][q]));
+            st_fr(totals + row, s);
+        }
+        __syncthreads();   // part[] is rewritten by the next pair of rows
     }
 }
 
@@ -499,10 +512,10 @@ int launch_mat_vec_prefix2(h2svd_ctx* ctx, const Fr* a0, size_t rows0, Fr* out0,
 
 int launch_mat_vec_totals(h2svd_ctx* ctx, const Fr* a, const Fr* v, size_t rows, size_t len, Fr* totals) {
     if (rows == 0) return H2SVD_OK;
-    size_t blocks = (rows + MVT_WARPS - 1) / MVT_WARPS;
-    const size_t cap = (size_t)ctx->sm_count * 8;
+    size_t blocks = (rows + MVT_ROWS - 1) / MVT_ROWS;
+    const size_t cap = (size_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    mat_vec_totals_kernel<<<(unsigned)blocks, MVT_WARPS * 32, 0, ctx->stream>>>(a, v, totals, rows, len);
+    mat_vec_totals_kernel<<<(unsigned)blocks, MVT_WPR * MVT_ROWS * 32, 0, ctx->stream>>>(a, v, totals, rows, len);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }

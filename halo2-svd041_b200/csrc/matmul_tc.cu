@@ -29,11 +29,11 @@
 //     accumulator columns are re-zeroed and handed back before the field arithmetic, which overlaps the next tile.
 // Operands are pre-split into byte planes by O(N^2) kernels (A8[p][i][k], B8[q][j][k], both K-major so that
 // TMA with the 128-byte swizzle delivers the canonical K-major UMMA layout).
-#include <cuda.h>  // CUtensorMap and enums only; the encoder comes from cudaGetDriverEntryPoint (no -lcuda)
 
 #include "common.cuh"
 #include "rescale_dev.cuh"
 #include "tc_small.cuh"
+#include "tma_util.cuh"
 
 namespace h2svd {
 
@@ -228,7 +228,7 @@ __device__ __forceinline__ void tc_plane_words(const Fr* e, uint32_t* words, int
         uint32_t t[4][3];
         bool ok = true;
 #pragma unroll
-        for (int r = 0; r < 4; r++) ok &= fr::small_biased(e[r], t[r]);   // zero (K padding) is in range: digits 0
+        for (int r = 0; r < 4; r++) ok &= fr::small_biased_fast(e[r], t[r]);   // zero (K padding) is in range: digits 0
         *out_of_range = !ok;
 #pragma unroll
         for (int p = 0; p < 32; p++) {
@@ -525,21 +525,8 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
 }
 
-typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-tc_encode_fn tc_encoder() {
-    static tc_encode_fn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<tc_encode_fn>(p);
-    }
-    return fn;
-}
+using tc_encode_fn = tma_encode_fn;
+inline tc_encode_fn tc_encoder() { return tma_encoder(); }
 
 // ---- tensor-pipe micro-benchmark: the measured denominator of the mat-mul roofline --------------------------------
 // One CTA per SM, operands resident in shared memory (pseudo-random bytes, the layouts of the real kernel), one elected

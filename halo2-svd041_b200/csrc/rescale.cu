@@ -150,6 +150,40 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// The same kernel with TMA tensor stores for the witness stream (WitnessStreamTma): the default when the stripe is at
+// least one 128-byte box column wide and the element count fits a 32-bit tensor coordinate.
+constexpr int RT_THREADS = 128;
+constexpr int RT_CH = 8;
+using RtStream = WitnessStreamTma<RT_CH, 2>;
+constexpr size_t RT_SMEM = (size_t)(RT_THREADS / 32) * RtStream::WARP_BYTES + 1024;   // + alignment slack
+__global__ void __launch_bounds__(RT_THREADS, 3)
+rescale_tma_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, size_t count, const __grid_constant__ CUtensorMap wmap,
+                   const __grid_constant__ RescaleConsts k) {
+    extern __shared__ uint8_t rt_stage_raw[];
+    const uint32_t raw = smem_addr(rt_stage_raw);
+    uint8_t* stage = rt_stage_raw + (((raw + 1023u) & ~1023u) - raw);   // the swizzle pattern repeats every 1024 bytes
+    const int lane = threadIdx.x & 31;
+    RtStream ws;
+    ws.tile0 = stage + (size_t)(threadIdx.x >> 5) * RtStream::WARP_BYTES;
+    ws.map = &wmap;
+    ws.lane = lane;
+    ws.buf = 0;
+    ws.fill = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // warp-uniform trip count: lanes past the end recompute the last element; their rows are outside the tensor
+    for (size_t e0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < count; e0 += stride) {
+        ws.begin((int)e0);
+        const bool live = e0 + lane < count;
+        const size_t e = live ? e0 + lane : count - 1;
+        const Fr am = ldg_fr(cs + e);
+        const Fr q = rescale_element(ws, k, am);
+        if (live) st_fr(out_q + e, q);
+    }
+    // shared memory must outlive every TMA read, and the writes must be complete at kernel end (every lane: the groups
+    // belong to whichever lane elect.sync picked)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // check_abs_less_than(x, bnd) (reference src/matrix/mod.rs:425-437), optionally of a difference x - y
 // (check_mat_diff :441-459): witnesses [x - y]?, t = d + (bnd - 1), check_big_less_than_safe(t, 2*bnd - 1).
 __global__ void __launch_bounds__(RS_THREADS)
@@ -314,6 +348,29 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     }
     RescaleConsts k;
     make_rescale_consts(P, lb, S, A, &k);
+    if (ctx->tune.rescale_tma != 0 && p.W >= 4 && count < (1ull << 31)) {
+        // witness stream as a 2-D tensor [count][W * 32 bytes]; one box = 32 elements x 128 bytes
+        tma_encode_fn encode = tma_encoder();
+        if (encode) {
+            CUtensorMap wmap;
+            const cuuint64_t dims[2] = {(cuuint64_t)p.W * 32, (cuuint64_t)count};
+            const cuuint64_t strides[1] = {(cuuint64_t)p.W * 32};
+            const cuuint32_t box[2] = {128, 32};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, out_wit, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) {
+                H2SVD_SET_SMEM(ctx, rescale_tma_kernel, RT_SMEM);
+                size_t blocks = (count + RT_THREADS - 1) / RT_THREADS;
+                const size_t cap = (size_t)ctx->sm_count * 3;
+                if (blocks > cap) blocks = cap;
+                rescale_tma_kernel<<<(unsigned)blocks, RT_THREADS, RT_SMEM, ctx->stream>>>(cs, out_q, count, wmap, k);
+                H2SVD_LAUNCH_CHECK(ctx);
+                return H2SVD_OK;
+            }
+        }
+    }
     switch (ctx->tune.rescale_ch) {
         case 4: return launch_rescale_ch<4>(ctx, cs, count, k, out_q, out_wit);
         case 6: return launch_rescale_ch<6>(ctx, cs, count, k, out_q, out_wit);

@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "fr_fast.cuh"
+#include "tma_util.cuh"
 
 namespace h2svd {
 namespace rs {
@@ -89,6 +90,60 @@ struct WitnessStreamT {
         }
         __syncwarp();
         gwarp += fill;
+        fill = 0;
+        if (NBUF == 2) buf ^= 1;
+    }
+};
+
+// Same interface, TMA tensor stores: the 32 stripes a warp fills are 32 ROWS of one 2-D tensor [element][W * 32 bytes], so
+// a burst of CH witnesses per lane leaves as CH / 4 box stores (cp.async.bulk.tensor.2d: 32 rows x 128 bytes each) instead
+// of 32 separate bulk copies issued one after the other by the elected lane -- measured on the N = 1024 rescale, the
+// serialised issue of those copies (7.5 bursts x 32 copies per element) held the warps for about a third of their time.
+// Staging: per warp and buffer CH / 4 sub-tiles of 32 rows x 128 bytes in the 128-byte-swizzled layout the tensor map
+// declares (16-byte chunk c of row r lives at chunk c ^ (r & 7)): the lanes' stores are conflict-free.  Rows past the end
+// of the tensor (a partial last warp) and bytes past the end of a stripe (a partial last burst) are clipped by the TMA unit.
+template <int CH, int NBUF>
+struct WitnessStreamTma {
+    static_assert(CH % 4 == 0, "a burst is a whole number of 128-byte box columns");
+    static constexpr int SUB = CH / 4;                    // 128-byte sub-tiles per burst
+    static constexpr int WARP_BYTES = NBUF * SUB * 4096;  // staging per warp
+    uint8_t* tile0;          // this warp's staging area (1024-byte aligned)
+    const CUtensorMap* map;  // [count][W * 32 bytes], box 128 bytes x 32 rows, SWIZZLE_128B
+    int e0;                  // first element (tensor row) of this warp's 32
+    int wdone;               // witnesses of the current element already shipped
+    int lane, buf, fill;
+
+    __device__ __forceinline__ void begin(int first_element) {
+        e0 = first_element;
+        wdone = 0;
+    }
+    __device__ __forceinline__ void put(const Fr& v) {
+        uint8_t* t = tile0 + (buf * SUB + (fill >> 2)) * 4096 + lane * 128;
+        const int c = 2 * (fill & 3);
+        *reinterpret_cast<uint4*>(t + (((c) ^ (lane & 7)) << 4)) = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        *reinterpret_cast<uint4*>(t + (((c + 1) ^ (lane & 7)) << 4)) = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        if (++fill == CH) flush();
+    }
+    __device__ __forceinline__ void flush() {  // warp-uniform: every lane has the same `fill`
+        if (fill == 0) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (elect_one()) {
+            const int nsub = (fill + 3) >> 2;
+            for (int h = 0; h < nsub; h++) {
+                const uint32_t src = smem_addr(tile0 + (buf * SUB + h) * 4096);
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+                             "r"((wdone + 4 * h) * 32), "r"(e0), "r"(src)
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (NBUF == 2)
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        wdone += fill;
         fill = 0;
         if (NBUF == 2) buf ^= 1;
     }

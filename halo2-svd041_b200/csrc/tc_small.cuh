@@ -49,6 +49,81 @@ FR_HD bool small_biased(const Fr& am, uint32_t* t) {
     t[2] = (uint32_t)c;
     return pos || neg;
 }
+// The same test and value with a third of the multiplications (32 instead of 80 wide products per element; the operand
+// split kernels are bound by exactly this).  For a small positive x, am = x * 2^256 mod r means x * 2^256 = am + j * r
+// for the integer j = (x * 2^256 - am) / r < x * 2^256 / r < 2^73, and j is determined by j = -am * r^-1 (mod 2^96): three
+// Montgomery steps on the low three limbs only (8 products).  For a small negative x the same holds for r - am with
+// j' = -(r - am) * r^-1 = -1 - j (mod 2^96), the bitwise complement -- so the sign hypothesis costs nothing.  One exact
+// 3 x 8-limb product then gives S = w + j * r, and w is the Montgomery form of a small |x| IF AND ONLY IF the low 256 bits
+// of S vanish and S >> 256 < 2^70: no false positives (the identity proves it), no false negatives (the bound on j).
+FR_HD bool small_biased_fast(const Fr& am, uint32_t* t) {
+    const uint32_t r0 = modulus(0), r1 = modulus(1), r2 = modulus(2);
+    // j+ = m0 + m1 * 2^32 + m2 * 2^64: Montgomery multipliers of the low 96 bits
+    const uint32_t m0 = am.l[0] * INV32;
+    uint64_t c = (uint64_t)m0 * r0 + am.l[0];              // low word becomes 0
+    c = (c >> 32) + (uint64_t)m0 * r1 + am.l[1];
+    uint32_t t1 = (uint32_t)c;
+    c = (c >> 32) + (uint64_t)m0 * r2 + am.l[2];
+    uint32_t t2 = (uint32_t)c;
+    const uint32_t m1 = t1 * INV32;
+    c = (uint64_t)m1 * r0 + t1;
+    c = (c >> 32) + (uint64_t)m1 * r1 + t2;
+    t2 = (uint32_t)c;
+    const uint32_t m2 = t2 * INV32;
+    const bool pos = m2 < (1u << 9), neg = ~m2 < (1u << 9);
+    if (!pos && !neg) return false;
+    uint32_t w[8], j[3], m[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = modulus(i);
+    if (pos) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = am.l[i];
+        j[0] = m0; j[1] = m1; j[2] = m2;
+    } else {
+        sub_n<8>(w, m, am.l);                               // r - am: Montgomery form of |x|
+        j[0] = ~m0; j[1] = ~m1; j[2] = ~m2;
+    }
+    // S = w + j * r  (11 limbs); its low 8 limbs must vanish
+    uint32_t S[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++) S[i] = i < 8 ? w[i] : 0u;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        uint64_t cy = 0;
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            cy += (uint64_t)j[i] * m[l] + S[i + l];
+            S[i + l] = (uint32_t)cy;
+            cy >>= 32;
+        }
+#pragma unroll
+        for (int l = i + 8; l < 11; l++) {
+            cy += S[l];
+            S[l] = (uint32_t)cy;
+            cy >>= 32;
+        }
+    }
+    uint32_t low = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) low |= S[i];
+    if (low != 0 || (S[10] >> (SMALL_BITS - 64)) != 0) return false;
+    uint32_t s0 = S[8], s1 = S[9], s2 = S[10];             // |x|
+    if (!pos) {                                             // -|x| mod 2^96
+        uint64_t n = (uint64_t)(~s0) + 1u;
+        s0 = (uint32_t)n;
+        n = (uint64_t)(~s1) + (n >> 32);
+        s1 = (uint32_t)n;
+        n = (uint64_t)(~s2) + (n >> 32);
+        s2 = (uint32_t)n;
+    }
+    c = (uint64_t)s0 + SMALL_C0;
+    t[0] = (uint32_t)c;
+    c = (uint64_t)s1 + SMALL_C1 + (c >> 32);
+    t[1] = (uint32_t)c;
+    c = (uint64_t)s2 + SMALL_C2 + (c >> 32);
+    t[2] = (uint32_t)c;
+    return true;
+}
 // s8 bit pattern of balanced digit p (0 <= p < 9) of a value biased by small_biased
 FR_HD uint32_t small_digit_bits(const uint32_t* t, int p) { return ((t[p >> 2] >> ((p & 3) * 8)) & 0xffu) ^ 0x80u; }
 

@@ -105,7 +105,7 @@ class Handle:
 
     # ---- triage / tuning switches (per handle; not part of the public header) ----
     TUNE_KEYS = ("matmul_tc", "matmul_small", "matmul_small_width", "matmul_karatsuba", "matmul_streamk", "matmul_variant", "fuse_rescale",
-                 "rescale_generic", "matvec_warp_kernel", "matvec_seg", "rescale_ch")
+                 "rescale_generic", "matvec_warp_kernel", "matvec_seg", "rescale_ch", "rescale_tma")
 
     def tune(self, key: str, value: int) -> None:
         """matmul_tc / matmul_small: -1 auto, 0 never, 1 always; matmul_karatsuba: -1 auto, 0 schoolbook, 1..3 variants;
@@ -273,6 +273,12 @@ class Handle:
     def microbench_imad(self, kind: int, iters: int = 2000) -> float:
         v = ct.c_double()
         _ffi.check(self._lib.h2svd_microbench_imad(self._h, kind, iters, ct.byref(v)))
+        return v.value
+
+    def microbench_hbm(self, kind: int, nbytes: int = 2 << 30) -> float:
+        """GB/s of a copy (0), streaming writes (1), bulk writes from shared memory (2) or reads (3) over nbytes."""
+        v = ct.c_double()
+        _ffi.check(self._lib.h2svd_microbench_hbm(self._h, kind, nbytes, ct.byref(v)))
         return v.value
 
     def microbench_tensor_i8(self, kind: int = 0, min_seconds: float = 0.0) -> float:

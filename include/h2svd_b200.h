@@ -346,6 +346,11 @@ void h2svd_host_fr_mul(const h2svd_fr *a, const h2svd_fr *b, h2svd_fr *out);
  * inner loop issues them, 3 = full 8x8 lazy multiply-accumulate (64 IMAD.WIDE + 16 IADD3.X).
  * Writes achieved multiply instructions per second (thread-level ops) to *ops_per_s. */
 int h2svd_microbench_imad(h2svd_ctx *ctx, int kind, int iters, double *ops_per_s);
+/* HBM micro-benchmark over `bytes` of the handle's workspace, best of five launches after a warm-up: kind 0 = copy (read +
+ * write, what MEASURED_PEAKS.json hbm_gbs measures), 1 = write-only streaming 16-byte stores, 2 = write-only 256-byte bulk
+ * stores from shared memory (the witness stream's path), 3 = read-only.  The witness kernels are 97 % writes: their
+ * roofline is the WRITE figure, reported beside the copy figure.  Writes GB/s (bytes moved / time). */
+int h2svd_microbench_hbm(h2svd_ctx *ctx, int kind, size_t bytes, double *gb_per_s);
 /* Tensor-pipe micro-benchmark, the measured denominator of the tensor-core mat-mul engines: back-to-back
  * tcgen05.mma.kind::i8 of the real kernels' shape with operands resident in shared memory, one CTA per SM.
  * kind 0 = unsigned, M128 N256 K32 (full-width engine); 1 = signed, M128 N240 K32 (small-operand engine).

@@ -47,6 +47,18 @@ int hs_small_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {
     *o = fr::signed6_to_mont(T);
     return 1;
 }
+// the cheap small-operand test must agree with the full-reduction one, bit for bit (returns -1 on any difference)
+int hs_small_fast_vs_full(const Fr* a, size_t n) {
+    int nsmall = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t t0[3] = {0, 0, 0}, t1[3] = {0, 0, 0};
+        const bool ok0 = fr::small_biased(a[i], t0), ok1 = fr::small_biased_fast(a[i], t1);
+        if (ok0 != ok1) return -1;
+        if (ok0 && (t0[0] != t1[0] || t0[1] != t1[1] || t0[2] != t1[2])) return -1;
+        nsmall += ok0 ? 1 : 0;
+    }
+    return nsmall;
+}
 int hs_small_ok(const Fr* a) { uint32_t t[3]; return fr::small_biased(*a, t) ? 1 : 0; }
 // Karatsuba lazy dot product exactly as the Karatsuba mat-mul accumulates it (fr_kara.cuh)
 void hs_kara_dot(const Fr* a, const Fr* b, size_t k, Fr* o) {

@@ -199,3 +199,24 @@ def test_small_operand_range_detection(shim):
     for v, ok in [(0, 1), (lim - 1, 1), (-(lim - 1), 1), (lim, 0), (-lim, 0), (lim + 5, 0), (R // 2, 0), (-(R // 2), 0),
                   ((1 << 200) + 3, 0), (1 << 96, 0), (-(1 << 96), 0)]:
         assert shim.hs_small_ok(P(_mont_signed([v]))) == ok, v
+
+
+def test_small_operand_fast_detection_agrees_with_full_reduction(shim):
+    """tc_small.cuh small_biased_fast (32 products: three Montgomery steps + one 3 x 8-limb product) == small_biased (full
+    reduction) on small values of both signs, the range boundaries, near-misses and arbitrary field elements."""
+    rng = random.Random(99)
+    lim = 1 << 70
+    small = [0, 1, -1, lim - 1, -(lim - 1), 2, -2, (1 << 64), -(1 << 64), (1 << 69) + 12345, 255, -256]
+    small += [rng.randrange(-lim + 1, lim) for _ in range(3000)]
+    near = [lim, -lim, lim + 1, -(lim + 1), (1 << 71), -(1 << 71), (1 << 72) + 5, -(1 << 73), (1 << 96), (1 << 95) - 1, R // 2]
+    big = [rng.randrange(R) for _ in range(3000)]
+    # Montgomery forms of values whose low multipliers happen to look small-ish: x * R with x just above the range
+    near += [rng.randrange(lim, lim << 6) * rng.choice((1, -1)) for _ in range(500)]
+    arr = _mont_signed(small)
+    assert shim.hs_small_fast_vs_full(P(arr), len(small)) == len(small)
+    arr = _mont_signed(near)
+    assert shim.hs_small_fast_vs_full(P(arr), len(near)) == 0
+    arr = raw_limbs(big)                       # raw limb patterns: arbitrary Montgomery-form elements
+    assert shim.hs_small_fast_vs_full(P(arr), len(big)) == 0
+    mixed = _mont_signed(small[:50] + near[:50])
+    assert shim.hs_small_fast_vs_full(P(mixed), 100) == 50

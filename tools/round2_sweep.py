@@ -48,9 +48,16 @@ c = fr(n, n)
 h.fr_matmul_dev(a, b, c)
 h.sync()
 print("mat-mul call (split + mm), quantized:", timed(lambda: h.fr_matmul_dev(a, b, c)), h.last_matmul_engine())
-a128 = a[:128].contiguous()
-c128 = fr(128, n)
-print("mat-mul call 128-row slab, quantized:", timed(lambda: h.fr_matmul_dev(a128, b, c128)))
+for rows in (128, 256, 512, 1024):
+    ar, cr = a[:rows].contiguous(), fr(rows, n)
+    res = []
+    for width in (0, 8, 16, 24):
+        h.tune("matmul_small_width", width)
+        res.append((width, round(timed(lambda: h.fr_matmul_dev(ar, b, cr))[0], 1)))
+    h.tune("matmul_small_width", 0)
+    print(f"mat-mul call {rows}-row slab, quantized, by tile width (0 = cost model): {res}")
+for kind, name in ((0, "copy"), (1, "write 16B streaming"), (2, "write 256B bulk from smem"), (3, "read")):
+    print(f"HBM {name}: {h.microbench_hbm(kind):.0f} GB/s")
 W = h.rescale_witness_count(63, 19)
 q, wit = fr(n, n), fr(n * n, W)
 ref = None
