@@ -1057,7 +1057,7 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
         {"matmul_variant", &ctx->tune.variant},    {"fuse_rescale", &ctx->tune.fuse_rescale},
         {"rescale_generic", &ctx->tune.rescale_generic}, {"matvec_warp_kernel", &ctx->tune.matvec_warp},
         {"matvec_seg", &ctx->tune.matvec_seg},       {"rescale_ch", &ctx->tune.rescale_ch},
-        {"rescale_tma", &ctx->tune.rescale_tma},
+        {"rescale_store", &ctx->tune.rescale_store},
     };
     for (const auto& e : keys)
         if (strcmp(e.name, key) == 0) {

@@ -40,7 +40,7 @@ struct h2svd_ctx {
         int variant = 0;          // schoolbook tile variant
         int fuse_rescale = 0;     // 1: rescale witnesses from the tensor-core epilogue (experimental)
         int rescale_generic = 0;  // 1: force the generic (unstaged) rescale kernel
-        int rescale_tma = 1;      // witness stream of the rescale kernel through TMA tensor stores (0: per-row bulk copies)
+        int rescale_store = 0;    // witness stream of the rescale kernel: 0 per-row bulk copies, 1 TMA tensor stores, 2 coalesced STG
         int rescale_ch = 8;       // witnesses per bulk store of the staged rescale kernel: 4, 6 or 8
         int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel
         int matvec_seg = -1;      // several-warps-per-row mat-vec prefix kernel: -1 auto (few long rows), 0 never, 1 always

@@ -184,6 +184,35 @@ rescale_tma_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, size_t cou
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// The same kernel with plain coalesced stores for the witness stream (WitnessStreamStg), one staging row per lane.
+constexpr int RG_THREADS = 128;
+constexpr int RG_CH = 8;
+using RgStream = WitnessStreamStg<RG_CH>;
+constexpr size_t RG_SMEM = (size_t)RG_THREADS * RgStream::ROW_U4 * sizeof(uint4);   // 34 KB
+__global__ void __launch_bounds__(RG_THREADS, 4)
+rescale_stg_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
+                   const __grid_constant__ RescaleConsts k) {
+    extern __shared__ __align__(16) uint4 rs_stage[];
+    const int lane = threadIdx.x & 31;
+    RgStream ws;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RgStream::ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RgStream::ROW_U4;
+    ws.W = k.p.W;
+    ws.lane = lane;
+    ws.fill = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < count; e0 += stride) {
+        const size_t left = count - e0;
+        ws.valid = left < 32 ? (int)left : 32;
+        ws.gwarp = out_wit + e0 * (size_t)k.p.W;
+        const bool live = lane < ws.valid;
+        const size_t e = live ? e0 + lane : count - 1;
+        const Fr am = ldg_fr(cs + e);
+        const Fr q = rescale_element(ws, k, am);
+        if (live) st_fr(out_q + e, q);
+    }
+}
+
 // check_abs_less_than(x, bnd) (reference src/matrix/mod.rs:425-437), optionally of a difference x - y
 // (check_mat_diff :441-459): witnesses [x - y]?, t = d + (bnd - 1), check_big_less_than_safe(t, 2*bnd - 1).
 __global__ void __launch_bounds__(RS_THREADS)
@@ -348,7 +377,16 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     }
     RescaleConsts k;
     make_rescale_consts(P, lb, S, A, &k);
-    if (ctx->tune.rescale_tma != 0 && p.W >= 4 && count < (1ull << 31)) {
+    if (ctx->tune.rescale_store == 2) {
+        H2SVD_SET_SMEM(ctx, rescale_stg_kernel, RG_SMEM);
+        size_t blocks = (count + RG_THREADS - 1) / RG_THREADS;
+        const size_t cap = (size_t)ctx->sm_count * 4;
+        if (blocks > cap) blocks = cap;
+        rescale_stg_kernel<<<(unsigned)blocks, RG_THREADS, RG_SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
+        H2SVD_LAUNCH_CHECK(ctx);
+        return H2SVD_OK;
+    }
+    if (ctx->tune.rescale_store == 1 && p.W >= 4 && count < (1ull << 31)) {
         // witness stream as a 2-D tensor [count][W * 32 bytes]; one box = 32 elements x 128 bytes
         tma_encode_fn encode = tma_encoder();
         if (encode) {

@@ -95,6 +95,42 @@ struct WitnessStreamT {
     }
 };
 
+// Same interface, plain coalesced stores: the warp reads its 32 staged rows back 16 bytes per lane -- half a warp per
+// 256-byte row -- and writes them with streaming 16-byte stores (STG.128), i.e. every store instruction covers two
+// contiguous 256-byte pieces of two stripes.  No copy engine, no async proxy: the staging rows are free again as soon as
+// the loads have returned, so one buffer per lane is enough (half the shared memory of the bulk-copy stream).
+template <int CH>
+struct WitnessStreamStg {
+    static constexpr int ROW_U4 = CH * 2 + 1;  // staging row in 16-byte units: CH witnesses + 16 B skew (conflict-free)
+    uint4* row0;       // this lane's staging row
+    uint4* warp_row0;  // lane 0's staging row
+    Fr* gwarp;         // out_wit position of lane 0's element, advanced by every flush
+    int W, valid;      // stripe distance in witnesses; lanes of this warp that hold a real element
+    int lane, fill;
+
+    __device__ __forceinline__ void put(const Fr& v) {
+        uint4* s = row0 + 2 * fill;
+        s[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        s[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        if (++fill == CH) flush();
+    }
+    __device__ __forceinline__ void flush() {  // warp-uniform: every lane has the same `fill`
+        if (fill == 0) return;
+        __syncwarp();
+        const int chunk = lane & 15, half = lane >> 4;
+        if (chunk < 2 * fill) {
+#pragma unroll 4
+            for (int r = half; r < valid; r += 2) {
+                const uint4 v = warp_row0[r * ROW_U4 + chunk];
+                __stcs(reinterpret_cast<uint4*>(gwarp + (size_t)r * W) + chunk, v);
+            }
+        }
+        __syncwarp();  // the rows are rewritten by the next burst
+        gwarp += fill;
+        fill = 0;
+    }
+};
+
 // Same interface, TMA tensor stores: the 32 stripes a warp fills are 32 ROWS of one 2-D tensor [element][W * 32 bytes], so
 // a burst of CH witnesses per lane leaves as CH / 4 box stores (cp.async.bulk.tensor.2d: 32 rows x 128 bytes each) instead
 // of 32 separate bulk copies issued one after the other by the elected lane -- measured on the N = 1024 rescale, the

@@ -375,9 +375,10 @@ def test_small_operand_engine_every_tile_width(handle, width, n, k, m):
 
 
 @pytest.mark.parametrize("P,lb,S,A", [(63, 19, -1, -1), (32, 19, -1, -1), (20, 32, -1, -1), (42, 12, -1, -1), (63, 19, 189, 190)])
-def test_rescale_tma_store_path_equals_bulk_copy_path(handle, P, lb, S, A):
-    """The witness stream through TMA tensor stores (default) and through per-row bulk copies: same bytes, incl. stripe
-    widths that are not a multiple of the 128-byte box (partial last burst, clipped by the TMA unit) and a partial last warp."""
+def test_rescale_store_paths_write_the_same_bytes(handle, P, lb, S, A):
+    """The witness stream through per-row bulk copies (0), TMA tensor stores (1) and coalesced 16-byte stores (2): same
+    bytes, incl. stripe widths that are not a multiple of the 128-byte TMA box (partial last burst, clipped by the TMA unit)
+    and a partial last warp; nothing is written past the end."""
     import torch
     rng = np.random.default_rng(P + lb)
     count = 1000 + 37
@@ -387,16 +388,16 @@ def test_rescale_tma_store_path_equals_bulk_copy_path(handle, P, lb, S, A):
     W = handle.rescale_witness_count(P, lb, S, A)
     tcs = torch.from_numpy(cs.view(np.int64)).to(dev)
     outs = []
-    for tma in (1, 0):
+    for store in (0, 1, 2):
         q = torch.full((count, 4), -1, dtype=torch.int64, device=dev)
         wit = torch.full((count + 3, W, 4), -1, dtype=torch.int64, device=dev)     # 3 guard stripes after the end
         torch.cuda.synchronize()
         try:
-            handle.tune("rescale_tma", tma)
+            handle.tune("rescale_store", store)
             handle.rescale_witness_dev(tcs, count, P, lb, q, wit, S, A)
             handle.sync()
         finally:
-            handle.tune("rescale_tma", 1)
+            handle.tune("rescale_store", 0)
         assert bool((wit[count:] == -1).all().item()), "wrote past the end of the witness array"
         outs.append((q.cpu().numpy().view(np.uint64), wit[:count].cpu().numpy().view(np.uint64)))
     eq, _, ewit = corac.rescale_witness(cs, P, lb, S, A, threads=0)

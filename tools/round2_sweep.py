@@ -61,15 +61,15 @@ for kind, name in ((0, "copy"), (1, "write 16B streaming"), (2, "write 256B bulk
 W = h.rescale_witness_count(63, 19)
 q, wit = fr(n, n), fr(n * n, W)
 ref = None
-for ch in (8, 6, 4):
-    h.tune("rescale_ch", ch)
+for store, name in ((0, "bulk copies"), (1, "TMA tensor stores"), (2, "coalesced STG.128")):
+    h.tune("rescale_store", store)
     wit.fill_(-1)
     t = timed(lambda: h.rescale_witness_dev(c, n * n, 63, 19, q, wit))
     if ref is None:
         ref = wit.clone()
     same = bool((wit == ref).all().item())
-    print(f"rescale ch={ch}: median {t[0]:.1f} us  min {t[1]:.1f} us  -> {n * n * 32 * (2 + W) / t[0] / 1e3:.0f} GB/s  same_bytes={same}")
-h.tune("rescale_ch", 8)
+    print(f"rescale {name}: median {t[0]:.1f} us  min {t[1]:.1f} us  -> {n * n * 32 * (2 + W) / t[0] / 1e3:.0f} GB/s  same_bytes={same}")
+h.tune("rescale_store", 0)
 del ref
 powers = fr(n)
 g = torch.tensor([[0x1234567, 0x89ABCDEF, 0x13579BDF, 0x2468ACE]], dtype=torch.int64, device=dev)
