@@ -273,6 +273,67 @@ FR_HD Fr mont_mul_fast(const Fr& a, const Fr& b) {
     return o;
 }
 
+// Two independent Montgomery products with their carry chains INTERLEAVED in program order: one product is a single long
+// dependent chain per column set (every row4 waits for the previous one through the carry predicate and the accumulator
+// registers), so a warp issues at most ~2 IMAD.WIDE per chain latency; two products give the scheduler four independent
+// chains.  Same arithmetic as mont_mul_fast, element for element.
+FR_HD void mont_mul_fast_x2(const Fr& a0, const Fr& b0, const Fr& a1, const Fr& b1, Fr& o0, Fr& o1) {
+    uint64_t E0[6] = {0, 0, 0, 0, 0, 0}, O0[5] = {0, 0, 0, 0, 0};
+    uint64_t E1[6] = {0, 0, 0, 0, 0, 0}, O1[5] = {0, 0, 0, 0, 0};
+    uint32_t x0 = 0, ca0 = 0, cb0 = 0, x1 = 0, ca1 = 0, cb1 = 0;
+    const uint32_t r0 = modulus(0), r1 = modulus(1), r2 = modulus(2), r3 = modulus(3), r4 = modulus(4),
+                   r5 = modulus(5), r6 = modulus(6), r7 = modulus(7);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        row4_fold(&E0[0], a0.l[0], a0.l[2], a0.l[4], a0.l[6], b0.l[i], x0, ca0, cb0);
+        row4_fold(&E1[0], a1.l[0], a1.l[2], a1.l[4], a1.l[6], b1.l[i], x1, ca1, cb1);
+        row4(&O0[0], a0.l[1], a0.l[3], a0.l[5], a0.l[7], b0.l[i]);
+        row4(&O1[0], a1.l[1], a1.l[3], a1.l[5], a1.l[7], b1.l[i]);
+        const uint32_t m00 = lo32(E0[0]) * INV32, m01 = lo32(E1[0]) * INV32;
+        row4(&E0[0], r0, r2, r4, r6, m00);
+        row4(&E1[0], r0, r2, r4, r6, m01);
+        row4(&O0[0], r1, r3, r5, r7, m00);
+        row4(&O1[0], r1, r3, r5, r7, m01);
+        row4(&O0[0], a0.l[0], a0.l[2], a0.l[4], a0.l[6], b0.l[i + 1]);
+        row4(&O1[0], a1.l[0], a1.l[2], a1.l[4], a1.l[6], b1.l[i + 1]);
+        row4(&E0[1], a0.l[1], a0.l[3], a0.l[5], a0.l[7], b0.l[i + 1]);
+        row4(&E1[1], a1.l[1], a1.l[3], a1.l[5], a1.l[7], b1.l[i + 1]);
+        const uint32_t m10 = (hi32(E0[0]) + lo32(O0[0])) * INV32, m11 = (hi32(E1[0]) + lo32(O1[0])) * INV32;
+        row4(&O0[0], r0, r2, r4, r6, m10);
+        row4(&O1[0], r0, r2, r4, r6, m11);
+        row4(&E0[1], r1, r3, r5, r7, m10);
+        row4(&E1[1], r1, r3, r5, r7, m11);
+        ca0 = hi32(E0[0]); cb0 = lo32(O0[0]); x0 = hi32(O0[0]);
+        ca1 = hi32(E1[0]); cb1 = lo32(O1[0]); x1 = hi32(O1[0]);
+#pragma unroll
+        for (int p = 0; p < 5; p++) {
+            E0[p] = E0[p + 1];
+            E1[p] = E1[p + 1];
+        }
+        E0[5] = 0;
+        E1[5] = 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            O0[p] = O0[p + 1];
+            O1[p] = O1[p + 1];
+        }
+        O0[4] = 0;
+        O1[4] = 0;
+    }
+    {
+        const uint32_t ev[8] = {lo32(E0[0]), hi32(E0[0]), lo32(E0[1]), hi32(E0[1]), lo32(E0[2]), hi32(E0[2]), lo32(E0[3]), hi32(E0[3])};
+        const uint32_t ov[8] = {x0, lo32(O0[0]), hi32(O0[0]), lo32(O0[1]), hi32(O0[1]), lo32(O0[2]), hi32(O0[2]), lo32(O0[3])};
+        add8_carry_in(o0.l, ev, ov, ca0, cb0);
+        cond_sub_r(o0.l);
+    }
+    {
+        const uint32_t ev[8] = {lo32(E1[0]), hi32(E1[0]), lo32(E1[1]), hi32(E1[1]), lo32(E1[2]), hi32(E1[2]), lo32(E1[3]), hi32(E1[3])};
+        const uint32_t ov[8] = {x1, lo32(O1[0]), hi32(O1[0]), lo32(O1[1]), hi32(O1[1]), lo32(O1[2]), hi32(O1[2]), lo32(O1[3])};
+        add8_carry_in(o1.l, ev, ov, ca1, cb1);
+        cond_sub_r(o1.l);
+    }
+}
+
 // Single-limb Montgomery step: l * c * 2^-32 mod r, canonical (l any u32, c canonical).
 // With c = x * 2^256 * 2^32 mod r this yields the Montgomery form of l * x in 16 IMAD.WIDE + 1 IMAD.
 FR_HD Fr mont_mul_small(uint32_t l, const Fr& c) {

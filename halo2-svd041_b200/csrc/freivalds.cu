@@ -199,6 +199,41 @@ __device__ __forceinline__ void mt_stage(uint4* buf, const Fr* src, int count, i
     }
 }
 
+// pass 1 of a tile: products and un-offset running sums of this lane's MT_EPL consecutive elements (written over the a
+// tile); returns the lane total.  X2: the products are taken two at a time with interleaved carry chains.
+template <bool X2>
+__device__ __forceinline__ Fr mt_pass1(uint4* sa, const uint4* sv, int lane, int nseg) {
+    Fr run = fr::zero();
+    if (X2) {
+#pragma unroll
+        for (int i = 0; i < MT_EPL; i += 2) {
+            const int e = MT_EPL * lane + i;
+            if (e + 1 < nseg) {
+                Fr p0, p1;
+                fr::mont_mul_fast_x2(mt_ld(sa, e), mt_ld(sv, e), mt_ld(sa, e + 1), mt_ld(sv, e + 1), p0, p1);
+                run = fr::add_fast(run, p0);
+                mt_st(sa, e, run);
+                run = fr::add_fast(run, p1);
+                mt_st(sa, e + 1, run);
+            } else if (e < nseg) {
+                run = fr::add_fast(run, fr::mont_mul_fast(mt_ld(sa, e), mt_ld(sv, e)));
+                mt_st(sa, e, run);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < MT_EPL; i++) {
+            const int e = MT_EPL * lane + i;
+            if (e < nseg) {
+                run = fr::add_fast(run, fr::mont_mul_fast(mt_ld(sa, e), mt_ld(sv, e)));
+                mt_st(sa, e, run);
+            }
+        }
+    }
+    return run;
+}
+
+template <bool X2>
 __global__ void __launch_bounds__(MT_WARPS * 32)
 mat_vec_prefix_tile_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len,
                            size_t v_row_stride) {
@@ -231,15 +266,7 @@ mat_vec_prefix_tile_kernel(const __grid_constant__ MvJobs jobs, const Fr* __rest
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             // pass 1: products and un-offset running sums of this lane's four consecutive elements
-            Fr run = fr::zero();
-#pragma unroll
-            for (int i = 0; i < MT_EPL; i++) {
-                const int e = MT_EPL * lane + i;
-                if (e < nseg) {
-                    run = fr::add_fast(run, fr::mont_mul_fast(mt_ld(sa, e), mt_ld(sv, e)));
-                    mt_st(sa, e, run);
-                }
-            }
+            const Fr run = mt_pass1<X2>(sa, sv, lane, nseg);
             const Fr incl = warp_scan_fr<32>(run, lane);
             Fr off = shfl_up_fr(incl, 1);  // exclusive over the lanes
             if (lane == 0) off = fr::zero();
@@ -266,7 +293,7 @@ mat_vec_prefix_tile_kernel(const __grid_constant__ MvJobs jobs, const Fr* __rest
 // tile-local running sums exactly like the tile kernel; the SEGS tile totals of a round meet in shared memory (one
 // __syncthreads per round, double-buffered by round parity), every warp adds the totals of the tiles before its own to
 // its lane offsets, and the second, coalesced pass stores.  Same arithmetic per element, SEGS times the parallelism.
-template <int SEGS>
+template <int SEGS, bool X2>
 __global__ void __launch_bounds__(SEGS * 32)
 mat_vec_prefix_seg_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len, size_t v_row_stride) {
     extern __shared__ __align__(128) uint4 mt_smem[];
@@ -301,15 +328,7 @@ mat_vec_prefix_seg_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restr
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
-                Fr run = fr::zero();
-#pragma unroll
-                for (int i = 0; i < MT_EPL; i++) {
-                    const int e = MT_EPL * lane + i;
-                    if (e < nseg) {
-                        run = fr::add_fast(run, fr::mont_mul_fast(mt_ld(sa, e), mt_ld(sv, e)));
-                        mt_st(sa, e, run);
-                    }
-                }
+                const Fr run = mt_pass1<X2>(sa, sv, lane, nseg);
                 incl = warp_scan_fr<32>(run, lane);
                 off = shfl_up_fr(incl, 1);  // exclusive over the lanes
                 if (lane == 0) off = fr::zero();
@@ -447,16 +466,21 @@ static int launch_mv(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, cons
     return H2SVD_OK;
 }
 
-template <int SEGS>
-static int launch_mv_seg(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, const Fr* v, size_t len, size_t vs) {
+template <int SEGS, bool X2>
+static int launch_mv_seg_x(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, const Fr* v, size_t len, size_t vs) {
     constexpr size_t smem = (size_t)SEGS * MT_WARP_U4 * sizeof(uint4) + 2 * SEGS * sizeof(Fr);
-    H2SVD_SET_SMEM(ctx, mat_vec_prefix_seg_kernel<SEGS>, smem);
+    H2SVD_SET_SMEM(ctx, (mat_vec_prefix_seg_kernel<SEGS, X2>), smem);
     size_t blocks = total_rows;
     const size_t cap = (size_t)ctx->sm_count * 16;   // grid-stride beyond a few waves of resident CTAs
     if (blocks > cap) blocks = cap;
-    mat_vec_prefix_seg_kernel<SEGS><<<(unsigned)blocks, SEGS * 32, smem, ctx->stream>>>(jobs, v, len, vs);
+    mat_vec_prefix_seg_kernel<SEGS, X2><<<(unsigned)blocks, SEGS * 32, smem, ctx->stream>>>(jobs, v, len, vs);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
+}
+template <int SEGS>
+static int launch_mv_seg(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, const Fr* v, size_t len, size_t vs) {
+    return ctx->tune.matvec_x2 ? launch_mv_seg_x<SEGS, true>(ctx, jobs, total_rows, v, len, vs)
+                               : launch_mv_seg_x<SEGS, false>(ctx, jobs, total_rows, v, len, vs);
 }
 
 static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_t len, size_t vs) {
@@ -473,11 +497,16 @@ static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_
     if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && ctx->tune.matvec_warp == 0) {
         // one warp per row, consecutive elements per lane (mat_vec_prefix_tile_kernel); needs enough rows to
         // give every SM a few warps, otherwise the row-splitting kernel below is the better fit
-        H2SVD_SET_SMEM(ctx, mat_vec_prefix_tile_kernel, MT_SMEM);
         size_t blocks = (total_rows + MT_WARPS - 1) / MT_WARPS;
         const size_t cap = (size_t)ctx->sm_count * 5;  // 5 CTAs (96 regs) of 4 independent warps per SM, grid-stride beyond
         if (blocks > cap) blocks = cap;
-        mat_vec_prefix_tile_kernel<<<(unsigned)blocks, MT_WARPS * 32, MT_SMEM, ctx->stream>>>(jobs, v, len, vs);
+        if (ctx->tune.matvec_x2) {
+            H2SVD_SET_SMEM(ctx, mat_vec_prefix_tile_kernel<true>, MT_SMEM);
+            mat_vec_prefix_tile_kernel<true><<<(unsigned)blocks, MT_WARPS * 32, MT_SMEM, ctx->stream>>>(jobs, v, len, vs);
+        } else {
+            H2SVD_SET_SMEM(ctx, mat_vec_prefix_tile_kernel<false>, MT_SMEM);
+            mat_vec_prefix_tile_kernel<false><<<(unsigned)blocks, MT_WARPS * 32, MT_SMEM, ctx->stream>>>(jobs, v, len, vs);
+        }
         H2SVD_LAUNCH_CHECK(ctx);
         return H2SVD_OK;
     }

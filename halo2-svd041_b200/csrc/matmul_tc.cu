@@ -65,6 +65,10 @@ struct TcSmallT {
     static constexpr int LA = fr::SMALL_DIGITS, LB = LB_, BJ = BJ_, SA = SA_, SB = 2, KB_PASS = 64;
     static constexpr bool SIGNED = true;
 };
+// Stage counts: measured (tools/tc_timeline.py), a 128 x 24 tile's MMA phase takes 22-25 us against 19 us of MMAs at the
+// measured pipe rate, with 7 AND with 10 A stages alike -- not a latency / bytes-in-flight problem.  The SS-mode MMAs read
+// (128 + N) x 32 bytes of operands from shared memory per N / 2 clocks (98 B/clk at N = 240, 121 at N = 144, 166 at N = 80)
+// while TMA writes the next stages into the same memory (40-64 B/clk): together above the SM's 128 B/clk.
 using TcSmall = TcSmallT<24, fr::SMALL_DIGITS + 1, 7>;     // 7 x 16 KB + 2 x 30 KB of stages
 using TcSmall16 = TcSmallT<16, fr::SMALL_DIGITS, 8>;       // 8 x 16 KB + 2 x 18 KB
 using TcSmall8 = TcSmallT<8, fr::SMALL_DIGITS + 1, 8>;     // 8 x 16 KB + 2 x 10 KB
@@ -81,6 +85,8 @@ struct TcD {
     static_assert(NMMA % 16 == 0 && NMMA >= 16 && NMMA <= 256, "MMA N for M = 128");
     static_assert(TCOLS <= 512 && C::BJ % 8 == 0 && CW % 2 == 0, "TMEM columns / epilogue mapping");
     static_assert(B_BYTES % 1024 == 0, "B stages must keep the 1024-byte swizzle-atom alignment");
+    static_assert((size_t)C::SA * TC_A_BYTES + (size_t)C::SB * B_BYTES + 256 + 1024 <= 232448, "stages exceed the SM's shared memory");
+    static_assert(16 * C::SA + 16 * C::SB + 24 <= 256, "barrier block");
 };
 // fused rescale (full-width engine only): every epilogue warp stages 4 witnesses (128 B + 16 B skew) per lane, single-buffered
 using TcWitnessStream = rs::WitnessStreamT<TC_CH_CFG, 1>;

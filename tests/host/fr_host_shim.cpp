@@ -29,6 +29,9 @@ void hs_add_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0;
 void hs_sub_fast(const Fr* a, const Fr* b, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::sub_fast(a[i], b[i]); }
 void hs_to_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::to_mont_fast(a[i]); }
 void hs_from_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::from_mont_fast(a[i]); }
+void hs_mont_mul_fast_x2(const Fr* a, const Fr* b, Fr* o, size_t n) {   // pairs (2i, 2i+1)
+    for (size_t i = 0; i + 1 < n; i += 2) fr::mont_mul_fast_x2(a[i], b[i], a[i + 1], b[i + 1], o[i], o[i + 1]);
+}
 void hs_mont_reduce_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::mont_reduce_fast(a[i]); }
 // Small-operand tensor-core engine, arithmetic only (tc_small.cuh): balanced digits of every operand, the 17 signed
 // diagonal sums a tile of s8 x s8 MMAs would leave in TMEM, signed carry, one Montgomery encode.  Returns 0 when an

@@ -220,3 +220,12 @@ def test_small_operand_fast_detection_agrees_with_full_reduction(shim):
     assert shim.hs_small_fast_vs_full(P(arr), len(big)) == 0
     mixed = _mont_signed(small[:50] + near[:50])
     assert shim.hs_small_fast_vs_full(P(mixed), 100) == 50
+
+
+def test_mont_mul_fast_x2_matches_bigint(shim):
+    vals = _vals()
+    vals = vals[: len(vals) // 2 * 2]
+    a, b = raw_limbs(vals), raw_limbs(vals[::-1])
+    o = np.zeros_like(a)
+    shim.hs_mont_mul_fast_x2(P(a), P(b), P(o), len(vals))
+    assert unraw(o) == [x * y * po.MONT_RINV % R for x, y in zip(vals, vals[::-1])]

@@ -403,3 +403,28 @@ def test_rescale_store_paths_write_the_same_bytes(handle, P, lb, S, A):
     eq, _, ewit = corac.rescale_witness(cs, P, lb, S, A, threads=0)
     for q, wit in outs:
         assert _eq(q, eq) and _eq(wit, ewit)
+
+
+@pytest.mark.parametrize("x2", [0, 1])
+@pytest.mark.parametrize("seg", [0, 1])
+@pytest.mark.parametrize("rows,ln", [(3, 300), (700, 131), (16, 1024), (600, 129), (2, 2100)])
+def test_mat_vec_prefix_interleaved_products_match_oracle(handle, x2, seg, rows, ln):
+    """mont_mul_fast_x2 (two Montgomery products with interleaved carry chains) inside both mat-vec prefix kernels: odd
+    tile tails exercise the single-product remainder."""
+    import torch
+    rng = np.random.default_rng(rows + ln + seg)
+    a, v = random_fr(rng, rows, ln), random_fr(rng, ln)
+    dev = torch.device("cuda", handle.device)
+    ta = torch.from_numpy(a.view(np.int64)).to(dev)
+    tv = torch.from_numpy(v.view(np.int64)).to(dev)
+    out = torch.full((rows, ln, 4), -1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    try:
+        handle.tune("matvec_x2", x2)
+        handle.tune("matvec_seg", seg)
+        handle.mat_vec_prefix_dev(ta, tv, out)
+        handle.sync()
+    finally:
+        handle.tune("matvec_x2", 1)
+        handle.tune("matvec_seg", -1)
+    assert _eq(out.cpu().numpy().view(np.uint64), corac.mat_vec_prefix(a, v, threads=0))

@@ -77,24 +77,27 @@ h.gamma_powers_dev(g, n, powers)
 out, tot = fr(n, n), fr(n)
 for rows in (1024, 128):
     base = None
-    for seg in (0, 1):
+    for seg, x2 in ((0, 0), (1, 0), (0, 1), (1, 1)):
         h.tune("matvec_seg", seg)
+        h.tune("matvec_x2", x2)
         o = out[:rows]
         o.fill_(-1)
         t = timed(lambda: h.mat_vec_prefix_dev(c[:rows], powers, o, tot[:rows]))
         if base is None:
             base = o.clone()
-        print(f"mat_vec_prefix {rows}x1024 seg={seg}: median {t[0]:.1f} us min {t[1]:.1f} us same={bool((o == base).all().item())}")
+        print(f"mat_vec_prefix {rows}x1024 seg={seg} x2={x2}: median {t[0]:.1f} us min {t[1]:.1f} us same={bool((o == base).all().item())}")
 x, s, o2 = quant(4096, 1024, 32), quant(4096, 1024, 32), fr(4096, 1024)
 base = None
-for seg in (0, 1):
+for seg, x2 in ((0, 0), (1, 0), (0, 1), (1, 1)):
     h.tune("matvec_seg", seg)
+    h.tune("matvec_x2", x2)
     o2.fill_(-1)
     t = timed(lambda: h.zkvec_inner_prefix_dev(x, s, o2))
     if base is None:
         base = o2.clone()
-    print(f"zkvec inner 4096x1024 seg={seg}: median {t[0]:.1f} us min {t[1]:.1f} us -> {4096 * 1024 * 96 / t[0] / 1e3:.0f} GB/s same={bool((o2 == base).all().item())}")
+    print(f"zkvec inner 4096x1024 seg={seg} x2={x2}: median {t[0]:.1f} us min {t[1]:.1f} us -> {4096 * 1024 * 96 / t[0] / 1e3:.0f} GB/s same={bool((o2 == base).all().item())}")
 h.tune("matvec_seg", -1)
+h.tune("matvec_x2", 0)
 tt = fr(n)
 print("mat_vec_totals 1024x1024:", timed(lambda: h.mat_vec_totals_dev(b, powers, tt)))
 print("gamma_powers 1024:", timed(lambda: h.gamma_powers_dev(g, n, powers)))
