@@ -111,24 +111,24 @@ constexpr int RS_CTAS_PER_SM = (int)((227 * 1024) / (RS_SMEM + 1024)) > 0 ? (int
 using WitnessStream = WitnessStreamT<RS_CH, RS_NBUF>;   // 256-byte bursts, double-buffered rows
 // the rescale kernel itself is instantiated for several burst sizes (tuning switch "rescale_ch"): fewer witnesses per
 // burst = a smaller staging area = more resident CTAs per SM (the kernel is latency-, not bandwidth-limited)
-template <int CH>
+template <int CH, int NBUF = RS_NBUF>
 struct RsCfg {
     static constexpr int ROW_U4 = CH * 2 + 1;
-    static constexpr size_t SMEM = (size_t)RS_THREADS * RS_NBUF * ROW_U4 * sizeof(uint4);
+    static constexpr size_t SMEM = (size_t)RS_THREADS * NBUF * ROW_U4 * sizeof(uint4);
     static constexpr int CTAS_PER_SM_SMEM = (int)((227 * 1024) / (SMEM + 1024));
     static constexpr int CTAS_PER_SM = CTAS_PER_SM_SMEM < 4 ? CTAS_PER_SM_SMEM : 4;   // 128 threads x 120 registers: 4 by registers
 };
 
-template <int CH>
-__global__ void __launch_bounds__(RS_THREADS, RsCfg<CH>::CTAS_PER_SM)
+template <int CH, int NBUF>
+__global__ void __launch_bounds__(RS_THREADS, RsCfg<CH, NBUF>::CTAS_PER_SM)
 rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
                const __grid_constant__ RescaleConsts k) {
     extern __shared__ __align__(16) uint4 rs_stage[];
     const int lane = threadIdx.x & 31;
-    WitnessStreamT<CH, RS_NBUF> ws;
-    ws.row0 = rs_stage + (size_t)threadIdx.x * RsCfg<CH>::ROW_U4;
-    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RsCfg<CH>::ROW_U4;
-    ws.buf_stride = RS_THREADS * RsCfg<CH>::ROW_U4;
+    WitnessStreamT<CH, NBUF> ws;
+    ws.row0 = rs_stage + (size_t)threadIdx.x * RsCfg<CH, NBUF>::ROW_U4;
+    ws.warp_row0 = rs_stage + (size_t)(threadIdx.x - lane) * RsCfg<CH, NBUF>::ROW_U4;
+    ws.buf_stride = RS_THREADS * RsCfg<CH, NBUF>::ROW_U4;
     ws.W = k.p.W;
     ws.buf = 0;
     ws.fill = 0;
@@ -347,13 +347,14 @@ int make_rescale_consts(int P, int lb, int S, int A, rs::RescaleConsts* out) {
     return p.W;
 }
 
-template <int CH>
+template <int CH, int NBUF = RS_NBUF>
 static int launch_rescale_ch(h2svd_ctx* ctx, const Fr* cs, size_t count, const rs::RescaleConsts& k, Fr* out_q, Fr* out_wit) {
-    H2SVD_SET_SMEM(ctx, rescale_kernel<CH>, RsCfg<CH>::SMEM);
+    using cfg = RsCfg<CH, NBUF>;
+    H2SVD_SET_SMEM(ctx, (rescale_kernel<CH, NBUF>), cfg::SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
-    const size_t cap = (size_t)ctx->sm_count * RsCfg<CH>::CTAS_PER_SM;  // resident CTAs, grid-stride beyond
+    const size_t cap = (size_t)ctx->sm_count * cfg::CTAS_PER_SM;  // resident CTAs, grid-stride beyond
     if (blocks > cap) blocks = cap;
-    rescale_kernel<CH><<<(unsigned)blocks, RS_THREADS, RsCfg<CH>::SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
+    rescale_kernel<CH, NBUF><<<(unsigned)blocks, RS_THREADS, cfg::SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }
@@ -410,6 +411,8 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
         }
     }
     switch (ctx->tune.rescale_ch) {
+        case 16: return launch_rescale_ch<16, 1>(ctx, cs, count, k, out_q, out_wit);   // 512-byte bursts, one buffer
+        case 12: return launch_rescale_ch<12, 1>(ctx, cs, count, k, out_q, out_wit);   // 384-byte bursts, one buffer
         case 4: return launch_rescale_ch<4>(ctx, cs, count, k, out_q, out_wit);
         case 6: return launch_rescale_ch<6>(ctx, cs, count, k, out_q, out_wit);
         default: return launch_rescale_ch<8>(ctx, cs, count, k, out_q, out_wit);

@@ -193,22 +193,49 @@ __device__ __forceinline__ Fr shr_small(const Fr& y, int s) {  // 1 <= s <= 32
     return o;
 }
 
-// RangeChip::range_check(x, n*lb): limbs l_i and running sums s_i = x mod 2^(lb*(i+1)), Montgomery form
+// RangeChip::range_check(x, n*lb): limbs l_i and running sums s_i = x mod 2^(lb*(i+1)), Montgomery form.
+// RS_LIMB_PAIRS (experiment, off): two limbs per trip, so that four single-limb Montgomery steps are independent of each
+// other and of the running sum.  Measured on the N = 1024 rescale: 471 us against 404 us one limb at a time -- the extra
+// live values cost more than the instruction-level parallelism gains.
+#ifndef RS_LIMB_PAIRS
+#define RS_LIMB_PAIRS 0
+#endif
 template <class WS>
 __device__ __forceinline__ void stream_range_check(WS& ws, const LimbConsts& k, Fr y, int n) {
     if (n == 1) return;
     Fr sum;
-    for (int i = 0; i < n; i++) {
+    {
+        const uint32_t l = y.l[0] & k.lb_mask;
+        y = shr_small(y, k.lb);
+        sum = fr::mont_mul_small(l, k.c[0]);
+        ws.put(sum);
+    }
+    int i = 1;
+#if RS_LIMB_PAIRS
+    for (; i + 1 < n; i += 2) {
+        const uint32_t l0 = y.l[0] & k.lb_mask;
+        y = shr_small(y, k.lb);
+        const uint32_t l1 = y.l[0] & k.lb_mask;
+        y = shr_small(y, k.lb);
+        const Fr ml0 = fr::mont_mul_small(l0, k.c[0]);
+        const Fr t0 = fr::mont_mul_small(l0, k.c[i]);
+        const Fr ml1 = fr::mont_mul_small(l1, k.c[0]);
+        const Fr t1 = fr::mont_mul_small(l1, k.c[i + 1]);
+        const Fr s0 = fr::add_fast(sum, t0);
+        sum = fr::add_fast(s0, t1);
+        ws.put(ml0);
+        ws.put(s0);
+        ws.put(ml1);
+        ws.put(sum);
+    }
+#endif
+    for (; i < n; i++) {
         const uint32_t l = y.l[0] & k.lb_mask;
         y = shr_small(y, k.lb);
         const Fr ml = fr::mont_mul_small(l, k.c[0]);
         ws.put(ml);
-        if (i == 0) {
-            sum = ml;
-        } else {
-            sum = fr::add_fast(sum, fr::mont_mul_small(l, k.c[i]));
-            ws.put(sum);
-        }
+        sum = fr::add_fast(sum, fr::mont_mul_small(l, k.c[i]));
+        ws.put(sum);
     }
 }
 

@@ -70,6 +70,20 @@ for store, name in ((0, "bulk copies"), (1, "TMA tensor stores"), (2, "coalesced
     same = bool((wit == ref).all().item())
     print(f"rescale {name}: median {t[0]:.1f} us  min {t[1]:.1f} us  -> {n * n * 32 * (2 + W) / t[0] / 1e3:.0f} GB/s  same_bytes={same}")
 h.tune("rescale_store", 0)
+for ch in (16, 12, 8):
+    h.tune("rescale_ch", ch)
+    wit.fill_(-1)
+    t = timed(lambda: h.rescale_witness_dev(c, n * n, 63, 19, q, wit))
+    print(f"rescale bulk copies, {ch} witnesses per burst: median {t[0]:.1f} us  same_bytes={bool((wit == ref).all().item())}")
+# one rank's share of the 8-GPU job: 128 x 1024 elements
+cnt = 128 * n
+for store, ch in ((0, 8), (0, 6), (0, 4), (0, 12), (0, 16), (2, 8)):
+    h.tune("rescale_store", store)
+    h.tune("rescale_ch", ch)
+    t = timed(lambda: h.rescale_witness_dev(c, cnt, 63, 19, q, wit))
+    print(f"rescale of a 128-row slab, store={store} burst={ch}: median {t[0]:.1f} us")
+h.tune("rescale_store", 0)
+h.tune("rescale_ch", 8)
 del ref
 powers = fr(n)
 g = torch.tensor([[0x1234567, 0x89ABCDEF, 0x13579BDF, 0x2468ACE]], dtype=torch.int64, device=dev)
