@@ -9,7 +9,8 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libh2svd_b200.so")
+# H2SVD_LIB: tuning only -- load another build of the same library (e.g. one compiled with experiment macros)
+LIB_PATH = os.environ.get("H2SVD_LIB") or os.path.join(_HERE, "libh2svd_b200.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEV, ERANGE = 0, -1, -2, -3, -4, -5
 _CODES = {EINVAL: "EINVAL", ECUDA: "ECUDA", ENOMEM: "ENOMEM", ENODEV: "ENODEV", ERANGE: "ERANGE"}

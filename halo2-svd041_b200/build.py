@@ -13,8 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libh2svd_b200.so")
+OBJ = os.environ.get("H2SVD_OBJ_DIR") or os.path.join(HERE, "build")
+LIB = os.environ.get("H2SVD_LIB_OUT") or os.path.join(HERE, "libh2svd_b200.so")   # (the two overrides: tuning builds)
 # one list for every build of the library: this script and rust/h2svd-b200/build.rs both read csrc/SOURCES.txt
 with open(os.path.join(CSRC, "SOURCES.txt")) as _fh:
     SOURCES = [ln.strip() for ln in _fh if ln.strip() and not ln.startswith("#")]
