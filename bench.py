@@ -433,6 +433,71 @@ def run_gpu(args) -> None:
         print(json.dumps(line), flush=True)
 
 
+def run_multi_handle(args) -> None:
+    """ONE process, --gpus N devices through h2svd_multi_zkmatrix_mul_witness (the single-process drop-in form of the same
+    row sharding): end-to-end only -- host arrays in, host arrays out, one host thread and one PCIe link per GPU."""
+    import torch
+
+    pkg = importlib.import_module("halo2-svd041_b200")
+    from oracle import corac
+    n = k = m = args.n
+    if args.shape:
+        n, k, m = (int(x) for x in args.shape.split(","))
+    ndev = args.gpus
+    avail = torch.cuda.device_count()
+    devices = [i % avail for i in range(ndev)]          # more handles than GPUs wrap round (same partitioning)
+    a_f, b_f, gamma = make_inputs(n, k, m)
+    with pkg.Handle(0) as h0:
+        W = h0.rescale_witness_count(P_BITS, LOOKUP_BITS)
+        a = h0.quantize(a_f, P_BITS)
+        b = h0.quantize(b_f, P_BITS)
+    shapes = dict(c_s=(n, m), q=(n, m), wit=(n * m, W), powers=(m,), prefix_cv=(n, m), prefix_bv=(k, m), prefix_abv=(n, k),
+                  diff=(n,), is_zero=(n,), inv=(n,))
+    pin_a, pin_b = pkg.PinnedBuffer(a.shape, np.uint64), pkg.PinnedBuffer(b.shape, np.uint64)
+    pin_a.array[...] = a
+    pin_b.array[...] = b
+    pin_out = {nm: pkg.PinnedBuffer(shp + (4,), np.uint64) for nm, shp in shapes.items()}
+    out = {nm: pb.array for nm, pb in pin_out.items()}
+    sampler = ClockSampler(0)
+    with pkg.MultiHandle(devices) as mh:
+        for _ in range(max(3, args.warmup)):
+            mh.zkmatrix_mul_witness(pin_a.array, pin_b.array, gamma, P_BITS, LOOKUP_BITS, out=out)
+        launches0 = mh.launch_count()
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            mh.zkmatrix_mul_witness(pin_a.array, pin_b.array, gamma, P_BITS, LOOKUP_BITS, out=out)
+        secs = (time.perf_counter() - t0) / args.steps
+        clocks = sampler.stop()
+        launches = mh.launch_count() - launches0
+    # verification against the oracle: sampled rows of C, their rescale stripes, the Freivalds identity on every row
+    sel = sorted({0, n // 3, n - 1})
+    want_c = corac.field_mat_mul(np.ascontiguousarray(a[sel]), b, threads=0)
+    ok = bool((out["c_s"][sel] == want_c).all()) and not out["diff"].any()
+    q_w, _r, wit_w = corac.rescale_witness(np.ascontiguousarray(want_c[:, :4].reshape(-1, 4)), P_BITS, LOOKUP_BITS)
+    idx = [r * m + c for r in sel for c in range(4)]
+    ok = ok and bool((out["wit"][idx] == wit_w).all())
+    if not ok:
+        raise SystemExit("bench --multi-handle: witness check against the oracle failed")
+    units = job_units(n, k, m)
+    d2h = sum(int(v.nbytes) for v in out.values())
+    line = {"metric": metric_name(n, k, m), "value": units / secs, "unit": UNIT, "n_gpus": ndev, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config_dict(n, k, m, ndev),
+            "mode": "one process, h2svd_multi (one handle + one host thread per GPU); value IS the end-to-end figure: host arrays "
+                    "in, every witness back on the host",
+            "devices": devices,
+            "e2e": {"value": units / secs, "unit": UNIT, "ms_per_step": secs * 1e3,
+                    "h2d_bytes_per_step": int(a.nbytes + ndev * b.nbytes + 32 * ndev), "d2h_bytes_per_step": d2h,
+                    "api": "h2svd_multi_zkmatrix_mul_witness (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "pcie", "note": "output-bound: the D2H copy of the witnesses; see the default mode for kernel rooflines",
+                         "achieved": d2h / secs / 1e9, "unit": "GB/s", "peak": None, "frac": None, "traffic": None,
+                         "verified": {"against": "CPU oracle", "rows_of_c": len(sel), "rescale_stripes": len(idx),
+                                      "freivalds_diff_all_zero": True}}}
+    print(json.dumps(line), flush=True)
+
+
 def verify_rank(h, torch, device, bufs, a_slab, b_dev, gamma, rows, k, m, b0, b1, W, host_out) -> dict:
     """Compares what the timed step left in this rank's buffers with the CPU oracle: sampled rows of C, the rescale witness
     stripes of those rows, sampled running-sum rows of C.v / A.(Bv) / B.v, the gamma powers, every is_equal cell."""
@@ -644,12 +709,16 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--matmul-small", type=int, default=None, help="tuning: 0 = never use the small-operand mat-mul engine")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure (0 = skip)")
+    ap.add_argument("--multi-handle", action="store_true",
+                    help="one process drives --gpus N devices through h2svd_multi (end-to-end only; no torchrun)")
     ap.add_argument("--quick", action="store_true", help="skip configs[1]/[2], the IMAD engine and the 2 s peak measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rules: W >= 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.multi_handle:
+        run_multi_handle(args)
     else:
         run_gpu(args)
 

@@ -1056,7 +1056,8 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
         {"matmul_karatsuba", &ctx->tune.kara},     {"matmul_streamk", &ctx->tune.streamk},
         {"matmul_variant", &ctx->tune.variant},    {"fuse_rescale", &ctx->tune.fuse_rescale},
         {"rescale_generic", &ctx->tune.rescale_generic}, {"matvec_warp_kernel", &ctx->tune.matvec_warp},
-        {"matvec_seg", &ctx->tune.matvec_seg},       {"matvec_x2", &ctx->tune.matvec_x2},       {"rescale_ch", &ctx->tune.rescale_ch},
+        {"matvec_seg", &ctx->tune.matvec_seg},       {"matvec_x2", &ctx->tune.matvec_x2},
+        {"matvec_segs", &ctx->tune.matvec_segs},       {"rescale_ch", &ctx->tune.rescale_ch},
         {"rescale_store", &ctx->tune.rescale_store},
     };
     for (const auto& e : keys)

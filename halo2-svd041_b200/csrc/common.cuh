@@ -44,6 +44,7 @@ struct h2svd_ctx {
         int rescale_ch = 8;       // witnesses per bulk store of the staged rescale kernel: 4, 6 or 8
         int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel
         int matvec_x2 = 1;        // mat-vec prefix kernels: 1 = two Montgomery products at a time with interleaved carry chains
+        int matvec_segs = 0;      // warps per row of the several-warps-per-row kernel: 0 auto (by row length), 2 / 4 / 8
         int matvec_seg = -1;      // several-warps-per-row mat-vec prefix kernel: -1 auto (few long rows), 0 never, 1 always
     } tune;
     int last_engine = -1;         // engine of the last mat-mul launch: 0 schoolbook, 1 Karatsuba, 2 tensor core, 3 small-operand

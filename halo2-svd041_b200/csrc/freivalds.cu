@@ -490,8 +490,9 @@ static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_
     // few long rows: several warps per row (mat_vec_prefix_seg_kernel); "matvec_seg": -1 auto, 0 never, 1 whenever len >= 256
     const bool few_rows = total_rows < (size_t)ctx->sm_count * 16;
     if (len >= 256 && ctx->tune.matvec_warp == 0 && (ctx->tune.matvec_seg > 0 || (ctx->tune.matvec_seg < 0 && few_rows))) {
-        if (len >= 1024) return launch_mv_seg<8>(ctx, jobs, total_rows, v, len, vs);
-        if (len >= 512) return launch_mv_seg<4>(ctx, jobs, total_rows, v, len, vs);
+        const int segs = ctx->tune.matvec_segs > 0 ? ctx->tune.matvec_segs : (len >= 1024 ? 8 : len >= 512 ? 4 : 2);
+        if (segs >= 8) return launch_mv_seg<8>(ctx, jobs, total_rows, v, len, vs);
+        if (segs >= 4) return launch_mv_seg<4>(ctx, jobs, total_rows, v, len, vs);
         return launch_mv_seg<2>(ctx, jobs, total_rows, v, len, vs);
     }
     if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && ctx->tune.matvec_warp == 0) {

@@ -88,7 +88,7 @@ struct TcD {
     static_assert((size_t)C::SA * TC_A_BYTES + (size_t)C::SB * B_BYTES + 256 + 1024 <= 232448, "stages exceed the SM's shared memory");
     static_assert(16 * C::SA + 16 * C::SB + 24 <= 256, "barrier block");
 };
-// fused rescale (full-width engine only): every epilogue warp stages 4 witnesses (128 B + 16 B skew) per lane, single-buffered
+// fused rescale (8-column tiles of either engine): every epilogue warp stages 4 witnesses (128 B + 16 B skew) per lane, single-buffered
 using TcWitnessStream = rs::WitnessStreamT<TC_CH_CFG, 1>;
 constexpr uint32_t TC_STAGE_BYTES = TC_EPI_WARPS * 32 * TcWitnessStream::ROW_U4 * 16;
 static_assert((size_t)TC_SA_FUSED_CFG * 16384 + 65536 + 1280 + TC_STAGE_BYTES <= 232448, "fused kernel: shared memory");
@@ -325,7 +325,6 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     constexpr int CW = D::CW;
     constexpr int BJ = C::BJ;
     constexpr uint32_t TC_B_BYTES = D::B_BYTES;
-    static_assert(!FUSE || !C::SIGNED, "the fused rescale epilogue exists for the full-width engine only");
     // engine arbitration (uniform over the grid): the split kernels earlier in the stream decided which engine runs
     if (mode != nullptr && (*mode != 0) != (run_if_mode != 0)) return;
     extern __shared__ uint8_t tc_smem_raw[];
@@ -671,11 +670,14 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
     }
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     if (fuse) {
-        if constexpr (!C::SIGNED) {
+        if constexpr (C::BJ == 8) {   // the fused epilogue is instantiated for the 8-column tiles of either engine
             H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, true>), (tc_smem_bytes<C, true>()));
             fr_matmul_tc_kernel<C, true><<<grid, TC_THREADS, tc_smem_bytes<C, true>(), ctx->stream>>>(
                 tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, *fuse, out_q,
                 out_wit);
+        } else {
+            set_error("fr_matmul (tensor-core engine): fused rescale needs 8-column tiles");
+            return H2SVD_EINVAL;
         }
     } else {
         static const rs::RescaleConsts none{};
@@ -740,7 +742,7 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
         set_error("fr_matmul (tensor-core engine): cuTensorMapEncodeTiled is not available from this driver");
         return H2SVD_ECUDA;
     }
-    const bool try_small = ctx->tune.matmul_small != 0 && fuse == nullptr;
+    const bool try_small = ctx->tune.matmul_small != 0;
     const size_t ldk = (k + 15) & ~(size_t)15;  // TMA row pitch: multiple of 16 bytes
     const size_t full_a = tc_align256(TcFull::LA * n * ldk), full_b = tc_align256(TcFull::LB * m * ldk);
     const size_t small_a = tc_align256(TcSmall::LA * n * ldk), small_b = tc_align256(TcSmall::LB * m * ldk);   // LB = 10: the largest
@@ -760,10 +762,10 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
     // small-operand split kernel, decides on the device which of them does the work.
     ctx->last_engine = 3;
     H2SVD_CUDA(cudaMemsetAsync(ctx->d_mode, 0, sizeof(int), ctx->stream));
-    const int width = tc_small_tile_width(ctx, n, k, m);
+    const int width = fuse ? 8 : tc_small_tile_width(ctx, n, k, m);
     auto small = [&](bool split_only, bool mm_only) -> int {
         switch (width) {
-            case 8: return tc_launch_engine<TcSmall8>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
+            case 8: return tc_launch_engine<TcSmall8>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, fuse, out_q, out_wit);
             case 16: return tc_launch_engine<TcSmall16>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
             default: return tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
         }
@@ -772,8 +774,8 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
     H2SVD_TRY(tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, true, false, nullptr,
                                        nullptr, nullptr));
     H2SVD_TRY(small(false, true));
-    return tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, false, true, nullptr,
-                                    nullptr, nullptr);
+    return tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, false, true, fuse, out_q,
+                                    out_wit);
 }
 
 }  // namespace h2svd
