@@ -126,6 +126,16 @@ static int freivalds_dev(h2svd_ctx* ctx, const Fr* a, const Fr* b, const Fr* cs,
 
 }  // namespace h2svd
 
+namespace h2svd {
+// after a failure inside a pipelined host call: nothing may still be writing the caller's buffers, no stale flag
+static void drain_after_error(h2svd_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaMemset(ctx->d_flag, 0, sizeof(int));
+    cudaGetLastError();
+}
+}  // namespace h2svd
 using namespace h2svd;
 
 extern "C" {
@@ -415,8 +425,8 @@ int h2svd_fr_matmul_rescale_dev(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_f
                                     a_num_bits, as_fr(out_q), as_fr(out_wit));
 }
 
-int h2svd_rescale_witness(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count, int precision_bits, int lookup_bits,
-                          int shift_bits, int a_num_bits, h2svd_fr* out_q, h2svd_fr* out_wit) {
+static int rescale_witness_host(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count, int precision_bits, int lookup_bits,
+                                int shift_bits, int a_num_bits, h2svd_fr* out_q, h2svd_fr* out_wit) {
     REQUIRE(ctx && c_s && out_q && out_wit, "rescale_witness: null argument");
     const int W = rescale_params(precision_bits, lookup_bits, shift_bits, a_num_bits, nullptr, nullptr);
     REQUIRE(W > 0, "rescale_witness: parameters out of range");
@@ -449,6 +459,14 @@ int h2svd_rescale_witness(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count, int
     H2SVD_TRY(d2h(ctx, out_q, dq, count * F));
     H2SVD_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return check_flag(ctx, "rescale_witness");
+}
+
+int h2svd_rescale_witness(h2svd_ctx* ctx, const h2svd_fr* c_s, size_t count, int precision_bits, int lookup_bits,
+                          int shift_bits, int a_num_bits, h2svd_fr* out_q, h2svd_fr* out_wit) {
+    REQUIRE(ctx && c_s && out_q && out_wit, "rescale_witness: null argument");
+    const int rc = rescale_witness_host(ctx, c_s, count, precision_bits, lookup_bits, shift_bits, a_num_bits, out_q, out_wit);
+    if (rc != H2SVD_OK && rc != H2SVD_EINVAL) drain_after_error(ctx);   // nothing may still be copying into the caller's buffers
+    return rc;
 }
 
 /* ---- range-check witnesses of the SVD verifier's helpers ---- */
@@ -605,15 +623,6 @@ static int mul_witness_dev(h2svd_ctx* ctx, const Fr* da, const Fr* db, const Fr*
     H2SVD_TRY(launch_rescale(ctx, dc, rows * m, P, lb, S, A, dq, dw));                            // :354
     H2SVD_CUDA(cudaStreamWaitEvent(main, ev_join, 0));
     return H2SVD_OK;
-}
-
-// after a failure inside a pipelined host call: nothing may still be writing the caller's buffers, no stale flag
-static void drain_after_error(h2svd_ctx* ctx) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->copy_stream);
-    cudaStreamSynchronize(ctx->side_stream);
-    cudaMemset(ctx->d_flag, 0, sizeof(int));
-    cudaGetLastError();
 }
 
 static int mul_witness_host(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr* b, const h2svd_fr* gamma, size_t rows,

@@ -65,3 +65,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs", ".toml")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), f"{f} references the oracle"
+
+
+def test_one_source_list_for_every_build():
+    """csrc/SOURCES.txt names every .cu of the library and is what BOTH builds read (build.rs had drifted from
+    build.py and missed matmul_tc.cu)."""
+    import importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "halo2-svd041_b200", "csrc")
+    listed = [ln.strip() for ln in open(os.path.join(csrc, "SOURCES.txt")) if ln.strip() and not ln.startswith("#")]
+    assert sorted(listed) == sorted(f for f in os.listdir(csrc) if f.endswith(".cu"))
+    b = importlib.import_module("halo2-svd041_b200.build")
+    assert b.SOURCES == listed
+    rs = open(os.path.join(root, "rust", "h2svd-b200", "build.rs")).read()
+    assert "SOURCES.txt" in rs and "matmul.cu" not in rs and "api.cu" not in rs      # no hard-coded list left

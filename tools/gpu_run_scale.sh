@@ -1,6 +1,7 @@
 #!/bin/bash
-# 1 -> 8 GPU scaling of the headline step, the way the driver launches it
+# 1 -> 8 GPU scaling of the headline step the way the driver launches it, BASELINE configs[4] on 8 GPUs, the one-process multi-handle mode
 mkdir -p gpurun_out
+rm -f gpurun_out/s_summary.txt
 nvidia-smi -L > gpurun_out/s_gpus.txt 2>&1
 for N in 1 2 4 8; do
   if [ $N -eq 1 ]; then
@@ -10,14 +11,23 @@ for N in 1 2 4 8; do
   fi
   echo "N=$N rc=$?" >> gpurun_out/s_summary.txt
 done
-cat gpurun_out/s_summary.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus 8 --steps 10 --warmup 3 --quick --no-cpu-baseline --no-e2e --shape 4096,2048,4096 > gpurun_out/s_cfg4_n8.json 2> gpurun_out/s_cfg4_n8.err
+echo "cfg4 N=8 rc=$?" >> gpurun_out/s_summary.txt
+timeout 600 python bench.py --multi-handle --gpus 8 --steps 5 --warmup 3 > gpurun_out/s_multi8.json 2> gpurun_out/s_multi8.err
+echo "multi-handle 8 rc=$?" >> gpurun_out/s_summary.txt
+timeout 300 python -m pytest tests/test_gpu_round2.py tests/test_gpu_edge.py -m gpu -q -k "multi_handle or two_handles" > gpurun_out/s_tests_multi.log 2>&1
+echo "multi-GPU tests rc=$?" >> gpurun_out/s_summary.txt
+cat gpurun_out/s_summary.txt; tail -2 gpurun_out/s_tests_multi.log
 python - <<'PY'
 import json
+def load(f): return json.loads([l for l in open(f) if l.startswith('{')][-1])
 for n in (1,2,4,8):
     try:
-        d=json.loads([l for l in open(f'gpurun_out/s_bench_n{n}.json') if l.startswith('{')][-1])
-        k=d['roofline']['kernels']
-        print(n, round(d['ms_per_step'],4), 'ms', f"{d['value']:.3e}", 'e2e ms', round(d['e2e']['ms_per_step'],2), 'mm', round(k['fr_matmul']['ms'],4), 'rescale', round(k['rescale_kernel']['ms'],4), 'matvec', round(k['mat_vec_prefix']['ms'],4), d['gpu_launches'])
-    except Exception as e:
-        print(n, 'failed', e)
+        d=load(f'gpurun_out/s_bench_n{n}.json'); k=d['roofline']['kernels']
+        print(n, round(d['ms_per_step'],4), 'ms', f"{d['value']:.3e}", 'e2e ms', round(d['e2e']['ms_per_step'],2), 'mm', round(k['fr_matmul']['ms'],4), 'rescale', round(k['rescale_kernel']['ms'],4), 'matvec', round(k['mat_vec_prefix']['ms'],4), d['gpu_launches'], d['roofline']['verified']['ranks'])
+    except Exception as e: print(n, 'failed', e)
+for f in ('s_cfg4_n8','s_multi8'):
+    try:
+        d=load(f'gpurun_out/{f}.json'); print(f, round(d['ms_per_step'],3), 'ms', f"{d['value']:.3e}")
+    except Exception as e: print(f, 'failed', e)
 PY
