@@ -315,7 +315,7 @@ tc_split_kernel(const Fr* __restrict__ a, uint32_t* __restrict__ planes_a, int n
 template <class C, bool FUSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    Fr* __restrict__ c, int n, int k, int m, int tiles_j, int num_tiles, int* err,
+                    Fr* __restrict__ c, int n, int k, int m, int j_begin, int j_end, int tiles_j, int num_tiles, int* err,
                     const int* __restrict__ mode, int run_if_mode, unsigned long long* __restrict__ tl,
                     const __grid_constant__ rs::RescaleConsts kc, Fr* __restrict__ out_q, Fr* __restrict__ out_wit) {
     using D = TcD<C>;
@@ -378,7 +378,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const uint32_t sb = ub % TC_SB;
                     tc_mbar_wait(empty_b + 8 * sb, ((ub / TC_SB) & 1) ^ 1, err);
                     tc_mbar_expect_tx(full_b + 8 * sb, TC_B_BYTES);
-                    tc_tma_3d(s_b + sb * TC_B_BYTES, &tm_b, kb * TC_BKB, jb * BJ, 0, full_b + 8 * sb);
+                    tc_tma_3d(s_b + sb * TC_B_BYTES, &tm_b, kb * TC_BKB, j_begin + jb * BJ, 0, full_b + 8 * sb);
                     ub++;
                     for (int p = 0; p < C::LA; p++) {
                         const uint32_t sa = ua % TC_SA;
@@ -494,8 +494,8 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 for (int q = 0; q < CW; q++) {
                     if constexpr (C::SIGNED) res[q] = fr::signed6_to_mont(T[q]);
                     else res[q] = fr::reduce_wide_acc(T[q]);
-                    const int gj = jb * BJ + j0 + q;
-                    if (gi < n && gj < m) {
+                    const int gj = j_begin + jb * BJ + j0 + q;   // this launch owns columns [j_begin, j_end)
+                    if (gi < n && gj < j_end) {
                         Fr* dst = c + (size_t)gi * m + gj;
                         if (pass > 0) res[q] = fr::add(ld_fr(dst), res[q]);
                         st_fr(dst, res[q]);
@@ -507,8 +507,8 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const int valid = n - row0 < 32 ? n - row0 : 32;
 #pragma unroll
                     for (int q = 0; q < CW; q++) {
-                        const int gj = jb * BJ + j0 + q;
-                        if (gj < m && valid > 0) {  // warp-uniform
+                        const int gj = j_begin + jb * BJ + j0 + q;
+                        if (gj < j_end && valid > 0) {  // warp-uniform
                             ws.valid = valid;
                             ws.gwarp = out_wit + ((size_t)row0 * m + gj) * (size_t)kc.p.W;
                             const Fr qv = rs::rescale_element(ws, kc, gi < n ? res[q] : fr::zero());
@@ -620,7 +620,8 @@ size_t tc_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 template <class C>
 int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m,
                      size_t ldk, uint8_t* a8, uint8_t* b8, int* mode, int run_if_mode, bool split_only, bool mm_only,
-                     const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit) {
+                     const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit, size_t j_begin = 0, size_t j_end = 0) {
+    if (j_end == 0) j_end = m;   // columns [j_begin, j_end) of C are produced by this launch
     using D = TcD<C>;
     const int ldk4 = (int)(ldk / 4);
     if (!mm_only) {
@@ -662,7 +663,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
             return H2SVD_ECUDA;
         }
     }
-    const int tiles_i = (int)((n + TC_BM - 1) / TC_BM), tiles_j = (int)((m + C::BJ - 1) / C::BJ);
+    const int tiles_i = (int)((n + TC_BM - 1) / TC_BM), tiles_j = (int)((j_end - j_begin + C::BJ - 1) / C::BJ);
     const long long tiles = (long long)tiles_i * tiles_j;
     if (tiles >= (1LL << 31)) {
         set_error("fr_matmul (tensor-core engine): too many tiles");
@@ -673,7 +674,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         if constexpr (C::BJ == 8) {   // the fused epilogue is instantiated for the 8-column tiles of either engine
             H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, true>), (tc_smem_bytes<C, true>()));
             fr_matmul_tc_kernel<C, true><<<grid, TC_THREADS, tc_smem_bytes<C, true>(), ctx->stream>>>(
-                tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, *fuse, out_q,
+                tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, *fuse, out_q,
                 out_wit);
         } else {
             set_error("fr_matmul (tensor-core engine): fused rescale needs 8-column tiles");
@@ -683,7 +684,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         static const rs::RescaleConsts none{};
         H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, false>), (tc_smem_bytes<C, false>()));
         fr_matmul_tc_kernel<C, false><<<grid, TC_THREADS, tc_smem_bytes<C, false>(), ctx->stream>>>(
-            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, none, nullptr,
+            tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, none, nullptr,
             nullptr);
     }
     H2SVD_LAUNCH_CHECK(ctx);
@@ -773,7 +774,24 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
     H2SVD_TRY(small(true, false));
     H2SVD_TRY(tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, true, false, nullptr,
                                        nullptr, nullptr));
-    H2SVD_TRY(small(false, true));
+    // A partial last wave of 128 x 24 tiles costs a whole tile time (N = 1024: 344 tiles on 148 SMs = 2.32 waves): when
+    // the last wave would be less than 60 % full, the 24-wide tiles take only the columns that fill WHOLE waves and the
+    // remaining columns go to 128 x 8 tiles (a third as long, same byte planes) in a second launch.
+    size_t cols24 = 0;
+    if (width == 24 && !fuse && ctx->tune.matmul_tail_split != 0) {
+        const size_t sms = (size_t)ctx->sm_count, ti = (n + TC_BM - 1) / TC_BM, t24 = ti * ((m + 23) / 24);
+        const size_t full = t24 / sms, last = t24 % sms;
+        const size_t cj = full * sms / ti;   // column tiles per row block inside the whole waves
+        if (full >= 1 && last != 0 && last * 10 < sms * 6 && cj >= 1 && cj * 24 < m) cols24 = cj * 24;
+    }
+    if (cols24 != 0) {
+        H2SVD_TRY(tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, true, nullptr,
+                                            nullptr, nullptr, 0, cols24));
+        H2SVD_TRY(tc_launch_engine<TcSmall8>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, true, nullptr,
+                                             nullptr, nullptr, cols24, m));
+    } else {
+        H2SVD_TRY(small(false, true));
+    }
     return tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, false, true, fuse, out_q,
                                     out_wit);
 }

@@ -428,3 +428,22 @@ def test_mat_vec_prefix_interleaved_products_match_oracle(handle, x2, seg, rows,
         handle.tune("matvec_x2", 1)
         handle.tune("matvec_seg", -1)
     assert _eq(out.cpu().numpy().view(np.uint64), corac.mat_vec_prefix(a, v, threads=0))
+
+
+def test_small_operand_engine_tail_split(handle):
+    """1024 x 64 x 1000: 336 tiles of 128 x 24 = 2.27 waves on 148 SMs, so the 24-wide launch takes the 888 columns that fill
+    two whole waves and a second launch of 128 x 8 tiles the other 112: same bytes as the unsplit product and the oracle."""
+    rng = np.random.default_rng(8)
+    n, k, m = 1024, 64, 1000
+    a, b = _signed_matrix(rng, n, k, 69), _signed_matrix(rng, k, m, 69)
+    try:
+        handle.tune("matmul_small_width", 24)
+        split = handle.fr_matmul(a, b)
+        assert handle.last_matmul_engine() == "tensor-small"
+        handle.tune("matmul_tail_split", 0)
+        plain = handle.fr_matmul(a, b)
+    finally:
+        handle.tune("matmul_small_width", 0)
+        handle.tune("matmul_tail_split", 1)
+    assert _eq(split, plain)
+    assert _eq(split, corac.field_mat_mul(a, b, threads=0))
