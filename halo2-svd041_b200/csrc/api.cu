@@ -43,6 +43,7 @@ int ws_reserve(h2svd_ctx* ctx, size_t bytes) {
     size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
     H2SVD_CUDA(cudaMalloc(&ctx->ws, want));
     ctx->ws_bytes = want;
+    ctx->ws_generation++;
     return H2SVD_OK;
 }
 
@@ -60,6 +61,7 @@ int ws_grow(h2svd_ctx* ctx, void** buf, size_t* cur, size_t need) {
     *cur = 0;
     H2SVD_CUDA(cudaMalloc(buf, need));
     *cur = need;
+    ctx->ws_generation++;
     return H2SVD_OK;
 }
 
@@ -769,7 +771,8 @@ int h2svd_zkmatrix_mul_witness(h2svd_ctx* ctx, const h2svd_fr* a, const h2svd_fr
 /* ---- CUDA-graph capture of any sequence of *_dev calls on one handle ---- */
 struct h2svd_graph {
     cudaGraphExec_t exec = nullptr;
-    uint64_t launches = 0;   // kernel launches recorded between begin and end
+    uint64_t launches = 0;        // kernel launches recorded between begin and end
+    uint64_t ws_generation = 0;   // the handle's workspace generation the recorded pointers belong to
 };
 
 int h2svd_graph_begin(h2svd_ctx* ctx) {
@@ -801,6 +804,7 @@ int h2svd_graph_end(h2svd_ctx* ctx, h2svd_graph** out) {
         return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
     }
     gr->launches = ctx->launches - ctx->capture_launches0;
+    gr->ws_generation = ctx->ws_generation;
     ctx->launches = ctx->capture_launches0;   // nothing has run yet: h2svd_graph_launch accounts for every replay
     *out = gr;
     return H2SVD_OK;
@@ -808,6 +812,9 @@ int h2svd_graph_end(h2svd_ctx* ctx, h2svd_graph** out) {
 
 int h2svd_graph_launch(h2svd_ctx* ctx, h2svd_graph* graph) {
     REQUIRE(ctx && graph && graph->exec, "graph_launch: null argument");
+    REQUIRE(graph->ws_generation == ctx->ws_generation,
+            "graph_launch: a workspace of the handle was reallocated after this graph was recorded (a larger call ran since): "
+            "record it again");
     H2SVD_CUDA(cudaSetDevice(ctx->device));
     H2SVD_CUDA(cudaGraphLaunch(graph->exec, ctx->stream));
     ctx->launches += graph->launches;

@@ -21,6 +21,7 @@ struct h2svd_ctx {
     cudaStream_t side_stream = nullptr;
     bool capturing = false;       // between h2svd_graph_begin and h2svd_graph_end
     uint64_t capture_launches0 = 0;
+    uint64_t ws_generation = 0;   // bumped whenever a workspace is reallocated: recorded graphs hold the old pointers
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 0-3 copy pipelines, 4-6 fork/mid/join of the two-stream step
     void* kara_ws = nullptr;  // pre-split (Karatsuba) operands of the mat-mul
     size_t kara_ws_bytes = 0;

@@ -216,8 +216,9 @@ int h2svd_zkmatrix_mul_witness_dev(h2svd_ctx *ctx, const h2svd_fr *a, const h2sv
  * Any sequence of *_dev calls on one handle between h2svd_graph_begin and h2svd_graph_end is recorded instead of run
  * (cudaStreamBeginCapture on the handle's stream) and can then be replayed with ONE launch: a row slab on one of 8 GPUs
  * is ~20 kernels of 2-70 us each, where launch gaps are a visible share of the step.  Rules: run the same calls once
- * un-captured first (workspaces only grow outside a capture); the recorded pointers and shapes are baked in;
- * host-pointer entry points cannot be captured.  h2svd_launch_count advances by the recorded kernel count per replay. */
+ * un-captured first (workspaces only grow outside a capture); the recorded pointers and shapes are baked in -- if a larger
+ * call makes a workspace of the handle grow afterwards, h2svd_graph_launch refuses the stale graph (H2SVD_EINVAL: record it
+ * again); host-pointer entry points cannot be captured.  h2svd_launch_count advances by the recorded kernel count per replay. */
 typedef struct h2svd_graph h2svd_graph;
 int h2svd_graph_begin(h2svd_ctx *ctx);
 int h2svd_graph_end(h2svd_ctx *ctx, h2svd_graph **out);

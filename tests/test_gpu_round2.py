@@ -447,3 +447,28 @@ def test_small_operand_engine_tail_split(handle):
         handle.tune("matmul_tail_split", 1)
     assert _eq(split, plain)
     assert _eq(split, corac.field_mat_mul(a, b, threads=0))
+
+
+def test_graph_is_refused_after_a_workspace_reallocation(pkg):
+    """A recorded graph holds workspace pointers: once a larger call has made the handle reallocate, replaying the old graph
+    is refused (EINVAL) instead of writing through stale pointers."""
+    import torch
+    with pkg.Handle() as h:
+        dev = torch.device("cuda", h.device)
+        def z(*s):
+            return torch.zeros(s + (4,), dtype=torch.int64, device=dev)
+        a, b, c = z(64, 64), z(64, 64), z(64, 64)
+        h.fr_matmul_dev(a, b, c)
+        h.sync()
+        h.graph_begin()
+        h.fr_matmul_dev(a, b, c)
+        g = h.graph_end()
+        g.launch()
+        h.sync()
+        a2, b2, c2 = z(256, 256), z(256, 256), z(256, 256)
+        h.fr_matmul_dev(a2, b2, c2)          # larger operand planes: the workspace grows
+        h.sync()
+        with pytest.raises(pkg.H2svdError) as ei:
+            g.launch()
+        assert ei.value.code == pkg._ffi.EINVAL
+        g.close()
