@@ -162,6 +162,43 @@ class Context {
     void constrain_equal(const AssignedValue& a, const AssignedValue& b) {
         copies.push_back({CellRef{a.ctx_id, a.index}, CellRef{b.ctx_id, b.index}});
     }
+    // Bulk form of `units` identical assign_region sequences: `values` holds the complete cell stream
+    // (units * layout->cells values, from h2svd_expand_cells) and is appended with ONE insert; the layout's offsets are
+    // then replayed unit by unit for kinds / selectors / lookups / copy constraints / constants.  inputs[u * layout->inputs
+    // + i] is the i-th input cell of unit u.  Leaves the context exactly as the per-cell path would (same vectors, same order
+    // within every unit).  Returns the index of the first appended cell.
+    size_t append_units(const h2svd_cells_layout* layout, const Fr* values, size_t units, const AssignedValue* inputs) {
+        const size_t base = advice.size(), cells = layout->cells;
+        advice.insert(advice.end(), values, values + units * cells);
+        kind.resize(base + units * cells);
+        selector.resize(base + units * cells, 0);
+        for (size_t u = 0; u < units; u++) {
+            const size_t row = base + u * cells;
+            auto ref = [&](int32_t off) -> CellRef {
+                if (off >= 0) return CellRef{ctx_id, row + (size_t)off};
+                const AssignedValue& in = inputs[u * layout->inputs + (size_t)(-1 - off)];
+                return CellRef{in.ctx_id, in.index};
+            };
+            // the per-cell path records a copy / constant as each cell is pushed and an extra constrain_equal(a, acc) right
+            // after the region that ends in `acc`: replaying the extra pairs (stored in order) after their second cell
+            // reproduces the very same vectors
+            uint32_t next_copy = 0;
+            for (uint32_t c = 0; c < cells; c++) {
+                const uint8_t k = layout->kind[c];
+                kind[row + c] = k == H2SVD_CELL_WITNESS ? (uint8_t)CellKind::Witness
+                                : k == H2SVD_CELL_CONSTANT ? (uint8_t)CellKind::Constant : (uint8_t)CellKind::Existing;
+                if (k == H2SVD_CELL_EXISTING) copies.push_back({ref(layout->source[c]), CellRef{ctx_id, row + c}});
+                if (k == H2SVD_CELL_CONSTANT) constants.push_back({row + c, layout->constants[layout->source[c]]});
+                while (next_copy < layout->n_copies && layout->copies[2 * next_copy + 1] == (int32_t)c) {
+                    copies.push_back({ref(layout->copies[2 * next_copy]), ref(layout->copies[2 * next_copy + 1])});
+                    next_copy++;
+                }
+            }
+            for (uint32_t g = 0; g < layout->n_gates; g++) selector[row + layout->gates[g]] = 1;
+            for (uint32_t l = 0; l < layout->n_lookups; l++) lookups.push_back(ref(layout->lookups[l]).index);
+        }
+        return base;
+    }
 
   private:
     void push(const QuantumCell& c) {
@@ -614,6 +651,38 @@ class ZkMatrix {
                     fpchip.assign_signed_div_scale(ctx, c_s[i][j], wit.data() + (i * cols + j) * (size_t)fpchip.W).first);
             out.matrix.push_back(std::move(new_row));
         }
+        return out;
+    }
+    // The same rescale_matrix with the bulk hand-off: one GPU call, one h2svd_expand_cells pass, ONE append
+    // of the complete cell stream instead of ~100 assign_region pushes per element.
+    static ZkMatrix rescale_matrix_bulk(Context& ctx, const Chip& fpchip, const AssignedMatrix& c_s) {
+        require(!c_s.empty(), "c_s is not empty");
+        const size_t rows = c_s.size(), cols = c_s[0].size(), count = rows * cols;
+        const std::vector<Fr> fc = gather_values(c_s);
+        std::vector<Fr> q(count), wit(count * (size_t)fpchip.W);
+        check(h2svd_rescale_witness(fpchip.gpu().raw(), fc.data(), count, (int)PRECISION_BITS, fpchip.lookup_bits, fpchip.S,
+                                    fpchip.A, q.data(), wit.data()),
+              "ZkMatrix::rescale_matrix_bulk");
+        h2svd_cells_layout* layout = nullptr;
+        check(h2svd_rescale_cells_layout((int)PRECISION_BITS, fpchip.lookup_bits, fpchip.S, fpchip.A, &layout),
+              "h2svd_rescale_cells_layout");
+        std::vector<Fr> values(count * (size_t)layout->cells);
+        check(h2svd_expand_cells(layout, fc.data(), wit.data(), count, values.data(), 0), "h2svd_expand_cells");
+        std::vector<AssignedValue> inputs;
+        inputs.reserve(count);
+        for (const auto& row : c_s) inputs.insert(inputs.end(), row.begin(), row.end());
+        const size_t base = ctx.append_units(layout, values.data(), count, inputs.data());
+        ZkMatrix out;
+        out.num_rows = rows;
+        out.num_col = cols;
+        // the quotient cell is the first cell of the final gate.sub region: 4 cells before the end of the unit
+        const size_t q_off = layout->cells - 4;
+        for (size_t i = 0; i < rows; i++) {
+            std::vector<AssignedValue> new_row;
+            for (size_t j = 0; j < cols; j++) new_row.push_back(ctx.get((ptrdiff_t)(base + (i * cols + j) * layout->cells + q_off)));
+            out.matrix.push_back(std::move(new_row));
+        }
+        h2svd_cells_layout_destroy(layout);
         return out;
     }
     // transpose_matrix (:408-419): copies cells, no constraints

@@ -34,6 +34,30 @@ static void run_zkmatrix(int lb, const double* a, const double* b, size_t n, siz
     for (const auto& row : c.dequantize(fpchip)) g_scalars.insert(g_scalars.end(), row.begin(), row.end());
 }
 
+// rescale_matrix through the per-cell path (ctx 0) and through the bulk hand-off (ctx 1) on the same quantized product
+// (needs the real library: the CPU-only build links the C ABI over the oracle, which has no cell-layout functions)
+#ifdef ZKH_WITH_EXPAND
+template <uint32_t P>
+static void run_rescale_bulk(int lb, const double* a, const double* b, size_t n, size_t k, size_t m) {
+    FixedPointChip041<P> fpchip(lb);
+    g_ctx.emplace_back(0);
+    g_ctx.emplace_back(0);
+    std::vector<std::vector<double>> am(n, std::vector<double>(k)), bm(k, std::vector<double>(m));
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < k; j++) am[i][j] = a[i * k + j];
+    for (size_t i = 0; i < k; i++) for (size_t j = 0; j < m; j++) bm[i][j] = b[i * m + j];
+    for (int which = 0; which < 2; which++) {
+        Context& ctx = g_ctx[which];
+        const ZkMatrix<P> za = ZkMatrix<P>::create(ctx, fpchip, am);
+        const ZkMatrix<P> zb = ZkMatrix<P>::create(ctx, fpchip, bm);
+        const AssignedMatrix c_s = honest_prover_mat_mul(ctx, za.matrix, zb.matrix);
+        const ZkMatrix<P> c = which == 0 ? ZkMatrix<P>::rescale_matrix(ctx, fpchip, c_s)
+                                         : ZkMatrix<P>::rescale_matrix_bulk(ctx, fpchip, c_s);
+        for (const auto& row : c.matrix)
+            for (const AssignedValue& x : row) g_scalars.push_back((double)x.index);   // the returned cells must be the same cells
+    }
+}
+#endif
+
 // src/matrix/test_matrix.rs:39-198 (test_zkvector), same inputs and call order, P = 32
 static void run_zkvector(int lb) {
     constexpr uint32_t P = 32;
@@ -143,6 +167,18 @@ int zkh_run_svd(int P, int lb, const double* m, const double* u, const double* v
         }
     });
 }
+#ifdef ZKH_WITH_EXPAND
+int zkh_run_rescale_bulk(int P, int lb, const double* a, const double* b, size_t n, size_t k, size_t m) {
+    return guarded(lb, [&] {
+        switch (P) {
+            case 32: run_rescale_bulk<32>(lb, a, b, n, k, m); break;
+            case 42: run_rescale_bulk<42>(lb, a, b, n, k, m); break;
+            case 63: run_rescale_bulk<63>(lb, a, b, n, k, m); break;
+            default: throw std::logic_error("unsupported PRECISION_BITS in the test driver");
+        }
+    });
+}
+#endif
 int zkh_run_zkvector(int lb) { return guarded(lb, [&] { run_zkvector(lb); }); }
 int zkh_run_mat_times_vec(int lb, const double* mat, const double* vec, size_t n, size_t m) {
     return guarded(lb, [&] { run_mat_times_vec(lb, mat, vec, n, m); });

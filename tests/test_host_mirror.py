@@ -28,7 +28,7 @@ def _build(tmp, gpu: bool) -> ct.CDLL:
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(HOST, "zk_host_shim.cpp")]
     if gpu:
         pkg_dir = os.path.join(ROOT, "halo2-svd041_b200")
-        cmd += [os.path.join(pkg_dir, "libh2svd_b200.so"), f"-Wl,-rpath,{pkg_dir}"]
+        cmd += ["-DZKH_WITH_EXPAND", os.path.join(pkg_dir, "libh2svd_b200.so"), f"-Wl,-rpath,{pkg_dir}"]
     else:
         corac.build()
         obj = os.path.join(tmp, "abi_over_oracle.o")
@@ -45,6 +45,8 @@ def _build(tmp, gpu: bool) -> ct.CDLL:
     lib.zkh_failure.argtypes = [ct.c_int]
     lib.zkh_run_zkmatrix.argtypes = [ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_size_t, ct.c_size_t, ct.c_void_p]
     lib.zkh_run_zkvector.argtypes = [ct.c_int]
+    if gpu:
+        lib.zkh_run_rescale_bulk.argtypes = [ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_size_t, ct.c_size_t]
     lib.zkh_run_svd.argtypes = [ct.c_int, ct.c_int] + [ct.c_void_p] * 4 + [ct.c_size_t] * 3 + [ct.c_void_p]
     lib.zkh_run_mat_times_vec.argtypes = [ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_size_t]
     lib.zkh_run_bad_shapes.argtypes = [ct.c_int]
@@ -299,3 +301,21 @@ def test_host_mirror_mat_times_vec_gpu(gpu_lib):
 def test_host_mirror_shape_asserts_gpu(gpu_lib):
     assert gpu_lib.zkh_run_bad_shapes(19) == -1
     assert b"a[0].len() == b.len()" in gpu_lib.zkh_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,lb,n,k,m", [(42, 19, 5, 4, 6), (63, 19, 9, 7, 8), (32, 12, 3, 3, 3)])
+def test_bulk_hand_off_leaves_the_same_context_as_the_per_cell_path(gpu_lib, P, lb, n, k, m):
+    """SURVEY.md 8(f)3 end to end in the C++ mirror: ZkMatrix::rescale_matrix_bulk (one GPU call, one h2svd_expand_cells pass,
+    ONE append of the complete cell stream + a replay of the per-unit layout) and ZkMatrix::rescale_matrix (~100
+    assign_region pushes per element) leave byte-identical contexts -- advice, kinds, selectors, copy constraints (same
+    order), constants, lookups -- and return the same cells."""
+    rng = np.random.default_rng(P + n)
+    a = np.ascontiguousarray(rng.uniform(-3, 3, size=(n, k)))
+    b = np.ascontiguousarray(rng.uniform(-3, 3, size=(k, m)))
+    assert gpu_lib.zkh_run_rescale_bulk(P, lb, _p(a), _p(b), n, k, m) == 0, gpu_lib.zkh_error().decode()
+    per_cell, bulk = _export(gpu_lib)
+    for key in per_cell:
+        assert per_cell[key].shape == bulk[key].shape and (per_cell[key] == bulk[key]).all(), key
+    cells = _scalars(gpu_lib)
+    assert (cells[: n * m] == cells[n * m:]).all()
