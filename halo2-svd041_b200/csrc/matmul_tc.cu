@@ -151,6 +151,30 @@ __device__ __forceinline__ void tc_tma_3d(uint32_t dst, const CUtensorMap* map, 
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+// Cluster forms (CS > 1: the CTAs of a cluster work on the same 128 rows of A and different columns of B): one TMA load
+// delivers its slice of an A-plane stage into the SAME shared-memory offset of every CTA of the cluster and signals the
+// same barrier offset in each; one tcgen05.commit arrives on the same barrier offset in every CTA.
+__device__ __forceinline__ void tc_tma_2d_multicast(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                                    uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], "
+        "[%4], %5;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 // K-major, 128-byte-swizzled operand tile (rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
     uint64_t d = 0;
@@ -312,7 +336,7 @@ tc_split_kernel(const Fr* __restrict__ a, uint32_t* __restrict__ planes_a, int n
 // element) is written under the MMAs of the next tile instead of after the mat-mul.  Bit-identical, but measured NOT to
 // pay: the MMAs read their operands from shared memory at 96 of the SM's 128 B/clk, and staging the witnesses for the
 // bulk stores needs another ~60 B/clk, so a fused tile takes 126 us against 69 us (MMAs) + 58 us (stand-alone rescale).
-template <class C, bool FUSE>
+template <class C, bool FUSE, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     Fr* __restrict__ c, int n, int k, int m, int j_begin, int j_end, int tiles_j, int num_tiles, int* err,
@@ -342,7 +366,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_SA; s++) {
             tc_mbar_init(full_a + 8 * s, 1);
-            tc_mbar_init(empty_a + 8 * s, 1);
+            tc_mbar_init(empty_a + 8 * s, CS);   // an A stage is refilled by every CTA of the cluster: all of them must have read it
         }
         for (int s = 0; s < TC_SB; s++) {
             tc_mbar_init(full_b + 8 * s, 1);
@@ -363,6 +387,14 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    // Cluster of CS CTAs: the same row block ib, CS consecutive column tiles.  crank = this CTA's column tile within the
+    // group and its slice of every A-plane stage.  No CTA may multicast before every barrier of the cluster exists.
+    const uint32_t crank = CS > 1 ? tc_cluster_rank() : 0u;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1u);
+    const int groups_j = (tiles_j + CS - 1) / CS;                  // column-tile groups per row block
+    const int num_groups = (num_tiles / tiles_j) * groups_j;       // num_tiles = tiles_i * tiles_j
+    const int cluster_id = blockIdx.x / CS, num_clusters = gridDim.x / CS;
+    if (CS > 1) tc_cluster_sync();
 
     const int kblocks = (k + TC_BKB - 1) / TC_BKB;
     const int passes = (kblocks + C::KB_PASS - 1) / C::KB_PASS;
@@ -371,8 +403,10 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t ua = 0, ub = 0, ptile = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ptile++) {
-                const int ib = tile / tiles_j, jb = tile % tiles_j;
+            for (int g = cluster_id; g < num_groups; g += num_clusters, ptile++) {
+                // jb >= tiles_j (a group's surplus CTA): still loads its slice of A for the others; its own columns
+                // are out of range (TMA zero-fills, the epilogue stores nothing)
+                const int ib = g / groups_j, jb = (g % groups_j) * CS + (int)crank;
                 tc_stamp(tl, ptile * passes, 6);
                 for (int kb = 0; kb < kblocks; kb++) {
                     const uint32_t sb = ub % TC_SB;
@@ -384,17 +418,30 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         const uint32_t sa = ua % TC_SA;
                         tc_mbar_wait(empty_a + 8 * sa, ((ua / TC_SA) & 1) ^ 1, err);
                         tc_mbar_expect_tx(full_a + 8 * sa, TC_A_BYTES);
-                        tc_tma_2d(s_a + sa * TC_A_BYTES, &tm_a, kb * TC_BKB, p * n + ib * TC_BM, full_a + 8 * sa);
+                        if constexpr (CS == 1) {
+                            tc_tma_2d(s_a + sa * TC_A_BYTES, &tm_a, kb * TC_BKB, p * n + ib * TC_BM, full_a + 8 * sa);
+                        } else {
+                            // rows [crank * 128/CS, +128/CS) of the stage, into every CTA of the cluster (the tensor map's
+                            // box is 128/CS rows; whole 1024-byte swizzle atoms)
+                            constexpr int SL = TC_BM / CS;
+                            tc_tma_2d_multicast(s_a + sa * TC_A_BYTES + crank * (SL * TC_BKB), &tm_a, kb * TC_BKB,
+                                                p * n + ib * TC_BM + (int)crank * SL, full_a + 8 * sa, CMASK);
+                        }
                         ua++;
                     }
                 }
                 tc_stamp(tl, ptile * passes, 7);
             }
+            if constexpr (CS > 1) {
+                // the other CTAs' MMA warps still signal this CTA's "empty" barriers: drain them before leaving
+                for (int i = 0; i < TC_SA; i++, ua++)
+                    tc_mbar_wait(empty_a + 8 * (ua % TC_SA), ((ua / TC_SA) & 1) ^ 1, err);
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         uint32_t ua = 0, ub = 0, round = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int g = cluster_id; g < num_groups; g += num_clusters) {
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_empty, round & 1, err);  // accumulators zeroed by the epilogue warps
                 tc_fence_after();
@@ -413,7 +460,9 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
                             for (int s = 0; s < TC_BKB / 32; s++)  // 32 bytes of K per instruction: +2 in 16-byte units
                                 tc_mma_i8(tmem_base + (uint32_t)(BJ * p), adesc + 2u * s, bdesc + 2u * s, D::IDESC, 1u);
-                            tc_commit(empty_a + 8 * sa);  // frees the A stage once these MMAs have read it
+                            // frees the A stage once these MMAs have read it (in every CTA that refills it)
+                            if constexpr (CS == 1) tc_commit(empty_a + 8 * sa);
+                            else tc_commit_multicast(empty_a + 8 * sa, CMASK);
                         }
                         __syncwarp();
                         ua++;
@@ -448,8 +497,8 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             ws.fill = 0;
         }
         uint32_t round = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int ib = tile / tiles_j, jb = tile % tiles_j;
+        for (int g = cluster_id; g < num_groups; g += num_clusters) {
+            const int ib = g / groups_j, jb = (g % groups_j) * CS + (int)crank;
             const int gi = ib * TC_BM + il;
             for (int pass = 0; pass < passes; pass++) {
                 tc_mbar_wait(tmem_full, round & 1, err);
@@ -525,6 +574,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) tc_cluster_sync();   // no CTA's shared memory goes away while a peer may still write or signal into it
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -617,7 +667,7 @@ int tc_peak_run(h2svd_ctx* ctx, double min_seconds, double* ops_per_s) {
 size_t tc_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // split kernels + mat-mul kernel of ONE engine on pre-carved plane buffers
-template <class C>
+template <class C, int CS = 1>
 int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m,
                      size_t ldk, uint8_t* a8, uint8_t* b8, int* mode, int run_if_mode, bool split_only, bool mm_only,
                      const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit, size_t j_begin = 0, size_t j_end = 0) {
@@ -640,7 +690,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
     {
         const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)(C::LA * n)};
         const cuuint64_t strides[1] = {(cuuint64_t)ldk};
-        const cuuint32_t box[2] = {(cuuint32_t)TC_BKB, (cuuint32_t)TC_BM};
+        const cuuint32_t box[2] = {(cuuint32_t)TC_BKB, (cuuint32_t)(TC_BM / CS)};   // a cluster's CTAs load a slice each
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, a8, dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -669,11 +719,49 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         set_error("fr_matmul (tensor-core engine): too many tiles");
         return H2SVD_EINVAL;
     }
+    if constexpr (CS > 1) {
+        // clusters of CS CTAs along the columns: (tiles_j rounded up to CS) column tiles per row block
+        static_assert(TC_BM % (8 * CS) == 0, "a slice is whole swizzle atoms");
+        if (fuse) {
+            set_error("fr_matmul (tensor-core engine): the fused rescale epilogue has no cluster form");
+            return H2SVD_EINVAL;
+        }
+        const long long groups = (long long)tiles_i * ((tiles_j + CS - 1) / CS);
+        const size_t smem = tc_smem_bytes<C, false>();
+        auto kern = fr_matmul_tc_kernel<C, false, CS>;
+        H2SVD_SET_SMEM(ctx, kern, smem);
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
+        int max_clusters = 0;   // co-resident clusters (GPC shapes can leave a few SMs out)
+        H2SVD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+        if (max_clusters < 1) {
+            set_error("fr_matmul (tensor-core engine): no cluster of %d CTAs fits this device", CS);
+            return H2SVD_ECUDA;
+        }
+        const long long clusters = groups < max_clusters ? groups : max_clusters;
+        cfg.gridDim = dim3((unsigned)(clusters * CS));
+        static const rs::RescaleConsts none{};
+        H2SVD_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j,
+                                      (int)tiles, ctx->d_flag, (const int*)mode, run_if_mode, ctx->d_timeline, none,
+                                      (Fr*)nullptr, (Fr*)nullptr));
+        H2SVD_LAUNCH_CHECK(ctx);
+        return H2SVD_OK;
+    }
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     if (fuse) {
         if constexpr (C::BJ == 8) {   // the fused epilogue is instantiated for the 8-column tiles of either engine
-            H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, true>), (tc_smem_bytes<C, true>()));
-            fr_matmul_tc_kernel<C, true><<<grid, TC_THREADS, tc_smem_bytes<C, true>(), ctx->stream>>>(
+            H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, true, 1>), (tc_smem_bytes<C, true>()));
+            fr_matmul_tc_kernel<C, true, 1><<<grid, TC_THREADS, tc_smem_bytes<C, true>(), ctx->stream>>>(
                 tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, *fuse, out_q,
                 out_wit);
         } else {
@@ -682,8 +770,8 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         }
     } else {
         static const rs::RescaleConsts none{};
-        H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, false>), (tc_smem_bytes<C, false>()));
-        fr_matmul_tc_kernel<C, false><<<grid, TC_THREADS, tc_smem_bytes<C, false>(), ctx->stream>>>(
+        H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, false, 1>), (tc_smem_bytes<C, false>()));
+        fr_matmul_tc_kernel<C, false, 1><<<grid, TC_THREADS, tc_smem_bytes<C, false>(), ctx->stream>>>(
             tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, none, nullptr,
             nullptr);
     }
@@ -764,7 +852,22 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
     ctx->last_engine = 3;
     H2SVD_CUDA(cudaMemsetAsync(ctx->d_mode, 0, sizeof(int), ctx->stream));
     const int width = fuse ? 8 : tc_small_tile_width(ctx, n, k, m);
+    const int cluster = fuse ? 1 : ctx->tune.matmul_cluster;
     auto small = [&](bool split_only, bool mm_only) -> int {
+        if (cluster == 2 && !split_only) {
+            switch (width) {
+                case 8: return tc_launch_engine<TcSmall8, 2>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
+                case 16: return tc_launch_engine<TcSmall16, 2>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
+                default: return tc_launch_engine<TcSmall, 2>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
+            }
+        }
+        if (cluster == 4 && !split_only) {
+            switch (width) {
+                case 8: return tc_launch_engine<TcSmall8, 4>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
+                case 16: return tc_launch_engine<TcSmall16, 4>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
+                default: return tc_launch_engine<TcSmall, 4>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
+            }
+        }
         switch (width) {
             case 8: return tc_launch_engine<TcSmall8>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, fuse, out_q, out_wit);
             case 16: return tc_launch_engine<TcSmall16>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);

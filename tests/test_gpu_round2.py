@@ -438,15 +438,37 @@ def test_small_operand_engine_tail_split(handle):
     a, b = _signed_matrix(rng, n, k, 69), _signed_matrix(rng, k, m, 69)
     try:
         handle.tune("matmul_small_width", 24)
+        handle.tune("matmul_tail_split", 1)
         split = handle.fr_matmul(a, b)
         assert handle.last_matmul_engine() == "tensor-small"
         handle.tune("matmul_tail_split", 0)
         plain = handle.fr_matmul(a, b)
     finally:
         handle.tune("matmul_small_width", 0)
-        handle.tune("matmul_tail_split", 1)
+        handle.tune("matmul_tail_split", 0)
     assert _eq(split, plain)
     assert _eq(split, corac.field_mat_mul(a, b, threads=0))
+
+
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("width", [8, 16, 24])
+@pytest.mark.parametrize("shape", [(1024, 64, 1000), (130, 200, 56), (257, 129, 9), (128, 1024, 24)])
+def test_small_operand_engine_cluster_multicast(handle, cluster, width, shape):
+    """Clusters of 2 / 4 CTAs on the same 128 rows of A: every A-plane stage is loaded once per cluster (each CTA
+    multicasts a slice).  Odd numbers of column tiles (surplus CTAs that only feed their peers), partial row blocks and
+    several K blocks: the same bytes as the oracle."""
+    rng = np.random.default_rng(80 + cluster + width)
+    n, k, m = shape
+    a, b = _signed_matrix(rng, n, k, 69), _signed_matrix(rng, k, m, 69)
+    try:
+        handle.tune("matmul_small_width", width)
+        handle.tune("matmul_cluster", cluster)
+        got = handle.fr_matmul(a, b)
+        assert handle.last_matmul_engine() == "tensor-small"
+    finally:
+        handle.tune("matmul_small_width", 0)
+        handle.tune("matmul_cluster", 0)
+    assert _eq(got, corac.field_mat_mul(a, b, threads=0))
 
 
 def test_graph_is_refused_after_a_workspace_reallocation(pkg):
