@@ -1069,7 +1069,7 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
     struct { const char* name; int* slot; } const keys[] = {
         {"matmul_tc", &ctx->tune.matmul_tc},       {"matmul_small", &ctx->tune.matmul_small},
         {"matmul_small_width", &ctx->tune.matmul_small_width},
-        {"matmul_tail_split", &ctx->tune.matmul_tail_split}, {"matmul_cluster", &ctx->tune.matmul_cluster},
+        {"matmul_cluster", &ctx->tune.matmul_cluster},
         {"matmul_karatsuba", &ctx->tune.kara},     {"matmul_streamk", &ctx->tune.streamk},
         {"matmul_variant", &ctx->tune.variant},    {"fuse_rescale", &ctx->tune.fuse_rescale},
         {"rescale_generic", &ctx->tune.rescale_generic}, {"matvec_warp_kernel", &ctx->tune.matvec_warp},

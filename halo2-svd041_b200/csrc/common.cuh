@@ -35,9 +35,8 @@ struct h2svd_ctx {
     struct Tuning {
         int matmul_tc = -1;       // tensor-core mat-mul engines: -1 auto, 0 never, 1 always
         int matmul_small = -1;    // small-operand tensor-core engine: -1 auto (range-detected on the device), 0 never
-        int matmul_tail_split = 0;   // small-operand engine: finish a partial last wave of 24-wide tiles with 8-wide tiles (measured: no gain, off)
-        int matmul_cluster = 0;      // small-operand engine: clusters of 2 or 4 CTAs share each A-plane stage by TMA multicast (0: off)
-        int matmul_small_width = 0;  // tile width of the small-operand engine: 0 auto (cost model), 8 / 16 / 24 forced
+        int matmul_cluster = 0;      // small-operand engine: clusters of 2 CTAs share each A-plane stage by TMA multicast (0: off; measured: no gain)
+        int matmul_small_width = 0;  // tile width of the small-operand engine: 0 auto (cost model), 8 / 16 / 24 / 28 forced
         int kara = -1;            // IMAD engines: -1 auto, 0 schoolbook kernels only, 1..3 force a Karatsuba variant
         int streamk = -1;         // IMAD engines: -1 auto, 0 never, 1 always use the stream-K schedule
         int variant = 0;          // schoolbook tile variant

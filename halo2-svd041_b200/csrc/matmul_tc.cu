@@ -11,12 +11,12 @@
 //
 // SMALL-OPERAND engine (TcSmall, tc_small.cuh).  Quantized fixed-point operands (ZkMatrix::new, :230-252) are small SIGNED
 // integers in standard form (|q| < 2^70 covers P = 63 and |x| < 128).  The split kernels detect this on the device; the
-// product is then taken over 9 x 10 balanced signed byte digits (s8 x s8, 10th B plane zero so that MMA N is a multiple
-// of 16) -- 90 instead of 1024 byte products per multiply-add -- and Montgomery-encoded once per C element.  Same bytes
+// product is then taken over 9 x 9 balanced signed byte digits (s8 x s8; MMA N padded to a multiple of 16 by zero rows or a
+// zero 10th B plane) -- 81 instead of 1024 byte products per multiply-add -- and Montgomery-encoded once per C element.  Same bytes
 // out.  If any operand is out of range the full-width engine runs instead: both engines are enqueued, a device flag
 // written by the split kernels decides which one does the work (no host round trip, so the sequence is graph-capturable).
 //
-// Mapping (one CTA per SM, persistent over tiles of 128 rows x BJ columns of C; BJ = 8 full-width, 24 small):
+// Mapping (one CTA per SM, persistent over tiles of 128 rows x BJ columns of C; BJ = 8 full-width, 8-28 small):
 //   * MMA M = 128 rows i of A; for ONE byte plane p at a time the A operand is the 128 x K byte matrix a_p(i,k).
 //   * MMA N = LB byte planes q x BJ columns j of B, ordered q-major: row q*BJ+j of the B operand is b_q(k,j).
 //   * the product for plane p is accumulated at TMEM column offset BJ*p: column (q*BJ+j) + BJ*p = (p+q)*BJ + j = d*BJ + j,
@@ -58,32 +58,40 @@ struct TcFull {
 };
 // Small signed operands: 9 (A) x 9 or 10 (B) balanced byte digits (a zero 10th plane where MMA N = LB * BJ would not be a
 // multiple of 16 otherwise); |D_d| <= 9 * k * 128^2 stays below 2^31 for k <= 14563: 64 K blocks (8192 k values) per pass.
-// Three tile widths: 128 x 24 (MMA N = 240: the fewest operand bytes per multiply-add, for products with at least a
-// wave of such tiles), 128 x 16 and 128 x 8 (N = 144 / 80: more, shorter tiles for the row slabs of a sharded job).
+// Four tile widths: 128 x 28 (MMA N = 252 + 4 zero rows: the fewest operand bytes per multiply-add), 128 x 24 (N = 240),
+// 128 x 16 and 128 x 8 (N = 144 / 80: more tiles for the row slabs of a sharded job); tc_small_tile_width() picks.
 template <int BJ_, int LB_, int SA_>
 struct TcSmallT {
     static constexpr int LA = fr::SMALL_DIGITS, LB = LB_, BJ = BJ_, SA = SA_, SB = 2, KB_PASS = 64;
     static constexpr bool SIGNED = true;
 };
-// Stage counts: measured (tools/tc_timeline.py), a 128 x 24 tile's MMA phase takes 22-25 us against 19 us of MMAs at the
-// measured pipe rate, with 7 AND with 10 A stages alike -- not a latency / bytes-in-flight problem.  The SS-mode MMAs read
-// (128 + N) x 32 bytes of operands from shared memory per N / 2 clocks (98 B/clk at N = 240, 121 at N = 144, 166 at N = 80)
-// while TMA writes the next stages into the same memory (40-64 B/clk): together above the SM's 128 B/clk.
+// What bounds a tile (measured: tools/tc_timeline.py, tools/cluster_bench.py, h2svd_microbench_tensor_i8):
+//   * MMAs alone (operands resident): N = 256 runs at 4.33-4.40 P op/s (128 clocks per instruction), N = 144 at 3.93 P
+//     (81 clocks), N = 80 at 2.69 P (68 clocks -- the 128 x 32-byte A operand cannot be read faster).
+//   * In the real kernel a tile's MMA phase takes 2.5-3.3 us per 1024 bytes of K for EVERY width (20-27 us at k = 1024):
+//     each K block streams 9 x 16 KB of A planes + the B stage from L2 into each of the 148 SMs, ~32 B/clk per SM =
+//     ~4700 B/clk for the chip, three quarters of the L2 throughput cap (~6300 B/clk).  7 and 10 A stages alike; clusters
+//     of 2 or 4 CTAs multicasting each A stage alike (the L2 does not deduplicate multicast below 8 CTAs).
+// Hence: the widest tile (most columns per A byte) wherever it does not cost a wave -- 28 columns use 252 of the MMA's
+// 256 N (the 24-column tile 216 of 240: its 10th B plane is padding).
+using TcSmall28 = TcSmallT<28, fr::SMALL_DIGITS, 7>;       // 7 x 16 KB + 2 x 32 KB: MMA N = 252 (+ 4 zero rows = 256)
 using TcSmall = TcSmallT<24, fr::SMALL_DIGITS + 1, 7>;     // 7 x 16 KB + 2 x 30 KB of stages
 using TcSmall16 = TcSmallT<16, fr::SMALL_DIGITS, 8>;       // 8 x 16 KB + 2 x 18 KB
 using TcSmall8 = TcSmallT<8, fr::SMALL_DIGITS + 1, 8>;     // 8 x 16 KB + 2 x 10 KB
 template <class C>
 struct TcD {
-    static constexpr int NMMA = C::LB * C::BJ;                  // MMA N
+    static constexpr int NROWS = C::LB * C::BJ;                 // rows of the B operand TMA delivers: (plane q, column j)
+    static constexpr int NMMA = (NROWS + 15) / 16 * 16;         // MMA N; rows NROWS .. NMMA-1 of a B stage stay zero
     static constexpr int NDIAG = C::LA + C::LB - 1;             // diagonals d = p + q
-    static constexpr int TCOLS = NDIAG * C::BJ;                 // TMEM columns in use
-    static constexpr int CW = C::BJ / 4;                        // columns j per epilogue warp
-    static constexpr uint32_t B_BYTES = (uint32_t)NMMA * TC_BKB;
+    static constexpr int TCOLS = C::BJ * (C::LA - 1) + NMMA;    // TMEM columns the MMAs write (the padding rows add zeros)
+    static constexpr int CW = ((C::BJ + 3) / 4 + 1) / 2 * 2;    // columns j per epilogue warp (even; the last group may hold fewer)
+    static constexpr uint32_t B_BYTES = (uint32_t)NMMA * TC_BKB;   // stage size
+    static constexpr uint32_t B_TX = (uint32_t)NROWS * TC_BKB;     // bytes one TMA load delivers
     // kind::i8 instruction descriptor: D = S32, A/B = unsigned (0) or signed (1) 8-bit, both K-major, N, M = 128
     static constexpr uint32_t IDESC = (2u << 4) | ((C::SIGNED ? 1u : 0u) << 7) | ((C::SIGNED ? 1u : 0u) << 10) |
                                       ((uint32_t)(NMMA >> 3) << 17) | ((128u >> 4) << 24);
     static_assert(NMMA % 16 == 0 && NMMA >= 16 && NMMA <= 256, "MMA N for M = 128");
-    static_assert(TCOLS <= 512 && C::BJ % 8 == 0 && CW % 2 == 0, "TMEM columns / epilogue mapping");
+    static_assert(TCOLS <= 512 && C::BJ % 4 == 0 && CW % 2 == 0 && 3 * CW < C::BJ && C::BJ <= 4 * CW, "TMEM columns / epilogue mapping");
     static_assert(B_BYTES % 1024 == 0, "B stages must keep the 1024-byte swizzle-atom alignment");
     static_assert((size_t)C::SA * TC_A_BYTES + (size_t)C::SB * B_BYTES + 256 + 1024 <= 232448, "stages exceed the SM's shared memory");
     static_assert(16 * C::SA + 16 * C::SB + 24 <= 256, "barrier block");
@@ -236,11 +244,12 @@ __device__ __forceinline__ void tc_stamp(unsigned long long* tl, uint32_t round,
 // this warp's accumulators (its TMEM lanes, its CW columns j of every diagonal) := 0, then hand them (back)
 // to the MMA warp.  Each warp zeroes only its own columns, so the warps of a lane quarter never race.
 template <class C>
-__device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, uint32_t bar) {
+__device__ __forceinline__ void tc_zero_and_release(uint32_t tcol0, uint32_t bar, int cw) {
 #pragma unroll 9
     for (int d = 0; d < TcD<C>::NDIAG; d++) {
 #pragma unroll
-        for (int pr = 0; pr < TcD<C>::CW / 2; pr++) tc_st2_zero(tcol0 + (uint32_t)(C::BJ * d + 2 * pr));
+        for (int pr = 0; pr < TcD<C>::CW / 2; pr++)
+            if (4 * TcD<C>::CW == C::BJ || 2 * pr < cw) tc_st2_zero(tcol0 + (uint32_t)(C::BJ * d + 2 * pr));
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
@@ -383,6 +392,15 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if constexpr (D::NMMA != D::NROWS) {
+        // MMA N is rounded up to a multiple of 16: the rows of every B stage that TMA never writes are zero for the
+        // whole kernel (their products land on the first columns of later diagonals, as zeros)
+        constexpr int PAD_U4 = (D::NMMA - D::NROWS) * TC_BKB / 16;
+        for (int i = threadIdx.x; i < TC_SB * PAD_U4; i += TC_THREADS)
+            reinterpret_cast<uint4*>(smem + (s_b - base) + (size_t)(i / PAD_U4) * TC_B_BYTES + (size_t)D::NROWS * TC_BKB)[i % PAD_U4] =
+                make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -411,7 +429,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 for (int kb = 0; kb < kblocks; kb++) {
                     const uint32_t sb = ub % TC_SB;
                     tc_mbar_wait(empty_b + 8 * sb, ((ub / TC_SB) & 1) ^ 1, err);
-                    tc_mbar_expect_tx(full_b + 8 * sb, TC_B_BYTES);
+                    tc_mbar_expect_tx(full_b + 8 * sb, D::B_TX);
                     tc_tma_3d(s_b + sb * TC_B_BYTES, &tm_b, kb * TC_BKB, j_begin + jb * BJ, 0, full_b + 8 * sb);
                     ub++;
                     for (int p = 0; p < C::LA; p++) {
@@ -483,10 +501,11 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ===== epilogue: thread = row of the tile =====
         const uint32_t quarter = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int il = quarter * 32 + lane;
-        const int jg = (warp - 2) >> 2;     // this warp's columns j0 .. j0+CW-1 of the tile
+        const int jg = (warp - 2) >> 2;     // this warp's columns j0 .. j0+cw-1 of the tile
         const int j0 = jg * CW;
+        const int cw = BJ - j0 < CW ? BJ - j0 : CW;   // warp-uniform; < CW only in the last group of a 28-column tile
         const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
-        tc_zero_and_release<C>(tlane + j0, tmem_empty);
+        tc_zero_and_release<C>(tlane + j0, tmem_empty, cw);
         TcWitnessStream ws;
         if (FUSE) {
             ws.warp_row0 = stage + (size_t)(warp - 2) * 32 * TcWitnessStream::ROW_U4;
@@ -510,6 +529,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 uint32_t T[CW][TW];
 #pragma unroll
                 for (int pr = 0; pr < CW / 2; pr++) {
+                    if (4 * CW != BJ && 2 * pr >= cw) break;
                     uint32_t dg[2][64];
 #pragma unroll
                     for (int d = 0; d < D::NDIAG; d++) tc_ld2(tlane + (uint32_t)(BJ * d + j0 + 2 * pr), dg[0][d], dg[1][d]);
@@ -535,12 +555,13 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 // Montgomery reductions (and the rescale witnesses) below run
                 tc_fence_before();  // order the TMEM reads above before the zeroing stores / the next MMAs
                 if (threadIdx.x == 64) tc_stamp(tl, round, 3);
-                tc_zero_and_release<C>(tlane + j0, tmem_empty);
+                tc_zero_and_release<C>(tlane + j0, tmem_empty, cw);
                 if (threadIdx.x == 64) tc_stamp(tl, round, 4);
                 // Phase 2 (overlaps the next tile's MMAs)
                 Fr res[CW];
 #pragma unroll
                 for (int q = 0; q < CW; q++) {
+                    if (4 * CW != BJ && q >= cw) break;
                     if constexpr (C::SIGNED) res[q] = fr::signed6_to_mont(T[q]);
                     else res[q] = fr::reduce_wide_acc(T[q]);
                     const int gj = j_begin + jb * BJ + j0 + q;   // this launch owns columns [j_begin, j_end)
@@ -783,12 +804,16 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
 }  // namespace
 
 int launch_microbench_i8(h2svd_ctx* ctx, int kind, double min_seconds, double* ops_per_s) {
-    if (!ops_per_s || kind < 0 || kind > 1) {
+    if (!ops_per_s || kind < 0 || kind > 3) {
         set_error("microbench_tensor_i8: bad arguments");
         return H2SVD_EINVAL;
     }
-    return kind == 0 ? tc_peak_run<TcD<TcFull>::NMMA, false>(ctx, min_seconds, ops_per_s)
-                     : tc_peak_run<TcD<TcSmall>::NMMA, true>(ctx, min_seconds, ops_per_s);
+    switch (kind) {   // 0 / 1: the shapes of the two engines; 2, 3: narrower N (the per-instruction floor)
+        case 0: return tc_peak_run<TcD<TcFull>::NMMA, false>(ctx, min_seconds, ops_per_s);
+        case 1: return tc_peak_run<TcD<TcSmall28>::NMMA, true>(ctx, min_seconds, ops_per_s);
+        case 2: return tc_peak_run<TcD<TcSmall16>::NMMA, true>(ctx, min_seconds, ops_per_s);
+        default: return tc_peak_run<TcD<TcSmall8>::NMMA, true>(ctx, min_seconds, ops_per_s);
+    }
 }
 
 bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
@@ -796,25 +821,24 @@ bool fr_matmul_tc_supported(size_t n, size_t k, size_t m) {
     return k >= 1 && n * 32 < (1ull << 31) && m * 32 < (1ull << 31) && k < (1ull << 30);
 }
 
-// Tile width of the small-operand engine for one product: estimated time = waves of tiles x time per tile, a tile being
-// bound by its MMAs (LA * 4 instructions of N / 2 cycles per K block) or by the L2 -> shared-memory delivery of its
-// operands (~6000 B/clk for the whole chip, ~100 B/clk for one SM), plus the field arithmetic of the last tile's columns.
+// Tile width of the small-operand engine for one product.  Measured (tools/cluster_bench.py, tools/tc_timeline.py): a tile's
+// MMA phase lasts about as long for 8, 16, 24 and 28 columns (~2.5-3 us per 1024 bytes of K: every MMA streams its
+// 128 x 32-byte A operand from shared memory in ~128 clocks whatever its N), so the time of a product is the number of
+// WAVES of tiles times that, plus the field arithmetic of the last tile (proportional to its columns per warp).  The
+// widest tile wins whenever it saves a wave; otherwise the narrowest with the same wave count.
 static int tc_small_tile_width(const h2svd_ctx* ctx, size_t n, size_t k, size_t m) {
-    if (ctx->tune.matmul_small_width == 8 || ctx->tune.matmul_small_width == 16 || ctx->tune.matmul_small_width == 24)
-        return ctx->tune.matmul_small_width;
+    const int w = ctx->tune.matmul_small_width;
+    if (w == 8 || w == 16 || w == 24 || w == 28) return w;
     const double sms = ctx->sm_count, kblocks = (double)((k + TC_BKB - 1) / TC_BKB);
-    const int widths[3] = {24, 16, 8}, planes_b[3] = {10, 9, 10};
-    int best = 24;
+    const int widths[4] = {8, 16, 24, 28};
+    int best = 28;
     double best_t = 1e300;
-    for (int i = 0; i < 3; i++) {
-        const double bj = widths[i], lb = planes_b[i];
+    for (int i = 0; i < 4; i++) {
+        const double bj = widths[i];
         const double tiles = (double)((n + TC_BM - 1) / TC_BM) * (double)((m + widths[i] - 1) / widths[i]);
-        const double active = tiles < sms ? tiles : sms;
         const double waves = (double)(long long)((tiles + sms - 1) / sms);
-        const double bw = 6000.0 / active < 100.0 ? 6000.0 / active : 100.0;                 // bytes per clock per busy SM
-        const double mma = 9.0 * 4.0 * (lb * bj / 2.0), bytes = 9.0 * 16384.0 + lb * bj * 128.0;
-        const double tile = kblocks * (mma > bytes / bw ? mma : bytes / bw) + 700.0;          // + accumulator hand-over
-        const double t = waves * tile + 2900.0 * (bj / 4.0);                                  // + the last tile's field arithmetic
+        const double tile = kblocks * (4600.0 + 40.0 * bj) + 700.0;                 // clocks; + accumulator hand-over
+        const double t = waves * tile + 2900.0 * (double)(((widths[i] + 3) / 4 + 1) / 2 * 2);   // + the last tile's field arithmetic
         if (t < best_t) {
             best_t = t;
             best = widths[i];
@@ -852,49 +876,32 @@ int launch_fr_matmul_tc(h2svd_ctx* ctx, const Fr* a, const Fr* b, Fr* c, size_t 
     ctx->last_engine = 3;
     H2SVD_CUDA(cudaMemsetAsync(ctx->d_mode, 0, sizeof(int), ctx->stream));
     const int width = fuse ? 8 : tc_small_tile_width(ctx, n, k, m);
+    // clusters of 2 CTAs sharing each A-plane stage by TMA multicast: byte-identical, measured to change nothing
+    // (tuning switch "matmul_cluster", off) -- the tile is bound by the MMAs' own operand reads, not by L2 delivery
     const int cluster = fuse ? 1 : ctx->tune.matmul_cluster;
     auto small = [&](bool split_only, bool mm_only) -> int {
+#define H2SVD_SMALL_ARGS ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only
         if (cluster == 2 && !split_only) {
             switch (width) {
-                case 8: return tc_launch_engine<TcSmall8, 2>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
-                case 16: return tc_launch_engine<TcSmall16, 2>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
-                default: return tc_launch_engine<TcSmall, 2>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
-            }
-        }
-        if (cluster == 4 && !split_only) {
-            switch (width) {
-                case 8: return tc_launch_engine<TcSmall8, 4>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
-                case 16: return tc_launch_engine<TcSmall16, 4>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
-                default: return tc_launch_engine<TcSmall, 4>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, mm_only, nullptr, nullptr, nullptr);
+                case 8: return tc_launch_engine<TcSmall8, 2>(H2SVD_SMALL_ARGS, nullptr, nullptr, nullptr);
+                case 16: return tc_launch_engine<TcSmall16, 2>(H2SVD_SMALL_ARGS, nullptr, nullptr, nullptr);
+                case 24: return tc_launch_engine<TcSmall, 2>(H2SVD_SMALL_ARGS, nullptr, nullptr, nullptr);
+                default: return tc_launch_engine<TcSmall28, 2>(H2SVD_SMALL_ARGS, nullptr, nullptr, nullptr);
             }
         }
         switch (width) {
-            case 8: return tc_launch_engine<TcSmall8>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, fuse, out_q, out_wit);
-            case 16: return tc_launch_engine<TcSmall16>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
-            default: return tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, split_only, mm_only, nullptr, nullptr, nullptr);
+            case 8: return tc_launch_engine<TcSmall8>(H2SVD_SMALL_ARGS, fuse, out_q, out_wit);
+            case 16: return tc_launch_engine<TcSmall16>(H2SVD_SMALL_ARGS, nullptr, nullptr, nullptr);
+            case 24: return tc_launch_engine<TcSmall>(H2SVD_SMALL_ARGS, nullptr, nullptr, nullptr);
+            default: return tc_launch_engine<TcSmall28>(H2SVD_SMALL_ARGS, nullptr, nullptr, nullptr);
         }
+#undef H2SVD_SMALL_ARGS
     };
     H2SVD_TRY(small(true, false));
     H2SVD_TRY(tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, true, false, nullptr,
                                        nullptr, nullptr));
-    // A partial last wave of 128 x 24 tiles costs a whole tile time (N = 1024: 344 tiles on 148 SMs = 2.32 waves): when
-    // the last wave would be less than 60 % full, the 24-wide tiles take only the columns that fill WHOLE waves and the
-    // remaining columns go to 128 x 8 tiles (a third as long, same byte planes) in a second launch.
-    size_t cols24 = 0;
-    if (width == 24 && !fuse && ctx->tune.matmul_tail_split != 0) {
-        const size_t sms = (size_t)ctx->sm_count, ti = (n + TC_BM - 1) / TC_BM, t24 = ti * ((m + 23) / 24);
-        const size_t full = t24 / sms, last = t24 % sms;
-        const size_t cj = full * sms / ti;   // column tiles per row block inside the whole waves
-        if (full >= 1 && last != 0 && last * 10 < sms * 6 && cj >= 1 && cj * 24 < m) cols24 = cj * 24;
-    }
-    if (cols24 != 0) {
-        H2SVD_TRY(tc_launch_engine<TcSmall>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, true, nullptr,
-                                            nullptr, nullptr, 0, cols24));
-        H2SVD_TRY(tc_launch_engine<TcSmall8>(ctx, encode, a, b, c, n, k, m, ldk, sa8, sb8, ctx->d_mode, 0, false, true, nullptr,
-                                             nullptr, nullptr, cols24, m));
-    } else {
-        H2SVD_TRY(small(false, true));
-    }
+    // (Finishing a partial last wave of wide tiles with 128 x 8 tiles was measured and dropped: narrow tiles take as long.)
+    H2SVD_TRY(small(false, true));
     return tc_launch_engine<TcFull>(ctx, encode, a, b, c, n, k, m, ldk, fa8, fb8, ctx->d_mode, 1, false, true, fuse, out_q,
                                     out_wit);
 }

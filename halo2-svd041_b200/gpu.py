@@ -104,7 +104,7 @@ class Handle:
         _ffi.check(self._lib.h2svd_sync(self._h))
 
     # ---- triage / tuning switches (per handle; not part of the public header) ----
-    TUNE_KEYS = ("matmul_tc", "matmul_small", "matmul_small_width", "matmul_tail_split", "matmul_cluster", "matmul_karatsuba", "matmul_streamk", "matmul_variant", "fuse_rescale",
+    TUNE_KEYS = ("matmul_tc", "matmul_small", "matmul_small_width", "matmul_cluster", "matmul_karatsuba", "matmul_streamk", "matmul_variant", "fuse_rescale",
                  "rescale_generic", "matvec_warp_kernel", "matvec_seg", "matvec_segs", "matvec_x2", "rescale_ch", "rescale_store")
 
     def tune(self, key: str, value: int) -> None:

@@ -354,7 +354,8 @@ int h2svd_microbench_imad(h2svd_ctx *ctx, int kind, int iters, double *ops_per_s
 int h2svd_microbench_hbm(h2svd_ctx *ctx, int kind, size_t bytes, double *gb_per_s);
 /* Tensor-pipe micro-benchmark, the measured denominator of the tensor-core mat-mul engines: back-to-back
  * tcgen05.mma.kind::i8 of the real kernels' shape with operands resident in shared memory, one CTA per SM.
- * kind 0 = unsigned, M128 N256 K32 (full-width engine); 1 = signed, M128 N240 K32 (small-operand engine).
+ * kind 0 = unsigned, M128 N256 K32 (full-width engine); 1 = signed, M128 N256 K32 (small-operand engine, 28-column tiles);
+ * 2, 3 = signed, N144 / N80 (its 16- and 8-column tiles: the time of one MMA does not shrink with N).
  * min_seconds <= 0: best of three ~4 ms launches (burst); > 0: launches back to back for at least that long (sustained
  * under the power cap).  Writes 8-bit ops per second (multiply-add = 2 ops). */
 int h2svd_microbench_tensor_i8(h2svd_ctx *ctx, int kind, double min_seconds, double *ops_per_s);

@@ -356,10 +356,11 @@ def test_freivalds_witness_with_seg_kernel_two_jobs(handle):
         assert _eq(fw[key], val), key
 
 
-@pytest.mark.parametrize("width", [8, 16, 24])
-@pytest.mark.parametrize("n,k,m", [(129, 130, 50), (300, 257, 47), (128, 1024, 100), (40, 8300, 30)])
+@pytest.mark.parametrize("width", [8, 16, 24, 28])
+@pytest.mark.parametrize("n,k,m", [(129, 130, 50), (300, 257, 47), (128, 1024, 100), (40, 8300, 30), (256, 256, 57)])
 def test_small_operand_engine_every_tile_width(handle, width, n, k, m):
-    """The three tile widths of the small-operand engine (128 x 8 / 16 / 24: MMA N = 80 / 144 / 240) forced in turn on ragged
+    """The four tile widths of the small-operand engine (128 x 8 / 16 / 24 / 28: MMA N = 80 / 144 / 240 / 252 + 4 zero rows;
+    the 28-column tile splits its columns 8 / 8 / 8 / 4 over the epilogue warps) forced in turn on ragged
     shapes (m not a multiple of any width, n not a multiple of 128, k tails, two accumulation passes): same bytes."""
     rng = np.random.default_rng(n + k + m)
     a, b = _signed_matrix(rng, n, k, 69), _signed_matrix(rng, k, m, 69)
@@ -430,31 +431,11 @@ def test_mat_vec_prefix_interleaved_products_match_oracle(handle, x2, seg, rows,
     assert _eq(out.cpu().numpy().view(np.uint64), corac.mat_vec_prefix(a, v, threads=0))
 
 
-def test_small_operand_engine_tail_split(handle):
-    """1024 x 64 x 1000: 336 tiles of 128 x 24 = 2.27 waves on 148 SMs, so the 24-wide launch takes the 888 columns that fill
-    two whole waves and a second launch of 128 x 8 tiles the other 112: same bytes as the unsplit product and the oracle."""
-    rng = np.random.default_rng(8)
-    n, k, m = 1024, 64, 1000
-    a, b = _signed_matrix(rng, n, k, 69), _signed_matrix(rng, k, m, 69)
-    try:
-        handle.tune("matmul_small_width", 24)
-        handle.tune("matmul_tail_split", 1)
-        split = handle.fr_matmul(a, b)
-        assert handle.last_matmul_engine() == "tensor-small"
-        handle.tune("matmul_tail_split", 0)
-        plain = handle.fr_matmul(a, b)
-    finally:
-        handle.tune("matmul_small_width", 0)
-        handle.tune("matmul_tail_split", 0)
-    assert _eq(split, plain)
-    assert _eq(split, corac.field_mat_mul(a, b, threads=0))
-
-
-@pytest.mark.parametrize("cluster", [2, 4])
-@pytest.mark.parametrize("width", [8, 16, 24])
+@pytest.mark.parametrize("cluster", [2])
+@pytest.mark.parametrize("width", [8, 16, 24, 28])
 @pytest.mark.parametrize("shape", [(1024, 64, 1000), (130, 200, 56), (257, 129, 9), (128, 1024, 24)])
 def test_small_operand_engine_cluster_multicast(handle, cluster, width, shape):
-    """Clusters of 2 / 4 CTAs on the same 128 rows of A: every A-plane stage is loaded once per cluster (each CTA
+    """Clusters of 2 CTAs on the same 128 rows of A: every A-plane stage is loaded once per cluster (each CTA
     multicasts a slice).  Odd numbers of column tiles (surplus CTAs that only feed their peers), partial row blocks and
     several K blocks: the same bytes as the oracle."""
     rng = np.random.default_rng(80 + cluster + width)

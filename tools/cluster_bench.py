@@ -1,5 +1,5 @@
 """Times the small-operand tensor-core mat-mul with and without cluster multicast of the A planes (developer tool, run
-under gpurun): tile widths 8/16/24 x cluster sizes 1/2/4 on the shapes of the sharded jobs; every variant must produce
+under gpurun): tile widths 8/16/24/28 x cluster sizes 1/2 on the shapes of the sharded jobs; every variant must produce
 the same bytes."""
 import importlib
 import os
@@ -15,6 +15,8 @@ torch.cuda.set_stream(stream)
 h = pkg.Handle(0, stream.cuda_stream)
 gen = torch.Generator(device=dev)
 gen.manual_seed(1)
+for kind, label in ((0, "u8 N256"), (1, "s8 N256"), (2, "s8 N144"), (3, "s8 N80")):
+    print(f"tensor pipe {label}: {h.microbench_tensor_i8(kind) / 1e15:.3f} P op/s", flush=True)
 shapes = [(1024, 1024, 1024), (512, 1024, 1024), (256, 1024, 1024), (128, 1024, 1024), (4096, 2048, 4096), (512, 2048, 4096)]
 if os.environ.get("SHAPES"):
     shapes = [tuple(int(x) for x in sh.split("x")) for sh in os.environ["SHAPES"].split(",")]
@@ -27,8 +29,8 @@ for (n, k, m) in shapes:
     h.quantize_dev(af, 63, a)
     h.quantize_dev(bf, 63, b)
     ref = None
-    for width in (0, 24, 16, 8):
-        for cluster in (0, 2, 4):
+    for width in (0, 28, 24, 16, 8):
+        for cluster in (0, 2):
             h.tune("matmul_small_width", width)
             h.tune("matmul_cluster", cluster)
             ts = []
