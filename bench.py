@@ -573,7 +573,7 @@ def measure_kernels(h, pkg, torch, device, stream, flush_buf, a_slab, b_dev, buf
     t_mm = timed(lambda: h.fr_matmul_dev(a_slab, b_dev, c_tmp))
     engine = h.last_matmul_engine()
     same = bool((c_tmp == bufs["c_s"]).all().item())
-    ops_per_muladd = {"tensor-small": 2.0 * 9 * 10, "tensor": 2.0 * 32 * 32}.get(engine)
+    ops_per_muladd = {"tensor-small": 2.0 * 9 * 9, "tensor": 2.0 * 32 * 32}.get(engine)   # algorithmic digit products
     mmd = {"kernel": f"fr_matmul_tc_kernel<{'TcSmall' if engine == 'tensor-small' else 'TcFull'}> + its byte-plane split kernels",
            "engine": engine, "ms": t_mm, "fr_mul_adds_per_s": rows * k * m / (t_mm * 1e-3), "same_bytes_as_step": same}
     if ops_per_muladd:
@@ -583,7 +583,8 @@ def measure_kernels(h, pkg, torch, device, stream, flush_buf, a_slab, b_dev, buf
         ach = rows * k * m * ops_per_muladd / (t_mm * 1e-3) / 1e12
         mmd.update({"bound": "tensor", "achieved": ach, "peak": burst, "unit": "TOP/s (8-bit)", "frac": ach / burst,
                     "op": f"8-bit multiply-add = 2 ops; {int(ops_per_muladd // 2)} byte products per Fr mul-add "
-                          + ("(9 x 10 signed digits)" if engine == "tensor-small" else "(32 x 32 byte planes)"),
+                          + ("(9 x 9 signed byte digits; the MMAs execute 82-90 with the N padding of the tile width)"
+                             if engine == "tensor-small" else "(32 x 32 byte planes)"),
                     "peak_source": "measured live: h2svd_microbench_tensor_i8 (back-to-back tcgen05.mma kind::i8 of the kernel's "
                                    "shape, operands resident in smem, all SMs), burst",
                     "peak_sustained_2s": sust, "peak_proxy_2x_bf16": 2.0 * measured_peaks().get("bf16_tflops", 1590.0),

@@ -1075,7 +1075,7 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
         {"rescale_generic", &ctx->tune.rescale_generic}, {"matvec_warp_kernel", &ctx->tune.matvec_warp},
         {"matvec_seg", &ctx->tune.matvec_seg},       {"matvec_x2", &ctx->tune.matvec_x2},
         {"matvec_segs", &ctx->tune.matvec_segs},       {"rescale_ch", &ctx->tune.rescale_ch},
-        {"rescale_store", &ctx->tune.rescale_store},
+        {"rescale_store", &ctx->tune.rescale_store}, {"rescale_fast_sums", &ctx->tune.rescale_fast_sums},
     };
     for (const auto& e : keys)
         if (strcmp(e.name, key) == 0) {

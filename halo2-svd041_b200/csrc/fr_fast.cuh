@@ -353,7 +353,65 @@ FR_HD Fr mont_mul_small(uint32_t l, const Fr& c) {
     const uint32_t ov[8] = {lo32(O[0]), hi32(O[0]), lo32(O[1]), hi32(O[1]), lo32(O[2]), hi32(O[2]), lo32(O[3]), hi32(O[3])};
     Fr o;
     add8_carry_in(o.l, ev, ov, 0u, 0u);
-    cond_sub_r(o.l);
+    // o < l * c / 2^32 + r: for the small l of a limb decomposition (l < 2^lb) o exceeds r about once in 2^(32 - lb) calls,
+    // and o >= r needs o's top limb >= r's: a rarely-taken branch replaces the 17-instruction compare-and-select
+    if (o.l[7] >= modulus(7)) cond_sub_r(o.l);
+    return o;
+}
+
+// ---- running sums of small multiples of fixed constants, every partial sum canonical --------------------------------
+// s_i = sum_{j<=i} l_j * rho_j mod r for 32-bit l_j and fixed canonical rho_j (range-check running sums: rho_j = the
+// Montgomery form of 2^(lb*j)), WITHOUT a Montgomery step and a compare-and-subtract per term:
+//   U_i = sum l_j * rho_j            the unreduced integer (< 2^32 * r when sum l_j < 2^32): 8 wide products per term,
+//   F_i = sum l_j * phi_j            phi_j = floor(rho_j * 2^64 / r): a 64-bit fixed-point estimate of U_i / r from below,
+//   Q   = floor(F_i / 2^64)          = floor(U_i / r) or one less; it can be one less only when the fraction of F_i is
+//                                    within sum l_j / 2^64 < 2^-32 of 1,
+//   s_i = U_i - Q * r = U_i + Q * (2^256 - r) mod 2^256   (8 wide products; s_i < 2r < 2^256 so the wrap is exact)
+// and a compare-and-subtract only in the rare case the top 20 fraction bits are all ones.  The partial sums are independent
+// of each other given (U_i, F_i): no dependent chain through the canonical values.
+struct SmallSum {
+    uint64_t E[5], O[5];     // U = E + O * 2^32 (64-bit columns at even / odd limbs, as in mont_mul_fast)
+    uint32_t f0, f1, f2;     // F = f0 + f1 * 2^32 + f2 * 2^64
+};
+FR_HD void small_sum_init(SmallSum& s) {
+#pragma unroll
+    for (int p = 0; p < 5; p++) s.E[p] = s.O[p] = 0;
+    s.f0 = s.f1 = s.f2 = 0;
+}
+FR_HD void small_sum_add(SmallSum& s, uint32_t l, const Fr& rho, uint32_t phi_lo, uint32_t phi_hi) {
+    row4(s.E, rho.l[0], rho.l[2], rho.l[4], rho.l[6], l);
+    row4(s.O, rho.l[1], rho.l[3], rho.l[5], rho.l[7], l);
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32       %2, %2, 0;\n\t"
+        "mad.lo.cc.u32  %1, %3, %5, %1;\n\t"
+        "madc.hi.u32    %2, %3, %5, %2;"
+        : "+r"(s.f0), "+r"(s.f1), "+r"(s.f2)
+        : "r"(l), "r"(phi_lo), "r"(phi_hi));
+#else
+    const unsigned __int128 f = ((unsigned __int128)s.f2 << 64) | ((uint64_t)s.f1 << 32) | s.f0;
+    const unsigned __int128 g = f + (unsigned __int128)l * (((uint64_t)phi_hi << 32) | phi_lo);
+    s.f0 = (uint32_t)g;
+    s.f1 = (uint32_t)(g >> 32);
+    s.f2 = (uint32_t)(g >> 64);
+#endif
+}
+FR_HD Fr small_sum_value(const SmallSum& s) {
+    uint64_t E[5], O[5];
+#pragma unroll
+    for (int p = 0; p < 5; p++) {
+        E[p] = s.E[p];
+        O[p] = s.O[p];
+    }
+    // 2^256 - r: r is odd, so only limb 0 takes the +1 of the two's complement
+    row4(E, 0u - modulus(0), ~modulus(2), ~modulus(4), ~modulus(6), s.f2);
+    row4(O, ~modulus(1), ~modulus(3), ~modulus(5), ~modulus(7), s.f2);
+    const uint32_t ev[8] = {lo32(E[0]), hi32(E[0]), lo32(E[1]), hi32(E[1]), lo32(E[2]), hi32(E[2]), lo32(E[3]), hi32(E[3])};
+    const uint32_t ov[8] = {0u, lo32(O[0]), hi32(O[0]), lo32(O[1]), hi32(O[1]), lo32(O[2]), hi32(O[2]), lo32(O[3])};
+    Fr o;
+    add8_carry_in(o.l, ev, ov, 0u, 0u);   // mod 2^256
+    if (s.f1 >= 0xFFFFF000u) cond_sub_r(o.l);
     return o;
 }
 

@@ -111,16 +111,16 @@ constexpr int RS_CTAS_PER_SM = (int)((227 * 1024) / (RS_SMEM + 1024)) > 0 ? (int
 using WitnessStream = WitnessStreamT<RS_CH, RS_NBUF>;   // 256-byte bursts, double-buffered rows
 // the rescale kernel itself is instantiated for several burst sizes (tuning switch "rescale_ch"): fewer witnesses per
 // burst = a smaller staging area = more resident CTAs per SM (the kernel is latency-, not bandwidth-limited)
-template <int CH, int NBUF = RS_NBUF>
+template <int CH, int NBUF = RS_NBUF, int MAXCTA = 4>
 struct RsCfg {
     static constexpr int ROW_U4 = CH * 2 + 1;
     static constexpr size_t SMEM = (size_t)RS_THREADS * NBUF * ROW_U4 * sizeof(uint4);
     static constexpr int CTAS_PER_SM_SMEM = (int)((227 * 1024) / (SMEM + 1024));
-    static constexpr int CTAS_PER_SM = CTAS_PER_SM_SMEM < 4 ? CTAS_PER_SM_SMEM : 4;   // 128 threads x 120 registers: 4 by registers
+    static constexpr int CTAS_PER_SM = CTAS_PER_SM_SMEM < MAXCTA ? CTAS_PER_SM_SMEM : MAXCTA;   // 128 threads x 120 registers: 4 by registers (5: 96)
 };
 
-template <int CH, int NBUF>
-__global__ void __launch_bounds__(RS_THREADS, RsCfg<CH, NBUF>::CTAS_PER_SM)
+template <int CH, int NBUF, int MAXCTA, bool FAST>
+__global__ void __launch_bounds__(RS_THREADS, RsCfg<CH, NBUF, MAXCTA>::CTAS_PER_SM)
 rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict__ out_wit, size_t count,
                const __grid_constant__ RescaleConsts k) {
     extern __shared__ __align__(16) uint4 rs_stage[];
@@ -141,7 +141,13 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
         const bool live = lane < ws.valid;
         const size_t e = live ? e0 + lane : count - 1;
         const Fr am = ldg_fr(cs + e);
-        const Fr q = rescale_element(ws, k, am);
+#ifdef RS_STORE_ONLY   // experiment: the store path alone (W copies of the input instead of the witnesses)
+        for (int w = 0; w < k.p.W; w++) ws.put(am);
+        ws.flush();
+        const Fr q = am;
+#else
+        const Fr q = rescale_element<FAST>(ws, k, am);
+#endif
         if (live) st_fr(out_q + e, q);
     }
     // shared memory must outlive every bulk read, and the writes must be complete at kernel end.  Bulk async-groups
@@ -215,6 +221,7 @@ rescale_stg_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __rest
 
 // check_abs_less_than(x, bnd) (reference src/matrix/mod.rs:425-437), optionally of a difference x - y
 // (check_mat_diff :441-459): witnesses [x - y]?, t = d + (bnd - 1), check_big_less_than_safe(t, 2*bnd - 1).
+template <bool FAST>
 __global__ void __launch_bounds__(RS_THREADS)
 abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __restrict__ out_wit, size_t count,
                      const __grid_constant__ AbsLtConsts k) {
@@ -240,7 +247,7 @@ abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __r
         }
         const Fr tm = fr::add_fast(dm, k.m_add);     // gate.add(x, Constant(bnd - 1))
         ws.put(tm);
-        stream_cbls(ws, k.lc, fr::mont_reduce_fast(tm), tm, k.n, k.i_pow, k.i_bound, k.m_pow, k.m_bound);
+        stream_cbls<FAST>(ws, k.lc, fr::mont_reduce_fast(tm), tm, k.n, k.i_pow, k.i_bound, k.m_pow, k.m_bound);
         ws.flush();
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every lane: see rescale_kernel
@@ -248,6 +255,7 @@ abs_less_than_kernel(const Fr* __restrict__ x, const Fr* __restrict__ y, Fr* __r
 
 // RangeChip::range_check(x, range_bits) with n = ceil(range_bits / lb) limbs: limbs + running sums (none when
 // n == 1), plus last_limb * 2^(lb - rem) when range_bits % lb = rem > 1 (ZkVector::entries_less_than, :185-197).
+template <bool FAST>
 __global__ void __launch_bounds__(RS_THREADS)
 range_check_kernel(const Fr* __restrict__ x, Fr* __restrict__ out_wit, size_t count, const __grid_constant__ RangeConsts k) {
     extern __shared__ __align__(16) uint4 rs_stage[];
@@ -267,7 +275,7 @@ range_check_kernel(const Fr* __restrict__ x, Fr* __restrict__ out_wit, size_t co
         const size_t e = lane < ws.valid ? e0 + lane : count - 1;
         const Fr xm = ldg_fr(x + e);
         const Fr xi = fr::mont_reduce_fast(xm);
-        stream_range_check(ws, k.lc, xi, k.n);
+        stream_range_check<FAST>(ws, k.lc, xi, k.n);
         if (k.rem > 1) {
             if (k.n == 1) {
                 ws.put(fr::mont_mul_fast(xm, k.m_shift));   // gate.mul(x, 2^(lb-rem)): x is the only "limb", at full width
@@ -309,12 +317,47 @@ int rescale_params(int P, int lb, int S, int A, int* n_d, int* n_r) {
     return 4 + (nd >= 2 ? 4 * nd : 2) + (nr >= 2 ? 4 * nr : 2);
 }
 
+// floor(x * 2^64 / r) for canonical x < r: 64 steps of shift-compare-subtract
+static uint64_t frac64_of_r(const Fr& x) {
+    uint32_t m[8], rem[8];
+    for (int i = 0; i < 8; i++) {
+        m[i] = fr::modulus(i);
+        rem[i] = x.l[i];
+    }
+    uint64_t q = 0;
+    for (int b = 63; b >= 0; b--) {
+        uint32_t carry = 0;   // rem <<= 1 (rem < r < 2^254: no overflow)
+        for (int i = 0; i < 8; i++) {
+            const uint32_t nc = rem[i] >> 31;
+            rem[i] = (rem[i] << 1) | carry;
+            carry = nc;
+        }
+        bool ge = true;
+        for (int i = 7; i >= 0; i--)
+            if (rem[i] != m[i]) {
+                ge = rem[i] > m[i];
+                break;
+            }
+        if (ge) {
+            fr::sub_n<8>(rem, rem, m);
+            q |= 1ull << b;
+        }
+    }
+    return q;
+}
 static void fill_limb_consts(LimbConsts& lc, int lb, int npos) {
     lc.lb = lb;
     lc.lb_mask = lb == 32 ? 0xffffffffu : ((1u << lb) - 1u);
+    // sum of npos limbs < npos * 2^lb must stay below 2^32 (fr::SmallSum)
+    lc.fast_sums = ((unsigned long long)npos << lb) <= (1ull << 32) ? 1 : 0;
     const Fr m_2_32 = fr::to_mont(fr::pow2(32));
-    for (int i = 0; i < MAX_POS; i++)
-        lc.c[i] = i < npos ? fr::mont_mul(fr::to_mont(fr::pow2(lb * i)), m_2_32) : fr::zero();
+    for (int i = 0; i < MAX_POS; i++) {
+        lc.rho[i] = i < npos ? fr::to_mont(fr::pow2(lb * i)) : fr::zero();
+        lc.c[i] = i < npos ? fr::mont_mul(lc.rho[i], m_2_32) : fr::zero();
+        const uint64_t phi = frac64_of_r(lc.rho[i]);
+        lc.phi_lo[i] = (uint32_t)phi;
+        lc.phi_hi[i] = (uint32_t)(phi >> 32);
+    }
 }
 static int bit_length(const Fr& x) {
     for (int i = 7; i >= 0; i--)
@@ -347,14 +390,14 @@ int make_rescale_consts(int P, int lb, int S, int A, rs::RescaleConsts* out) {
     return p.W;
 }
 
-template <int CH, int NBUF = RS_NBUF>
+template <int CH, int NBUF = RS_NBUF, int MAXCTA = 4, bool FAST = false>
 static int launch_rescale_ch(h2svd_ctx* ctx, const Fr* cs, size_t count, const rs::RescaleConsts& k, Fr* out_q, Fr* out_wit) {
-    using cfg = RsCfg<CH, NBUF>;
-    H2SVD_SET_SMEM(ctx, (rescale_kernel<CH, NBUF>), cfg::SMEM);
+    using cfg = RsCfg<CH, NBUF, MAXCTA>;
+    H2SVD_SET_SMEM(ctx, (rescale_kernel<CH, NBUF, MAXCTA, FAST>), cfg::SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
     const size_t cap = (size_t)ctx->sm_count * cfg::CTAS_PER_SM;  // resident CTAs, grid-stride beyond
     if (blocks > cap) blocks = cap;
-    rescale_kernel<CH, NBUF><<<(unsigned)blocks, RS_THREADS, cfg::SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
+    rescale_kernel<CH, NBUF, MAXCTA, FAST><<<(unsigned)blocks, RS_THREADS, cfg::SMEM, ctx->stream>>>(cs, out_q, out_wit, count, k);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }
@@ -376,8 +419,14 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
         H2SVD_LAUNCH_CHECK(ctx);
         return H2SVD_OK;
     }
-    RescaleConsts k;
-    make_rescale_consts(P, lb, S, A, &k);
+    // the constants of a configuration cost ~50 us of host arithmetic: keep the last one
+    static thread_local struct { int P, lb, S, A; bool ok; RescaleConsts k; } cache = {0, 0, 0, 0, false, {}};
+    if (!cache.ok || cache.P != P || cache.lb != lb || cache.S != S || cache.A != A) {
+        make_rescale_consts(P, lb, S, A, &cache.k);
+        cache.P = P; cache.lb = lb; cache.S = S; cache.A = A;
+        cache.ok = true;
+    }
+    const RescaleConsts& k = cache.k;
     if (ctx->tune.rescale_store == 2) {
         H2SVD_SET_SMEM(ctx, rescale_stg_kernel, RG_SMEM);
         size_t blocks = (count + RG_THREADS - 1) / RG_THREADS;
@@ -410,12 +459,15 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
             }
         }
     }
+    // Burst sizes / residencies measured on the N = 1024 rescale: 8 witnesses per burst, two staging
+    // rows per lane, 3 CTAs per SM is the fastest; 4- and 6-witness bursts remain as tuning switches.
+    const bool fast = k.lc.fast_sums && ctx->tune.rescale_fast_sums != 0;
     switch (ctx->tune.rescale_ch) {
-        case 16: return launch_rescale_ch<16, 1>(ctx, cs, count, k, out_q, out_wit);   // 512-byte bursts, one buffer
-        case 12: return launch_rescale_ch<12, 1>(ctx, cs, count, k, out_q, out_wit);   // 384-byte bursts, one buffer
         case 4: return launch_rescale_ch<4>(ctx, cs, count, k, out_q, out_wit);
         case 6: return launch_rescale_ch<6>(ctx, cs, count, k, out_q, out_wit);
-        default: return launch_rescale_ch<8>(ctx, cs, count, k, out_q, out_wit);
+        default:
+            return fast ? launch_rescale_ch<8, RS_NBUF, 4, true>(ctx, cs, count, k, out_q, out_wit)
+                        : launch_rescale_ch<8>(ctx, cs, count, k, out_q, out_wit);
     }
 }
 
@@ -454,11 +506,16 @@ int launch_abs_less_than(h2svd_ctx* ctx, const Fr* x, const Fr* y, size_t count,
     k.i_bound = bound;
     k.m_pow = fr::to_mont(k.i_pow);
     k.m_bound = fr::to_mont(bound);
-    H2SVD_SET_SMEM(ctx, abs_less_than_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
     const size_t cap = (size_t)ctx->sm_count * RS_CTAS_PER_SM;
     if (blocks > cap) blocks = cap;
-    abs_less_than_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, y, out_wit, count, k);
+    if (k.lc.fast_sums && ctx->tune.rescale_fast_sums != 0) {
+        H2SVD_SET_SMEM(ctx, abs_less_than_kernel<true>, RS_SMEM);
+        abs_less_than_kernel<true><<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, y, out_wit, count, k);
+    } else {
+        H2SVD_SET_SMEM(ctx, abs_less_than_kernel<false>, RS_SMEM);
+        abs_less_than_kernel<false><<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, y, out_wit, count, k);
+    }
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }
@@ -483,11 +540,16 @@ int launch_range_check(h2svd_ctx* ctx, const Fr* x, size_t count, int range_bits
     fill_limb_consts(k.lc, lb, k.n);
     k.m_shift = k.rem > 1 ? fr::to_mont(fr::pow2(lb - k.rem)) : fr::zero();
     k.c_shift = k.rem > 1 ? fr::mont_mul(k.m_shift, fr::to_mont(fr::pow2(32))) : fr::zero();
-    H2SVD_SET_SMEM(ctx, range_check_kernel, RS_SMEM);
     size_t blocks = (count + RS_THREADS - 1) / RS_THREADS;
     const size_t cap = (size_t)ctx->sm_count * RS_CTAS_PER_SM;
     if (blocks > cap) blocks = cap;
-    range_check_kernel<<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, out_wit, count, k);
+    if (k.lc.fast_sums && ctx->tune.rescale_fast_sums != 0) {
+        H2SVD_SET_SMEM(ctx, range_check_kernel<true>, RS_SMEM);
+        range_check_kernel<true><<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, out_wit, count, k);
+    } else {
+        H2SVD_SET_SMEM(ctx, range_check_kernel<false>, RS_SMEM);
+        range_check_kernel<false><<<(unsigned)blocks, RS_THREADS, RS_SMEM, ctx->stream>>>(x, out_wit, count, k);
+    }
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }

@@ -20,7 +20,10 @@ struct RescaleParams {
 struct LimbConsts {
     int lb;
     uint32_t lb_mask;
-    Fr c[MAX_POS];  // c[i] = 2^(lb*i) * 2^288 mod r
+    int fast_sums;                                // npos * 2^lb <= 2^32: the SmallSum running sums (fr_fast.cuh) are exact
+    Fr c[MAX_POS];                                // c[i] = 2^(lb*i) * 2^288 mod r
+    Fr rho[MAX_POS];                              // rho[i] = 2^(lb*i) * 2^256 mod r, canonical integer = M(2^(lb*i))
+    uint32_t phi_lo[MAX_POS], phi_hi[MAX_POS];    // floor(rho[i] * 2^64 / r)
 };
 struct RescaleConsts {
     RescaleParams p;
@@ -200,9 +203,28 @@ __device__ __forceinline__ Fr shr_small(const Fr& y, int s) {  // 1 <= s <= 32
 #ifndef RS_LIMB_PAIRS
 #define RS_LIMB_PAIRS 0
 #endif
-template <class WS>
+// FAST: the running sums through fr::SmallSum (needs k.fast_sums; the kernels are instantiated both ways).
+template <bool FAST = false, class WS>
 __device__ __forceinline__ void stream_range_check(WS& ws, const LimbConsts& k, Fr y, int n) {
     if (n == 1) return;
+    if constexpr (FAST) {
+        fr::SmallSum ss;
+        fr::small_sum_init(ss);
+        {
+            const uint32_t l = y.l[0] & k.lb_mask;
+            y = shr_small(y, k.lb);
+            fr::small_sum_add(ss, l, k.rho[0], k.phi_lo[0], k.phi_hi[0]);
+            ws.put(fr::mont_mul_small(l, k.c[0]));
+        }
+        for (int i = 1; i < n; i++) {
+            const uint32_t l = y.l[0] & k.lb_mask;
+            y = shr_small(y, k.lb);
+            ws.put(fr::mont_mul_small(l, k.c[0]));
+            fr::small_sum_add(ss, l, k.rho[i], k.phi_lo[i], k.phi_hi[i]);
+            ws.put(fr::small_sum_value(ss));
+        }
+        return;
+    }
     Fr sum;
     {
         const uint32_t l = y.l[0] & k.lb_mask;
@@ -240,21 +262,21 @@ __device__ __forceinline__ void stream_range_check(WS& ws, const LimbConsts& k, 
 }
 
 // RangeChip::check_big_less_than_safe(x, B)
-template <class WS>
+template <bool FAST = false, class WS>
 __device__ __forceinline__ void stream_cbls(WS& ws, const LimbConsts& k, const Fr& x_int,
                                             const Fr& x_mont, int n, const Fr& i_pow, const Fr& i_bound,
                                             const Fr& m_pow, const Fr& m_bound) {
-    stream_range_check(ws, k, x_int, n);
+    stream_range_check<FAST>(ws, k, x_int, n);
     const Fr chk_int = fr::sub_fast(fr::add_fast(x_int, i_pow), i_bound);  // x + 2^bits - B (mod r)
     const Fr m_xp = fr::add_fast(x_mont, m_pow);
     ws.put(fr::sub_fast(m_xp, m_bound));
     ws.put(m_xp);
-    stream_range_check(ws, k, chk_int, n);
+    stream_range_check<FAST>(ws, k, chk_int, n);
 }
 
 // One element of rescale_matrix: the W witnesses of signed_div_scale(c) go to `ws` in assignment order, the quotient
 // (Montgomery form) is returned.  Warp-uniform control flow (every lane streams the same number of witnesses).
-template <class WS>
+template <bool FAST = false, class WS>
 __device__ __forceinline__ Fr rescale_element(WS& ws, const RescaleConsts& k, const Fr& am) {
     const Fr a = fr::mont_reduce_fast(am);                  // canonical integer (reduction only: 80 instead of 132 IMAD.WIDE)
     const Fr ash = fr::add_fast(a, k.i_2S);                 // gate.add(a, Constant(2^S))
@@ -265,8 +287,8 @@ __device__ __forceinline__ Fr rescale_element(WS& ws, const RescaleConsts& k, co
     ws.put(fr::add_fast(am, k.m_2S));
     ws.put(m_rem);
     ws.put(m_div);
-    stream_cbls(ws, k.lc, div, m_div, k.p.n_d, k.i_pow_d, k.i_bound_d, k.m_pow_d, k.m_bound_d);
-    stream_cbls(ws, k.lc, rem, m_rem, k.p.n_r, k.i_pow_r, k.i_bound_r, k.m_pow_r, k.m_bound_r);
+    stream_cbls<FAST>(ws, k.lc, div, m_div, k.p.n_d, k.i_pow_d, k.i_bound_d, k.m_pow_d, k.m_bound_d);
+    stream_cbls<FAST>(ws, k.lc, rem, m_rem, k.p.n_r, k.i_pow_r, k.i_bound_r, k.m_pow_r, k.m_bound_r);
     const Fr q = fr::sub_fast(m_div, k.m_2SP);              // gate.sub(div, Constant(2^(S-P)))
     ws.put(q);
     ws.flush();

@@ -32,6 +32,15 @@ void hs_from_mont_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n;
 void hs_mont_mul_fast_x2(const Fr* a, const Fr* b, Fr* o, size_t n) {   // pairs (2i, 2i+1)
     for (size_t i = 0; i + 1 < n; i += 2) fr::mont_mul_fast_x2(a[i], b[i], a[i + 1], b[i + 1], o[i], o[i + 1]);
 }
+// running sums of n small multiples l[j] * rho[j] (fr::SmallSum): out[i] = sum_{j<=i} l[j] * rho[j] mod r
+void hs_small_sums(const uint32_t* l, const Fr* rho, const uint64_t* phi, Fr* out, size_t n) {
+    fr::SmallSum s;
+    fr::small_sum_init(s);
+    for (size_t i = 0; i < n; i++) {
+        fr::small_sum_add(s, l[i], rho[i], (uint32_t)phi[i], (uint32_t)(phi[i] >> 32));
+        out[i] = fr::small_sum_value(s);
+    }
+}
 void hs_mont_reduce_fast(const Fr* a, Fr* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fr::mont_reduce_fast(a[i]); }
 // Small-operand tensor-core engine, arithmetic only (tc_small.cuh): balanced digits of every operand, the 17 signed
 // diagonal sums a tile of s8 x s8 MMAs would leave in TMEM, signed carry, one Montgomery encode.  Returns 0 when an

@@ -92,6 +92,53 @@ def test_carry_chain_primitives_match_bigint(shim):
     assert unraw(o) == [l * x * inv32 % R for l, x in zip(ls, cs)]
 
 
+def _small_sums(shim, ls, rhos):
+    n = len(ls)
+    larr = np.array(ls, dtype=np.uint32)
+    rho = raw_limbs(rhos)
+    phi = np.array([(x << 64) // R for x in rhos], dtype=np.uint64)
+    o = np.zeros_like(rho)
+    shim.hs_small_sums(P(larr), P(rho), P(phi), P(o), n)
+    return unraw(o)
+
+
+@pytest.mark.parametrize("lb", [1, 8, 12, 19, 27])
+def test_small_sum_running_sums_are_canonical_partial_sums(shim, lb):
+    """fr::SmallSum (the range-check running sums of the rescale / range-check kernels): every partial sum of
+    l_j * M(2^(lb*j)) equals the exact residue, for random limbs, all-ones limbs (the largest sums) and zeros."""
+    rng = random.Random(lb)
+    npos = min(32, 253 // lb, (1 << 32) >> lb)
+    rhos = [(1 << (lb * i)) * (1 << 256) % R for i in range(npos)]
+    cases = [[rng.randrange(1 << lb) for _ in range(npos)] for _ in range(200)]
+    cases += [[(1 << lb) - 1] * npos, [0] * npos, [1] * npos]
+    for ls in cases:
+        want, acc = [], 0
+        for l, rho in zip(ls, rhos):
+            acc = (acc + l * rho) % R
+            want.append(acc)
+        assert _small_sums(shim, ls, rhos) == want
+
+
+def test_small_sum_quotient_estimate_edge(shim):
+    """The 64-bit fixed-point quotient estimate can be one short only when the fraction of F is within 2^-32 of 1; the code
+    takes the exact compare-and-subtract whenever the top 20 fraction bits are ones.  Search limb pairs (l0, l1) that
+    land there (about 2^-20 of all pairs) and check them, plus their neighbours, against exact arithmetic."""
+    lb = 19
+    rhos = [(1 << (lb * i)) * (1 << 256) % R for i in range(2)]
+    phi = [(x << 64) // R for x in rhos]
+    l0 = np.arange(1 << lb, dtype=np.uint64)
+    hits = []
+    for l1 in range(1, 97):
+        f = l0 * np.uint64(phi[0]) + np.uint64((l1 * phi[1]) % (1 << 64))     # mod 2^64: the fraction of F
+        for a in np.nonzero((f >> np.uint64(44)) == np.uint64(0xFFFFF))[0]:
+            hits.append((int(a), l1))
+    assert len(hits) >= 10
+    for a, l1 in hits:
+        for ls in ([a, l1], [max(a - 1, 0), l1], [min(a + 1, (1 << lb) - 1), l1]):
+            want = [ls[0] * rhos[0] % R, (ls[0] * rhos[0] + ls[1] * rhos[1]) % R]
+            assert _small_sums(shim, ls, rhos) == want
+
+
 def test_shift_and_mask_helpers(shim):
     vals = _vals()
     n = len(vals)

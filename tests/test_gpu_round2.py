@@ -389,17 +389,22 @@ def test_rescale_store_paths_write_the_same_bytes(handle, P, lb, S, A):
     W = handle.rescale_witness_count(P, lb, S, A)
     tcs = torch.from_numpy(cs.view(np.int64)).to(dev)
     outs = []
-    for store in (0, 1, 2):
+    # the three store paths; the default one also with the witness array starting 1 and 4 witnesses past a 256-byte
+    # boundary, and with the running sums computed both ways (fr::SmallSum / Montgomery step + modular add)
+    for store, off, fast in ((0, 0, 1), (1, 0, 1), (2, 0, 1), (0, 0, 0), (0, 1, 1), (0, 4, 0)):
         q = torch.full((count, 4), -1, dtype=torch.int64, device=dev)
-        wit = torch.full((count + 3, W, 4), -1, dtype=torch.int64, device=dev)     # 3 guard stripes after the end
+        flat = torch.full(((count + 3) * W + 8, 4), -1, dtype=torch.int64, device=dev)   # 3 guard stripes after the end
+        wit = flat[off:off + (count + 3) * W].view(count + 3, W, 4)
         torch.cuda.synchronize()
         try:
             handle.tune("rescale_store", store)
+            handle.tune("rescale_fast_sums", fast)
             handle.rescale_witness_dev(tcs, count, P, lb, q, wit, S, A)
             handle.sync()
         finally:
             handle.tune("rescale_store", 0)
-        assert bool((wit[count:] == -1).all().item()), "wrote past the end of the witness array"
+            handle.tune("rescale_fast_sums", 1)
+        assert bool((wit[count:] == -1).all().item()) and bool((flat[:off] == -1).all().item()), "wrote outside the witness array"
         outs.append((q.cpu().numpy().view(np.uint64), wit[:count].cpu().numpy().view(np.uint64)))
     eq, _, ewit = corac.rescale_witness(cs, P, lb, S, A, threads=0)
     for q, wit in outs:

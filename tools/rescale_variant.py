@@ -16,6 +16,11 @@ a, b, c = fr(n, n), fr(n, n), fr(n, n)
 h.quantize_dev(x, 63, a); h.quantize_dev(y, 63, b); h.fr_matmul_dev(a, b, c); h.sync()
 W = h.rescale_witness_count(63, 19)
 q, wit = fr(n, n), fr(n * n, W)
+if os.environ.get("RESCALE_CH"):
+    h.tune("rescale_ch", int(os.environ["RESCALE_CH"]))
+for kv in filter(None, os.environ.get("TUNE", "").split(",")):
+    key, val = kv.split("=")
+    h.tune(key, int(val))
 ts = []
 for i in range(9):
     flush.fill_(1)
@@ -23,4 +28,4 @@ for i in range(9):
     e0.record(stream); h.rescale_witness_dev(c, n * n, 63, 19, q, wit); e1.record(stream); e1.synchronize()
     if i >= 2: ts.append(e0.elapsed_time(e1) * 1e3)
 chk = int(wit.sum().item()) ^ int(q.sum().item())
-print(f"{os.environ.get('H2SVD_LIB', 'default')}: rescale median {np.median(ts):.1f} us min {min(ts):.1f} us checksum {chk & 0xffffffffffff:x}")
+print(f"{os.environ.get('H2SVD_LIB', 'default')} rescale_ch={os.environ.get('RESCALE_CH', 'default')} {os.environ.get('TUNE', '')}: rescale median {np.median(ts):.1f} us min {min(ts):.1f} us checksum {chk & 0xffffffffffff:x}")

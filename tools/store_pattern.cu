@@ -1,0 +1,251 @@
+// Developer micro-benchmark (not part of the library): what the memory system delivers to the WRITE PATTERN of the
+// witness stream -- 32 lanes of a warp each own a stripe of W x 32 bytes (consecutive stripes are consecutive in memory)
+// and fill it CH witnesses (CH x 32 bytes) at a time -- for several store mechanisms, burst sizes and residencies, with
+// no arithmetic at all.  Measured on B200 (W = 60, 1 M elements = 2.0 GB per launch; profiles/r02_store_pattern.txt):
+//   * 32 stripes x 256-byte pieces per burst (the rescale kernel's pattern):       5.3 TB/s at 4 to 12 warps per SM
+//   * the same with W = 56 or 64 (every piece 256-byte ALIGNED):                   5.9-6.1 TB/s
+//   * W = 60 with every lane's pieces cut at the 256-byte boundaries of memory:    5.9 TB/s (mode 5)
+//   * a warp's burst as one contiguous piece (not the required layout, mode 3):    6.2-6.3 TB/s = the write peak
+//   * direct 16-byte stores from registers into the 32 stripes (mode 1):           1.5-2.2 TB/s
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o variants/store_pattern tools/store_pattern.cu
+//   mode 0: per-row bulk copies from shared memory (cp.async.bulk), double-buffered   (the rescale kernel's path)
+//   mode 1: direct 16-byte stores from registers, each lane into its own stripe (no staging)
+//   mode 2: staged, then coalesced 16-byte stores (half a warp per 256-byte piece)
+//   mode 3: like mode 0 but every burst of a warp is ONE contiguous piece of memory (not the required layout: shows what
+//           the scatter over 32 stripes costs)
+//   mode 4: like mode 0, single-buffered
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x)                                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = (x);                                                                  \
+        if (e_ != cudaSuccess) {                                                               \
+            fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_));         \
+            exit(1);                                                                           \
+        }                                                                                      \
+    } while (0)
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+    return is_leader != 0;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) store_kernel(uint4* __restrict__ out, size_t elements, int W, int CH, int nbuf) {
+    extern __shared__ __align__(16) uint4 stage[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row_u4 = 2 * CH + 1;
+    const uint32_t buf_stride = blockDim.x * row_u4;
+    uint4* row0 = stage + (size_t)threadIdx.x * row_u4;
+    uint4* warp_row0 = stage + (size_t)(threadIdx.x - lane) * row_u4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int buf = 0;
+    for (size_t e0 = (size_t)blockIdx.x * blockDim.x + warp * 32; e0 < elements; e0 += stride) {  // elements is a multiple of 32
+        uint4* gwarp = out + e0 * (size_t)W * 2;   // lane 0's stripe, in 16-byte units
+        for (int w0 = 0; w0 < W; w0 += CH) {
+            const int fill = W - w0 < CH ? W - w0 : CH;
+            const uint4 v = make_uint4((uint32_t)e0 + lane, (uint32_t)w0, 0x9e3779b9u, (uint32_t)lane);
+            if (MODE == 1) {
+                uint4* d = gwarp + (size_t)lane * W * 2 + (size_t)w0 * 2;
+                for (int i = 0; i < 2 * fill; i++) __stcs(d + i, v);
+                continue;
+            }
+            uint4* s = row0 + buf * buf_stride;
+            for (int i = 0; i < 2 * fill; i++) s[i] = v;
+            if (MODE == 2) {
+                __syncwarp();
+                const int chunk = lane & 15, half = lane >> 4;
+                if (chunk < 2 * fill)
+                    for (int r = half; r < 32; r += 2)
+                        __stcs(gwarp + (size_t)r * W * 2 + (size_t)w0 * 2 + chunk, warp_row0[r * row_u4 + chunk]);
+                __syncwarp();
+                continue;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (elect_one()) {
+                const uint32_t bytes = (uint32_t)fill * 32u;
+                uint32_t src = smem_addr(warp_row0 + buf * buf_stride);
+                uint4* dst = MODE == 3 ? gwarp + (size_t)w0 * 2 * 32 : gwarp + (size_t)w0 * 2;
+                const size_t dstep = MODE == 3 ? (size_t)fill * 2 : (size_t)W * 2;
+                for (int r = 0; r < 32; r++) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                                 : "memory");
+                    src += row_u4 * 16;
+                    dst += dstep;
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (nbuf == 2)
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+            if (nbuf == 2) buf ^= 1;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// mode 5: the required layout, 8-witness bursts, but every lane's chunk boundaries sit on 256-BYTE-ALIGNED addresses of
+// its stripe (stripes of W x 32 bytes start 0, 32, .. 224 bytes past such a boundary).  Per lane a ring of two 8-witness
+// buffers; witness w of an element goes to ring position (8 * F0 + a + w) & 15 (a = the stripe's misalignment in
+// witnesses, F0 = the warp's flush counter at the start of the element), so that aligned chunks coincide with buffers and
+// flush number F always ships buffer F & 1.  A flush happens every 8 witnesses and at the end of the element; each lane
+// publishes what it ships (destination, source, bytes) in a 16-byte descriptor and one elected lane issues the copies.
+__global__ void __launch_bounds__(128) store_aligned_kernel(uint4* __restrict__ out, size_t elements, int W) {
+    extern __shared__ __align__(16) uint4 stage[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int ROW_U4 = 33;
+    uint4* row = stage + (size_t)threadIdx.x * ROW_U4;
+    const uint32_t row_s = smem_addr(row);
+    uint4* desc = stage + (size_t)blockDim.x * ROW_U4 + warp * 32;     // this warp's descriptor table
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint32_t F = 0;            // flushes so far (warp-uniform)
+    int wait_at = 8;           // puts after a flush before which the previous flush's reads must be complete
+    for (size_t e0 = (size_t)blockIdx.x * blockDim.x + warp * 32; e0 < elements; e0 += stride) {
+        uint4* mine = out + (e0 + lane) * (size_t)W * 2;
+        const uint32_t a = (uint32_t)((reinterpret_cast<uintptr_t>(mine) >> 5) & 7u);
+        uint32_t amax = a;
+        for (int o = 16; o; o >>= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const uint32_t F0 = F;
+        int fill = 0;
+        uint32_t j = 0;   // chunks of this element shipped so far
+        auto ship = [&](uint32_t chunk, uint32_t count) {   // chunk index within the element; `count` witnesses exist
+            const uint32_t lo = max(8u * chunk, a), hi = min(min(8u * chunk + 8u, (uint32_t)W + a), count + a);
+            const uint32_t bytes = hi > lo ? (hi - lo) * 32u : 0u;
+            uint4* dst = mine + (size_t)(lo - a) * 2;
+            const uint32_t src = row_s + (((8u * F0 + lo) & 15u) * 32u);
+            desc[lane] = make_uint4((uint32_t)reinterpret_cast<uintptr_t>(dst), (uint32_t)(reinterpret_cast<uintptr_t>(dst) >> 32), src, bytes);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (elect_one()) {
+                for (int r = 0; r < 32; r++) {
+                    const uint4 d = desc[r];
+                    if (d.w != 0u) {
+                        const unsigned long long g = ((unsigned long long)d.y << 32) | d.x;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(d.z), "r"(d.w) : "memory");
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (amax == 0u) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
+            __syncwarp();
+            F++;
+        };
+        wait_at = amax == 0u ? 8 : 8 - (int)amax;
+        for (int w = 0; w < W; w++) {
+            const uint4 v = make_uint4((uint32_t)(e0 + lane), (uint32_t)w, 0x9e3779b9u, (uint32_t)lane);
+            if (fill == wait_at && amax != 0u) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+            uint4* s = row + 2 * ((8u * F0 + a + (uint32_t)w) & 15u);
+            s[0] = v;
+            s[1] = v;
+            if (++fill == 8) {
+                ship(j++, (uint32_t)w + 1u);
+                fill = 0;
+            }
+        }
+        // end of the element: the remaining chunks (one, or two when the last witnesses straddle a boundary for some lane).
+        // If the last flush period was too short to reach its wait point, the flush before it has not been waited for yet.
+        const uint32_t nchunks = ((uint32_t)W + amax + 7u) / 8u;
+        const bool two = nchunks - j >= 2u;
+        if (amax != 0u && fill <= wait_at) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+        while (j < nchunks) ship(j++, (uint32_t)W);
+        if (two) {   // both buffers in flight: the next element's first witnesses would overwrite the older one
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+int main(int argc, char** argv) {
+    const int W = argc > 1 ? atoi(argv[1]) : 60;
+    const size_t elements = 1024 * 1024;
+    const size_t bytes = elements * W * 32;
+    uint4* out;
+    CK(cudaMalloc(&out, bytes));
+    uint8_t* flush;
+    CK(cudaMalloc(&flush, 256u << 20));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    struct Cfg { int mode, ch, nbuf, threads, ctas; };
+    std::vector<Cfg> cfgs;
+    for (int mode : {0, 3})
+        for (int ch : {8})
+            for (int warps : {8, 12}) {
+                // split the warps into CTAs of at most 4 warps
+                const int threads = warps >= 4 ? (warps % 4 == 0 ? 128 : 64) : 32 * warps;
+                cfgs.push_back({mode, ch, 2, threads, warps * 32 / threads});
+            }
+    for (int ctas : {1, 2, 3}) {
+        const size_t smem = 128 * 33 * 16 + 4 * 32 * 16;
+        CK(cudaFuncSetAttribute(store_aligned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaMemsetAsync(flush, rep, 256u << 20));
+            CK(cudaEventRecord(e0));
+            store_aligned_kernel<<<sms * ctas, 128, smem>>>(out, elements, W);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        printf("W %d mode 5 (aligned chunks) CH  8 ring 16 128 thr x %d ctas/SM: %7.1f us  %6.0f GB/s\n", W, ctas, best * 1e3,
+               bytes / (best * 1e-3) / 1e9);
+        // verify the pattern landed where it should (lane/witness ids)
+        if (ctas == 3) {
+            std::vector<uint4> h(elements * W * 2);
+            CK(cudaMemcpy(h.data(), out, bytes, cudaMemcpyDeviceToHost));
+            size_t bad = 0;
+            for (size_t e = 0; e < elements; e++)
+                for (int w = 0; w < W; w++)
+                    for (int q = 0; q < 2; q++) {
+                        const uint4 v = h[(e * W + w) * 2 + q];
+                        if (v.x != (uint32_t)e || v.y != (uint32_t)w || v.w != (uint32_t)(e & 31)) bad++;
+                    }
+            printf("W %d mode 5 check: %zu bad of %zu\n", W, bad, elements * W * 2);
+        }
+        fflush(stdout);
+    }
+    for (const Cfg& c : cfgs) {
+        const int nbuf = c.nbuf;
+        const size_t smem = (size_t)c.threads * nbuf * (2 * c.ch + 1) * 16;
+        if ((smem + 1024) * c.ctas > 227 * 1024) continue;
+        void (*kern)(uint4*, size_t, int, int, int) = c.mode == 0 ? store_kernel<0> : store_kernel<3>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaMemsetAsync(flush, rep, 256u << 20));
+            CK(cudaEventRecord(e0));
+            kern<<<sms * c.ctas, c.threads, smem>>>(out, elements, W, c.ch, nbuf);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        printf("W %d mode %d CH %2d nbuf %d %3d thr x %2d ctas/SM (%2d warps, %3zu KB staging): %7.1f us  %6.0f GB/s\n", W, c.mode, c.ch, nbuf,
+               c.threads, c.ctas, c.ctas * c.threads / 32, smem * c.ctas / 1024, best * 1e3, bytes / (best * 1e-3) / 1e9);
+        fflush(stdout);
+    }
+    return 0;
+}
