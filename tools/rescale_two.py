@@ -1,4 +1,4 @@
-"""One launch of the N = 1024 rescale per store path (3: bursts cut at stripe offsets, 0: 256-byte-aligned bursts): the
+"""One launch of the N = 1024 rescale per running-sum variant (Montgomery step + modular add, then fr::SmallSum): the
 target of an ncu capture (-k regex:rescale_)."""
 import importlib, os, sys
 import torch
@@ -16,9 +16,9 @@ a, b, c = fr(n, n), fr(n, n), fr(n, n)
 h.quantize_dev(x, 63, a); h.quantize_dev(y, 63, b); h.fr_matmul_dev(a, b, c); h.sync()
 W = h.rescale_witness_count(63, 19)
 q, wit = fr(n, n), fr(n * n, W)
-for store in (3, 0):
-    h.tune("rescale_store", store)
+for fast in (0, 1):
+    h.tune("rescale_fast_sums", fast)
     h.rescale_witness_dev(c, n * n, 63, 19, q, wit)
     h.sync()
-h.tune("rescale_store", 0)
+h.tune("rescale_fast_sums", 1)
 h.close()

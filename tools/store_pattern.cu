@@ -186,13 +186,10 @@ int main(int argc, char** argv) {
     CK(cudaEventCreate(&e1));
     struct Cfg { int mode, ch, nbuf, threads, ctas; };
     std::vector<Cfg> cfgs;
-    for (int mode : {0, 3})
-        for (int ch : {8})
-            for (int warps : {8, 12}) {
-                // split the warps into CTAs of at most 4 warps
-                const int threads = warps >= 4 ? (warps % 4 == 0 ? 128 : 64) : 32 * warps;
-                cfgs.push_back({mode, ch, 2, threads, warps * 32 / threads});
-            }
+    for (int ch : {4, 8, 12, 16, 20})
+        for (int warps : {4, 8, 12}) cfgs.push_back({0, ch, 2, 128, warps / 4});
+    for (int warps : {8, 12}) cfgs.push_back({3, 8, 2, 128, warps / 4});
+    for (int warps : {8, 16, 32}) cfgs.push_back({1, 8, 1, 128, warps / 4});
     for (int ctas : {1, 2, 3}) {
         const size_t smem = 128 * 33 * 16 + 4 * 32 * 16;
         CK(cudaFuncSetAttribute(store_aligned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -227,9 +224,9 @@ int main(int argc, char** argv) {
     }
     for (const Cfg& c : cfgs) {
         const int nbuf = c.nbuf;
-        const size_t smem = (size_t)c.threads * nbuf * (2 * c.ch + 1) * 16;
+        const size_t smem = c.mode == 1 ? 0 : (size_t)c.threads * nbuf * (2 * c.ch + 1) * 16;
         if ((smem + 1024) * c.ctas > 227 * 1024) continue;
-        void (*kern)(uint4*, size_t, int, int, int) = c.mode == 0 ? store_kernel<0> : store_kernel<3>;
+        void (*kern)(uint4*, size_t, int, int, int) = c.mode == 0 ? store_kernel<0> : c.mode == 1 ? store_kernel<1> : store_kernel<3>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
