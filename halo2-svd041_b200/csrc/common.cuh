@@ -43,7 +43,7 @@ struct h2svd_ctx {
         int fuse_rescale = 0;     // 1: rescale witnesses from the tensor-core epilogue (experimental)
         int rescale_generic = 0;  // 1: force the generic (unstaged) rescale kernel
         int rescale_store = 0;    // witness stream of the rescale kernel: 0 per-row bulk copies, 1 TMA tensor stores, 2 coalesced STG
-        int rescale_fast_sums = 1;   // range-check running sums through fr::SmallSum when the configuration allows (0: Montgomery step + add)
+        int rescale_fast_sums = 0;   // 1: range-check running sums through fr::SmallSum (14 % fewer instructions, measured 1 % SLOWER: the kernel is store-bound)
         int rescale_ch = 8;       // witnesses per bulk store of the staged rescale kernel: 4, 6 or 8
         int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel
         int matvec_x2 = 1;        // mat-vec prefix kernels: 1 = two Montgomery products at a time with interleaved carry chains

@@ -227,9 +227,17 @@ def test_gamma_powers_edge_cases(handle):
 
 
 # ---------------------------------------------------------------- K4: rescale
+@pytest.fixture(params=[0, 1], ids=["sums=step+add", "sums=SmallSum"])
+def running_sums(handle, request):
+    """Both formulations of the range-check running sums (tuning switch rescale_fast_sums, fr::SmallSum when 1)."""
+    handle.tune("rescale_fast_sums", request.param)
+    yield request.param
+    handle.tune("rescale_fast_sums", 0)
+
+
 @pytest.mark.parametrize("P,lb,S,A", [(32, 19, -1, -1), (42, 19, -1, -1), (63, 19, -1, -1), (32, 12, -1, -1),
                                       (63, 8, -1, -1), (32, 20, -1, -1), (63, 19, 189, 190), (32, 19, 100, 110)])
-def test_rescale_witness_matches_oracle(handle, P, lb, S, A):
+def test_rescale_witness_matches_oracle(handle, running_sums, P, lb, S, A):
     rng = np.random.default_rng(P * 1000 + lb)
     pyr = __import__("random").Random(P + lb)
     Sv = 3 * P if S < 0 else S
@@ -444,7 +452,7 @@ def test_zkmatrix_mul_witness_fused_matches_oracle(handle, pkg, rows, k, m, P, b
 
 # ---------------------------------------------------------------- SVD-verifier range-check witnesses
 @pytest.mark.parametrize("bnd,lb", [((1 << 42) + 1, 19), (12345678901234567890123, 19), (5, 19), ((1 << 63) + 1, 12), (1 << 100, 8)])
-def test_abs_less_than_witness_matches_oracle(handle, bnd, lb):
+def test_abs_less_than_witness_matches_oracle(handle, running_sums, bnd, lb):
     rng = np.random.default_rng(lb)
     import random as _r
     r = _r.Random(bnd % 997)
@@ -461,7 +469,7 @@ def test_abs_less_than_witness_matches_oracle(handle, bnd, lb):
 
 
 @pytest.mark.parametrize("bits,lb", [(72, 19), (93, 19), (19, 19), (20, 19), (57, 19), (5, 19), (38, 19), (64, 8), (33, 32)])
-def test_range_check_witness_matches_oracle(handle, bits, lb):
+def test_range_check_witness_matches_oracle(handle, running_sums, bits, lb):
     import random as _r
     r = _r.Random(bits)
     x = po.pack_mont([r.randrange(1 << bits) for _ in range(1500)] + [0, (1 << bits) - 1])

@@ -403,7 +403,7 @@ def test_rescale_store_paths_write_the_same_bytes(handle, P, lb, S, A):
             handle.sync()
         finally:
             handle.tune("rescale_store", 0)
-            handle.tune("rescale_fast_sums", 1)
+            handle.tune("rescale_fast_sums", 0)
         assert bool((wit[count:] == -1).all().item()) and bool((flat[:off] == -1).all().item()), "wrote outside the witness array"
         outs.append((q.cpu().numpy().view(np.uint64), wit[:count].cpu().numpy().view(np.uint64)))
     eq, _, ewit = corac.rescale_witness(cs, P, lb, S, A, threads=0)

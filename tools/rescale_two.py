@@ -20,5 +20,5 @@ for fast in (0, 1):
     h.tune("rescale_fast_sums", fast)
     h.rescale_witness_dev(c, n * n, 63, 19, q, wit)
     h.sync()
-h.tune("rescale_fast_sums", 1)
+h.tune("rescale_fast_sums", 0)
 h.close()
