@@ -249,6 +249,9 @@ def run_gpu(args) -> None:
     W = h.rescale_witness_count(P_BITS, LOOKUP_BITS)
     if args.matmul_small is not None:
         h.tune("matmul_small", args.matmul_small)
+    for kv in args.tune or []:
+        key, val = kv.split("=")
+        h.tune(key, int(val))
 
     def fr(*shape):
         return torch.zeros(shape + (4,), dtype=torch.int64, device=device)
@@ -709,6 +712,7 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (large rectangular jobs: pinned host memory)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--matmul-small", type=int, default=None, help="tuning: 0 = never use the small-operand mat-mul engine")
+    ap.add_argument("--tune", action="append", default=None, metavar="KEY=VAL", help="triage: per-handle tuning switch (repeatable)")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure (0 = skip)")
     ap.add_argument("--multi-handle", action="store_true",
                     help="one process drives --gpus N devices through h2svd_multi (end-to-end only; no torchrun)")

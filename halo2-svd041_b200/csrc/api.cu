@@ -605,6 +605,28 @@ static int mul_witness_dev(h2svd_ctx* ctx, const Fr* da, const Fr* db, const Fr*
     Fr* dabv = cv.take<Fr>(rows);
     cudaStream_t main = ctx->stream, side = ctx->side_stream;
     cudaEvent_t ev_fork = ctx->ev[4], ev_mid = ctx->ev[5], ev_join = ctx->ev[6];
+    if (ctx->tune.step_schedule == 1) {
+        // Experiment: the whole of verify_mul runs AFTER the mat-mul, on the side stream, through the low-register
+        // mat-vec kernel whose CTAs fit next to the resident rescale CTAs (store-bound: half their issue slots idle).
+        H2SVD_TRY(launch_fr_matmul(ctx, da, db, dc, rows, k, m));                                 // :546
+        H2SVD_CUDA(cudaEventRecord(ev_mid, main));
+        H2SVD_TRY(launch_rescale(ctx, dc, rows * m, P, lb, S, A, dq, dw));                        // :354 (first: takes its SM slots)
+        H2SVD_CUDA(cudaStreamWaitEvent(side, ev_mid, 0));
+        {
+            StreamScope sc(ctx, side);
+            const int saved = ctx->tune.matvec_coreside;
+            ctx->tune.matvec_coreside = 1;
+            int rc = bv_part(ctx, db, dg, k, m, bv0, bv1, dpow, dpbv, dbv);
+            if (rc == H2SVD_OK) rc = launch_mat_vec_prefix(ctx, da, dbv, rows, k, 0, dpabv, dabv);     // :337
+            if (rc == H2SVD_OK) rc = launch_mat_vec_prefix(ctx, dc, dpow, rows, m, 0, dpcv, dcsv);     // :335
+            ctx->tune.matvec_coreside = saved;
+            H2SVD_TRY(rc);
+            H2SVD_TRY(launch_is_equal(ctx, dcsv, dabv, rows, ddiff, dz, dinv));                   // :339-341
+            H2SVD_CUDA(cudaEventRecord(ev_join, side));
+        }
+        H2SVD_CUDA(cudaStreamWaitEvent(main, ev_join, 0));
+        return H2SVD_OK;
+    }
     // fork: the C-independent half of verify_mul (integer-pipe mat-vecs) runs under the mat-mul (tensor pipe)
     H2SVD_CUDA(cudaEventRecord(ev_fork, main));
     H2SVD_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
@@ -1076,6 +1098,7 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
         {"matvec_seg", &ctx->tune.matvec_seg},       {"matvec_x2", &ctx->tune.matvec_x2},
         {"matvec_segs", &ctx->tune.matvec_segs},       {"rescale_ch", &ctx->tune.rescale_ch},
         {"rescale_store", &ctx->tune.rescale_store}, {"rescale_fast_sums", &ctx->tune.rescale_fast_sums},
+        {"matvec_coreside", &ctx->tune.matvec_coreside}, {"step_schedule", &ctx->tune.step_schedule},
     };
     for (const auto& e : keys)
         if (strcmp(e.name, key) == 0) {

@@ -76,8 +76,7 @@ struct MvJobs {
 // chunks; it keeps its four un-offset running sums in registers, the warps exchange their segment
 // totals through shared memory, and every running sum is written exactly once.
 template <int WPR>
-__global__ void __launch_bounds__(MV_WARPS * 32, 2)
-mat_vec_prefix_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len, size_t v_row_stride) {
+__device__ __forceinline__ void mat_vec_prefix_body(const MvJobs& jobs, const Fr* __restrict__ v, size_t len, size_t v_row_stride) {
     constexpr int RPC = MV_WARPS / WPR;       // rows per CTA pass
     constexpr int TILE = WPR * 32 * MV_C;
     __shared__ Fr wtot[MV_WARPS];
@@ -151,6 +150,19 @@ mat_vec_prefix_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict_
         }
         if (totals && wr == 0 && lane == 0) st_fr(totals, carry);
     }
+}
+template <int WPR>
+__global__ void __launch_bounds__(MV_WARPS * 32, 2)
+mat_vec_prefix_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len, size_t v_row_stride) {
+    mat_vec_prefix_body<WPR>(jobs, v, len, v_row_stride);
+}
+// The same kernel capped at 96 registers and ~1 KB of shared memory: one CTA of it fits on an SM NEXT TO the three resident
+// CTAs of the rescale kernel (104 registers x 384 threads, 209 KB of staging), whose store-bound warps leave half the issue
+// slots idle (experiment behind the tuning switch "step_schedule").
+template <int WPR>
+__global__ void __maxnreg__(96)
+mat_vec_prefix_lowreg_kernel(const __grid_constant__ MvJobs jobs, const Fr* __restrict__ v, size_t len, size_t v_row_stride) {
+    mat_vec_prefix_body<WPR>(jobs, v, len, v_row_stride);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -461,7 +473,10 @@ static int launch_mv(h2svd_ctx* ctx, const MvJobs& jobs, size_t total_rows, cons
     size_t blocks = (total_rows + RPC - 1) / RPC;
     const size_t cap = (size_t)ctx->sm_count * 2 * 4;  // 2 resident CTAs per SM, grid-stride beyond 4 waves
     if (blocks > cap) blocks = cap;
-    mat_vec_prefix_kernel<WPR><<<(unsigned)blocks, MV_WARPS * 32, 0, ctx->stream>>>(jobs, v, len, vs);
+    if (ctx->tune.matvec_coreside)
+        mat_vec_prefix_lowreg_kernel<WPR><<<(unsigned)blocks, MV_WARPS * 32, 0, ctx->stream>>>(jobs, v, len, vs);
+    else
+        mat_vec_prefix_kernel<WPR><<<(unsigned)blocks, MV_WARPS * 32, 0, ctx->stream>>>(jobs, v, len, vs);
     H2SVD_LAUNCH_CHECK(ctx);
     return H2SVD_OK;
 }
@@ -489,13 +504,13 @@ static int launch_mv_jobs(h2svd_ctx* ctx, const MvJobs& jobs, const Fr* v, size_
     if (total_rows == 0 || len == 0) return H2SVD_OK;
     // few long rows: several warps per row (mat_vec_prefix_seg_kernel); "matvec_seg": -1 auto, 0 never, 1 whenever len >= 256
     const bool few_rows = total_rows < (size_t)ctx->sm_count * 16;
-    if (len >= 256 && ctx->tune.matvec_warp == 0 && (ctx->tune.matvec_seg > 0 || (ctx->tune.matvec_seg < 0 && few_rows))) {
+    if (len >= 256 && ctx->tune.matvec_warp == 0 && !ctx->tune.matvec_coreside && (ctx->tune.matvec_seg > 0 || (ctx->tune.matvec_seg < 0 && few_rows))) {
         const int segs = ctx->tune.matvec_segs > 0 ? ctx->tune.matvec_segs : (len >= 1024 ? 8 : len >= 512 ? 4 : 2);
         if (segs >= 8) return launch_mv_seg<8>(ctx, jobs, total_rows, v, len, vs);
         if (segs >= 4) return launch_mv_seg<4>(ctx, jobs, total_rows, v, len, vs);
         return launch_mv_seg<2>(ctx, jobs, total_rows, v, len, vs);
     }
-    if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && ctx->tune.matvec_warp == 0) {
+    if (len >= 128 && total_rows >= (size_t)ctx->sm_count * 4 && ctx->tune.matvec_warp == 0 && !ctx->tune.matvec_coreside) {
         // one warp per row, consecutive elements per lane (mat_vec_prefix_tile_kernel); needs enough rows to
         // give every SM a few warps, otherwise the row-splitting kernel below is the better fit
         size_t blocks = (total_rows + MT_WARPS - 1) / MT_WARPS;

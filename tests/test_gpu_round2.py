@@ -457,6 +457,38 @@ def test_small_operand_engine_cluster_multicast(handle, cluster, width, shape):
     assert _eq(got, corac.field_mat_mul(a, b, threads=0))
 
 
+@pytest.mark.parametrize("rows,k,m", [(300, 200, 260), (128, 1024, 1024)])
+def test_device_step_alternate_schedule_writes_the_same_bytes(handle, rows, k, m):
+    """tuning switch step_schedule = 1 (all of verify_mul after the mat-mul, through the low-register mat-vec kernel that fits
+    next to the rescale CTAs): every output of the one-call step is byte-identical to the default schedule's."""
+    import torch
+    rng = np.random.default_rng(rows + k)
+    P, lb = 63, 19
+    a, b = quantized_matrix(rng, rows, k, P), quantized_matrix(rng, k, m, P)
+    gamma = random_fr(rng, 1)
+    dev = torch.device("cuda", handle.device)
+    def t(x):
+        return torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).to(dev)
+    W = handle.rescale_witness_count(P, lb)
+    outs = []
+    for sched in (0, 1):
+        def z(*shape):
+            return torch.full(shape + (4,), -1, dtype=torch.int64, device=dev)
+        bufs = dict(c_s=z(rows, m), q=z(rows, m), wit=z(rows * m, W), powers=z(m), prefix_cv=z(rows, m), prefix_bv=z(k, m),
+                    prefix_abv=z(rows, k), diff=z(rows), is_zero=z(rows), inv=z(rows))
+        try:
+            handle.tune("step_schedule", sched)
+            handle.zkmatrix_mul_witness_dev(t(a), t(b), t(gamma), P, lb, **bufs)
+            handle.sync()
+        finally:
+            handle.tune("step_schedule", 0)
+        outs.append({key: val.cpu().numpy() for key, val in bufs.items()})
+    for key in outs[0]:
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+    assert _eq(outs[1]["c_s"].view(np.uint64), corac.field_mat_mul(a, b, threads=0))
+    assert not outs[1]["diff"].any()
+
+
 def test_graph_is_refused_after_a_workspace_reallocation(pkg):
     """A recorded graph holds workspace pointers: once a larger call has made the handle reallocate, replaying the old graph
     is refused (EINVAL) instead of writing through stale pointers."""
