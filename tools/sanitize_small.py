@@ -41,6 +41,32 @@ def main():
             assert (w == ewit).all() and (q.reshape(-1, 4) == eq).all()
         res = h.zkmatrix_mul_witness(a, b, g, 42, 19, bv_rows=(1, k - 1))
         assert (res["c_s"] == c).all()
+    # tensor-core engines on small quantized operands: every tile width of the small-operand engine, with and without
+    # clusters; the full-width engine; both running-sum formulations of the rescale; the one-call step
+    from tests.util import quantized_matrix  # noqa: E402
+    n, k, m = 130, 200, 60
+    a, b = quantized_matrix(rng, n, k, 63), quantized_matrix(rng, k, m, 63)
+    want = corac.field_mat_mul(a, b)
+    h.tune("matmul_tc", 1)
+    for width in (8, 16, 24, 28):
+        for cluster in (0, 2):
+            h.tune("matmul_small_width", width)
+            h.tune("matmul_cluster", cluster)
+            assert (h.fr_matmul(a, b) == want).all(), (width, cluster)
+            assert h.last_matmul_engine() == "tensor-small"
+    h.tune("matmul_small_width", 0)
+    h.tune("matmul_cluster", 0)
+    h.tune("matmul_small", 0)
+    assert (h.fr_matmul(a, b) == want).all() and h.last_matmul_engine() == "tensor"
+    h.tune("matmul_small", -1)
+    h.tune("matmul_tc", -1)
+    for fast in (1, 0):
+        h.tune("rescale_fast_sums", fast)
+        q, w = h.rescale_witness(want, 63, 19)
+        eq, _, ewit = corac.rescale_witness(want.reshape(-1, 4), 63, 19)
+        assert (w == ewit).all() and (q.reshape(-1, 4) == eq).all()
+    res = h.zkmatrix_mul_witness(a, b, rfr(rng, 1), 63, 19)
+    assert (res["c_s"] == want).all() and not res["diff"].any()
     for batch, ln in ((3, 31), (700, 130), (5, 1000), (600, 129)):
         x, s = rfr(rng, batch, ln), rfr(rng, batch, ln)
         assert (h.zkvec_inner_prefix(x, s) == corac.zkvec_inner_prefix(x, s)).all()
