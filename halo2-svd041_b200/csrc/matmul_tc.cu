@@ -348,7 +348,7 @@ tc_split_kernel(const Fr* __restrict__ a, uint32_t* __restrict__ planes_a, int n
 template <class C, bool FUSE, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    Fr* __restrict__ c, int n, int k, int m, int j_begin, int j_end, int tiles_j, int num_tiles, int* err,
+                    Fr* __restrict__ c, int n, int k, int m, int tiles_j, int num_tiles, int* err,
                     const int* __restrict__ mode, int run_if_mode, unsigned long long* __restrict__ tl,
                     const __grid_constant__ rs::RescaleConsts kc, Fr* __restrict__ out_q, Fr* __restrict__ out_wit) {
     using D = TcD<C>;
@@ -430,7 +430,7 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const uint32_t sb = ub % TC_SB;
                     tc_mbar_wait(empty_b + 8 * sb, ((ub / TC_SB) & 1) ^ 1, err);
                     tc_mbar_expect_tx(full_b + 8 * sb, D::B_TX);
-                    tc_tma_3d(s_b + sb * TC_B_BYTES, &tm_b, kb * TC_BKB, j_begin + jb * BJ, 0, full_b + 8 * sb);
+                    tc_tma_3d(s_b + sb * TC_B_BYTES, &tm_b, kb * TC_BKB, jb * BJ, 0, full_b + 8 * sb);
                     ub++;
                     for (int p = 0; p < C::LA; p++) {
                         const uint32_t sa = ua % TC_SA;
@@ -564,8 +564,8 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     if (4 * CW != BJ && q >= cw) break;
                     if constexpr (C::SIGNED) res[q] = fr::signed6_to_mont(T[q]);
                     else res[q] = fr::reduce_wide_acc(T[q]);
-                    const int gj = j_begin + jb * BJ + j0 + q;   // this launch owns columns [j_begin, j_end)
-                    if (gi < n && gj < j_end) {
+                    const int gj = jb * BJ + j0 + q;
+                    if (gi < n && gj < m) {
                         Fr* dst = c + (size_t)gi * m + gj;
                         if (pass > 0) res[q] = fr::add(ld_fr(dst), res[q]);
                         st_fr(dst, res[q]);
@@ -577,8 +577,8 @@ fr_matmul_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const int valid = n - row0 < 32 ? n - row0 : 32;
 #pragma unroll
                     for (int q = 0; q < CW; q++) {
-                        const int gj = j_begin + jb * BJ + j0 + q;
-                        if (gj < j_end && valid > 0) {  // warp-uniform
+                        const int gj = jb * BJ + j0 + q;
+                        if (gj < m && valid > 0) {  // warp-uniform
                             ws.valid = valid;
                             ws.gwarp = out_wit + ((size_t)row0 * m + gj) * (size_t)kc.p.W;
                             const Fr qv = rs::rescale_element(ws, kc, gi < n ? res[q] : fr::zero());
@@ -691,8 +691,7 @@ size_t tc_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 template <class C, int CS = 1>
 int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr* b, Fr* c, size_t n, size_t k, size_t m,
                      size_t ldk, uint8_t* a8, uint8_t* b8, int* mode, int run_if_mode, bool split_only, bool mm_only,
-                     const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit, size_t j_begin = 0, size_t j_end = 0) {
-    if (j_end == 0) j_end = m;   // columns [j_begin, j_end) of C are produced by this launch
+                     const rs::RescaleConsts* fuse, Fr* out_q, Fr* out_wit) {
     using D = TcD<C>;
     const int ldk4 = (int)(ldk / 4);
     if (!mm_only) {
@@ -734,7 +733,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
             return H2SVD_ECUDA;
         }
     }
-    const int tiles_i = (int)((n + TC_BM - 1) / TC_BM), tiles_j = (int)((j_end - j_begin + C::BJ - 1) / C::BJ);
+    const int tiles_i = (int)((n + TC_BM - 1) / TC_BM), tiles_j = (int)((m + C::BJ - 1) / C::BJ);
     const long long tiles = (long long)tiles_i * tiles_j;
     if (tiles >= (1LL << 31)) {
         set_error("fr_matmul (tensor-core engine): too many tiles");
@@ -772,7 +771,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         const long long clusters = groups < max_clusters ? groups : max_clusters;
         cfg.gridDim = dim3((unsigned)(clusters * CS));
         static const rs::RescaleConsts none{};
-        H2SVD_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j,
+        H2SVD_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j,
                                       (int)tiles, ctx->d_flag, (const int*)mode, run_if_mode, ctx->d_timeline, none,
                                       (Fr*)nullptr, (Fr*)nullptr));
         H2SVD_LAUNCH_CHECK(ctx);
@@ -783,7 +782,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         if constexpr (C::BJ == 8) {   // the fused epilogue is instantiated for the 8-column tiles of either engine
             H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, true, 1>), (tc_smem_bytes<C, true>()));
             fr_matmul_tc_kernel<C, true, 1><<<grid, TC_THREADS, tc_smem_bytes<C, true>(), ctx->stream>>>(
-                tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, *fuse, out_q,
+                tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, *fuse, out_q,
                 out_wit);
         } else {
             set_error("fr_matmul (tensor-core engine): fused rescale needs 8-column tiles");
@@ -793,7 +792,7 @@ int tc_launch_engine(h2svd_ctx* ctx, tc_encode_fn encode, const Fr* a, const Fr*
         static const rs::RescaleConsts none{};
         H2SVD_SET_SMEM(ctx, (fr_matmul_tc_kernel<C, false, 1>), (tc_smem_bytes<C, false>()));
         fr_matmul_tc_kernel<C, false, 1><<<grid, TC_THREADS, tc_smem_bytes<C, false>(), ctx->stream>>>(
-            tm_a, tm_b, c, (int)n, (int)k, (int)m, (int)j_begin, (int)j_end, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, none, nullptr,
+            tm_a, tm_b, c, (int)n, (int)k, (int)m, tiles_j, (int)tiles, ctx->d_flag, mode, run_if_mode, ctx->d_timeline, none, nullptr,
             nullptr);
     }
     H2SVD_LAUNCH_CHECK(ctx);
