@@ -1098,7 +1098,7 @@ int h2svd_debug_tune(h2svd_ctx* ctx, const char* key, int value) {
         {"matvec_seg", &ctx->tune.matvec_seg},       {"matvec_x2", &ctx->tune.matvec_x2},
         {"matvec_segs", &ctx->tune.matvec_segs},       {"rescale_ch", &ctx->tune.rescale_ch},
         {"rescale_store", &ctx->tune.rescale_store}, {"rescale_fast_sums", &ctx->tune.rescale_fast_sums},
-        {"matvec_coreside", &ctx->tune.matvec_coreside}, {"step_schedule", &ctx->tune.step_schedule},
+        {"rescale_ctas", &ctx->tune.rescale_ctas}, {"matvec_coreside", &ctx->tune.matvec_coreside}, {"step_schedule", &ctx->tune.step_schedule},
     };
     for (const auto& e : keys)
         if (strcmp(e.name, key) == 0) {

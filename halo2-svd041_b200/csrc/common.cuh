@@ -42,9 +42,10 @@ struct h2svd_ctx {
         int variant = 0;          // schoolbook tile variant
         int fuse_rescale = 0;     // 1: rescale witnesses from the tensor-core epilogue (experimental)
         int rescale_generic = 0;  // 1: force the generic (unstaged) rescale kernel
-        int rescale_store = 0;    // witness stream of the rescale kernel: 0 per-row bulk copies, 1 TMA tensor stores, 2 coalesced STG
+        int rescale_store = 0;    // witness stream of the rescale kernel: 0 auto (1 when the layout allows, else 3), 1 256-byte-aligned TMA tensor stores, 2 coalesced STG, 3 per-row bulk copies
         int matvec_coreside = 0;     // mat-vecs through the low-register, shared-memory-free kernel (fits next to the rescale CTAs)
         int step_schedule = 0;       // zkmatrix_mul_witness_dev: 1 = every Freivalds mat-vec AFTER the mat-mul, co-resident with the rescale kernel
+        int rescale_ctas = 3;        // resident CTAs per SM of the TMA-store rescale kernel (2 or 3)
         int rescale_fast_sums = 0;   // 1: range-check running sums through fr::SmallSum (14 % fewer instructions, measured 1 % SLOWER: the kernel is store-bound)
         int rescale_ch = 8;       // witnesses per bulk store of the staged rescale kernel: 4, 6 or 8
         int matvec_warp = 0;      // 1: force the warp-per-segment mat-vec prefix kernel

@@ -156,33 +156,35 @@ rescale_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, Fr* __restrict
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// The same kernel with TMA tensor stores for the witness stream (WitnessStreamTma): the default when the stripe is at
-// least one 128-byte box column wide and the element count fits a 32-bit tensor coordinate.
+// The same kernel with 256-byte-aligned TMA tensor stores for the witness stream (WitnessStreamTma; W % 8 == 4).
 constexpr int RT_THREADS = 128;
-constexpr int RT_CH = 8;
-using RtStream = WitnessStreamTma<RT_CH, 2>;
-constexpr size_t RT_SMEM = (size_t)(RT_THREADS / 32) * RtStream::WARP_BYTES + 1024;   // + alignment slack
-__global__ void __launch_bounds__(RT_THREADS, 3)
-rescale_tma_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, size_t count, const __grid_constant__ CUtensorMap wmap,
+using RtStream = WitnessStreamTma;
+constexpr size_t RT_SMEM = (size_t)(RT_THREADS / 32) * RtStream::WARP_BYTES + 1024;   // + alignment slack: 73 KB, 3 CTAs per SM
+template <bool FAST, int CTAS>
+__global__ void __launch_bounds__(RT_THREADS, CTAS)
+rescale_tma_kernel(const Fr* __restrict__ cs, Fr* __restrict__ out_q, size_t count, const __grid_constant__ CUtensorMap map_even,
+                   const __grid_constant__ CUtensorMap map_odd, const __grid_constant__ CUtensorMap map_head,
                    const __grid_constant__ RescaleConsts k) {
     extern __shared__ uint8_t rt_stage_raw[];
     const uint32_t raw = smem_addr(rt_stage_raw);
     uint8_t* stage = rt_stage_raw + (((raw + 1023u) & ~1023u) - raw);   // the swizzle pattern repeats every 1024 bytes
-    const int lane = threadIdx.x & 31;
     RtStream ws;
-    ws.tile0 = stage + (size_t)(threadIdx.x >> 5) * RtStream::WARP_BYTES;
-    ws.map = &wmap;
-    ws.lane = lane;
-    ws.buf = 0;
-    ws.fill = 0;
+    ws.init(stage + (size_t)(threadIdx.x >> 5) * RtStream::WARP_BYTES, &map_even, &map_odd, &map_head);
+    const int lane = ws.lane;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    // warp-uniform trip count: lanes past the end recompute the last element; their rows are outside the tensor
+    // warp-uniform trip count: lanes past the end recompute the last element; their rows are outside the tensors
     for (size_t e0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < count; e0 += stride) {
         ws.begin((int)e0);
         const bool live = e0 + lane < count;
         const size_t e = live ? e0 + lane : count - 1;
         const Fr am = ldg_fr(cs + e);
-        const Fr q = rescale_element(ws, k, am);
+#ifdef RS_STORE_ONLY
+        for (int w = 0; w < k.p.W; w++) ws.put(am);
+        ws.flush();
+        const Fr q = am;
+#else
+        const Fr q = rescale_element<FAST>(ws, k, am);
+#endif
         if (live) st_fr(out_q + e, q);
     }
     // shared memory must outlive every TMA read, and the writes must be complete at kernel end (every lane: the groups
@@ -436,24 +438,41 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
         H2SVD_LAUNCH_CHECK(ctx);
         return H2SVD_OK;
     }
-    if (ctx->tune.rescale_store == 1 && p.W >= 4 && count < (1ull << 31)) {
-        // witness stream as a 2-D tensor [count][W * 32 bytes]; one box = 32 elements x 128 bytes
+    const bool fast = k.lc.fast_sums && ctx->tune.rescale_fast_sums != 0;
+    if ((ctx->tune.rescale_store == 0 || ctx->tune.rescale_store == 1) && ctx->tune.rescale_ch == 8 && RtStream::usable(out_wit, p.W, count)) {
+        // the even and the odd stripes as two 3-D tensors [128 B][halves][elements / 2]; box = 128 B x 2 halves x 16 rows,
+        // plus a one-half box for the first 128 bytes of the odd stripes
         tma_encode_fn encode = tma_encoder();
         if (encode) {
-            CUtensorMap wmap;
-            const cuuint64_t dims[2] = {(cuuint64_t)p.W * 32, (cuuint64_t)count};
-            const cuuint64_t strides[1] = {(cuuint64_t)p.W * 32};
-            const cuuint32_t box[2] = {128, 32};
-            const cuuint32_t estr[2] = {1, 1};
-            const CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, out_wit, dims, strides, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r == CUDA_SUCCESS) {
-                H2SVD_SET_SMEM(ctx, rescale_tma_kernel, RT_SMEM);
+            CUtensorMap maps[3];
+            bool ok = true;
+            for (int c = 0; c < 3 && ok; c++) {
+                const int odd = c >= 1;
+                const cuuint64_t rows = odd ? count / 2 : (count + 1) / 2;
+                const cuuint64_t dims[3] = {128, (cuuint64_t)(p.W / 4), rows};
+                const cuuint64_t strides[2] = {128, (cuuint64_t)p.W * 64};
+                const cuuint32_t box[3] = {128, c == 2 ? 1u : 2u, 16};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                ok = encode(&maps[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, reinterpret_cast<uint8_t*>(out_wit) + (size_t)odd * p.W * 32, dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            if (ok) {
                 size_t blocks = (count + RT_THREADS - 1) / RT_THREADS;
-                const size_t cap = (size_t)ctx->sm_count * 3;
+                const int ctas = ctx->tune.rescale_ctas == 2 ? 2 : 3;
+                const size_t cap = (size_t)ctx->sm_count * ctas;
                 if (blocks > cap) blocks = cap;
-                rescale_tma_kernel<<<(unsigned)blocks, RT_THREADS, RT_SMEM, ctx->stream>>>(cs, out_q, count, wmap, k);
+#define H2SVD_RT_LAUNCH(F, C)                                                                                               \
+    do {                                                                                                                    \
+        H2SVD_SET_SMEM(ctx, (rescale_tma_kernel<F, C>), RT_SMEM);                                                           \
+        rescale_tma_kernel<F, C><<<(unsigned)blocks, RT_THREADS, RT_SMEM, ctx->stream>>>(cs, out_q, count, maps[0], maps[1], \
+                                                                                         maps[2], k);                       \
+    } while (0)
+                if (fast && ctas == 2) H2SVD_RT_LAUNCH(true, 2);
+                else if (fast) H2SVD_RT_LAUNCH(true, 3);
+                else if (ctas == 2) H2SVD_RT_LAUNCH(false, 2);
+                else H2SVD_RT_LAUNCH(false, 3);
+#undef H2SVD_RT_LAUNCH
                 H2SVD_LAUNCH_CHECK(ctx);
                 return H2SVD_OK;
             }
@@ -461,7 +480,6 @@ int launch_rescale(h2svd_ctx* ctx, const Fr* cs, size_t count, int P, int lb, in
     }
     // Burst sizes / residencies measured on the N = 1024 rescale: 8 witnesses per burst, two staging
     // rows per lane, 3 CTAs per SM is the fastest; 4- and 6-witness bursts remain as tuning switches.
-    const bool fast = k.lc.fast_sums && ctx->tune.rescale_fast_sums != 0;
     switch (ctx->tune.rescale_ch) {
         case 4: return launch_rescale_ch<4>(ctx, cs, count, k, out_q, out_wit);
         case 6: return launch_rescale_ch<6>(ctx, cs, count, k, out_q, out_wit);

@@ -134,57 +134,115 @@ struct WitnessStreamStg {
     }
 };
 
-// Same interface, TMA tensor stores: the 32 stripes a warp fills are 32 ROWS of one 2-D tensor [element][W * 32 bytes], so
-// a burst of CH witnesses per lane leaves as CH / 4 box stores (cp.async.bulk.tensor.2d: 32 rows x 128 bytes each) instead
-// of 32 separate bulk copies issued one after the other by the elected lane -- measured on the N = 1024 rescale, the
-// serialised issue of those copies (7.5 bursts x 32 copies per element) held the warps for about a third of their time.
-// Staging: per warp and buffer CH / 4 sub-tiles of 32 rows x 128 bytes in the 128-byte-swizzled layout the tensor map
-// declares (16-byte chunk c of row r lives at chunk c ^ (r & 7)): the lanes' stores are conflict-free.  Rows past the end
-// of the tensor (a partial last warp) and bytes past the end of a stripe (a partial last burst) are clipped by the TMA unit.
-template <int CH, int NBUF>
+// Same interface, TMA tensor stores whose pieces sit on 256-BYTE-ALIGNED addresses (tuning switch rescale_store = 1).
+// Why: tools/store_pattern.cu (no arithmetic) -- 32 stripes x 256-byte pieces per burst reach 5.3 TB/s when half of the pieces
+// straddle a 256-byte boundary (every other stripe of W = 60 witnesses does: 1920 bytes = 7.5 x 256) and 5.9-6.1 TB/s when none
+// does; and the elected lane's 32 bulk copies per burst are a sixth of all executed instructions.  Here the EVEN and the ODD
+// stripes of a warp are rows of two 3-D tensors [128 B][halves of a stripe][elements / 2] (a "half" = 128 bytes = 4 witnesses):
+//   class 0 (even lanes, stripe 256-byte aligned):    chunk j = witnesses [8j, 8j + 8)       = halves 2j, 2j + 1
+//   class 1 (odd lanes, stripe starts 128 bytes in):  head    = witnesses [0, 4)             = half 0
+//                                                     chunk j = witnesses [4 + 8j, 12 + 8j)  = halves 2j + 1, 2j + 2
+// so every chunk is one 256-byte-aligned piece per stripe, and ONE instruction (a box of 128 B x 2 halves x 16 rows) ships a
+// class's chunk; the two classes complete their chunks 4 witnesses apart.  A stripe's last box reaches past its end
+// (W % 8 == 4): the TMA unit clips it, as it clips the rows of a partial last warp.  (Stores with a NEGATIVE coordinate
+// fault, hence the separate 128-byte head of class 1.)  Staging per warp: two buffers of 16 rows x 256 B per class in the
+// 128-byte-swizzled layout the tensor maps declare (16-byte chunk c of 128-byte line L at c ^ (L & 7)) + the head tile.
+// Buffer reuse: a class writes into a buffer again right after shipping the other one; the classes alternate, so the copy
+// that last read the buffer was committed two events earlier (wait until at most 2 groups are pending).
 struct WitnessStreamTma {
-    static_assert(CH % 4 == 0, "a burst is a whole number of 128-byte box columns");
-    static constexpr int SUB = CH / 4;                    // 128-byte sub-tiles per burst
-    static constexpr int WARP_BYTES = NBUF * SUB * 4096;  // staging per warp
-    uint8_t* tile0;          // this warp's staging area (1024-byte aligned)
-    const CUtensorMap* map;  // [count][W * 32 bytes], box 128 bytes x 32 rows, SWIZZLE_128B
-    int e0;                  // first element (tensor row) of this warp's 32
-    int wdone;               // witnesses of the current element already shipped
-    int lane, buf, fill;
+    static constexpr int WARP_BYTES = 2 * 2 * 4096 + 2048;     // [class][buffer] tiles + the head tile of class 1
+    // usable when every even stripe is 256-byte aligned, stripes are an odd number of halves and both classes have rows
+    static bool usable(const void* out_wit, int W, size_t count) {
+        return (W & 7) == 4 && (reinterpret_cast<uintptr_t>(out_wit) & 255u) == 0 && count >= 2 && count < (1ull << 31);
+    }
+    uint8_t* wbase;                      // this warp's staging (1024-byte aligned)
+    const CUtensorMap *map_even, *map_odd, *map_head;
+    int row0;                            // first row of this warp in the two class tensors (= first element / 2)
+    int lane;
+    uint32_t cls, rho;                   // this lane's class and its row within the class
+    uint32_t J0, J1;                     // chunks shipped so far per class (buffer parity), warp-uniform
+    uint32_t done0, done1, count;        // per element: chunks shipped per class, witnesses written
 
+    __device__ __forceinline__ void init(uint8_t* warp_stage, const CUtensorMap* me, const CUtensorMap* mo, const CUtensorMap* mh) {
+        lane = threadIdx.x & 31;
+        wbase = warp_stage;
+        map_even = me;
+        map_odd = mo;
+        map_head = mh;
+        cls = lane & 1;
+        rho = lane >> 1;
+        J0 = J1 = 0;
+    }
     __device__ __forceinline__ void begin(int first_element) {
-        e0 = first_element;
-        wdone = 0;
+        row0 = first_element >> 1;
+        done0 = done1 = 0;
+        count = 0;
+    }
+    __device__ __forceinline__ void commit_and_wait() {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
     }
     __device__ __forceinline__ void put(const Fr& v) {
-        uint8_t* t = tile0 + (buf * SUB + (fill >> 2)) * 4096 + lane * 128;
-        const int c = 2 * (fill & 3);
-        *reinterpret_cast<uint4*>(t + (((c) ^ (lane & 7)) << 4)) = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        *reinterpret_cast<uint4*>(t + (((c + 1) ^ (lane & 7)) << 4)) = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-        if (++fill == CH) flush();
+        // where witness `count` of this lane's element lives
+        uint8_t* line;
+        uint32_t sw, c;
+        if (cls == 1u && count < 4u) {                                    // head tile: [16 rows][128 B]
+            line = wbase + 4 * 4096 + rho * 128;
+            sw = rho & 7u;
+            c = 2u * count;
+        } else {
+            const uint32_t pos = cls ? (8u * J1 + count - 4u) & 15u : (8u * J0 + count) & 15u;
+            const uint32_t buf = pos >> 3, s = pos & 7u, half = s >> 2;
+            line = wbase + (cls * 2 + buf) * 4096 + rho * 256 + half * 128;
+            sw = (2u * rho + half) & 7u;
+            c = 2u * (s & 3u);
+        }
+        *reinterpret_cast<uint4*>(line + ((c ^ sw) << 4)) = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        *reinterpret_cast<uint4*>(line + (((c + 1u) ^ sw) << 4)) = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        count++;
+        const uint32_t ph = count & 7u;
+        if (ph == 0u || ph == 4u) {                                       // warp-uniform: a class has completed a chunk
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (elect_one()) {
+                if (ph == 0u) {
+                    const uint32_t src = smem_addr(wbase + (0 * 2 + ((J0 + done0) & 1u)) * 4096);
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map_even),
+                                 "r"(0), "r"(2 * (int)done0), "r"(row0), "r"(src)
+                                 : "memory");
+                } else if (count == 4u) {
+                    const uint32_t src = smem_addr(wbase + 4 * 4096);
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map_head),
+                                 "r"(0), "r"(0), "r"(row0), "r"(src)
+                                 : "memory");
+                } else {
+                    const uint32_t src = smem_addr(wbase + (1 * 2 + ((J1 + done1) & 1u)) * 4096);
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map_odd),
+                                 "r"(0), "r"(2 * (int)done1 + 1), "r"(row0), "r"(src)
+                                 : "memory");
+                }
+                commit_and_wait();
+            }
+            __syncwarp();
+            if (ph == 0u) done0++;
+            else if (count != 4u) done1++;
+        }
     }
-    __device__ __forceinline__ void flush() {  // warp-uniform: every lane has the same `fill`
-        if (fill == 0) return;
+    // end of the element (count = W, W % 8 == 4): class 0 has 4 witnesses left -- its box reaches one half past the stripe
+    // (clipped); class 1's last chunk ended exactly here and went out in put()
+    __device__ __forceinline__ void flush() {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (elect_one()) {
-            const int nsub = (fill + 3) >> 2;
-            for (int h = 0; h < nsub; h++) {
-                const uint32_t src = smem_addr(tile0 + (buf * SUB + h) * 4096);
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
-                             "r"((wdone + 4 * h) * 32), "r"(e0), "r"(src)
-                             : "memory");
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (NBUF == 2)
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            const uint32_t src = smem_addr(wbase + (0 * 2 + ((J0 + done0) & 1u)) * 4096);
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map_even), "r"(0),
+                         "r"(2 * (int)done0), "r"(row0), "r"(src)
+                         : "memory");
+            commit_and_wait();
         }
         __syncwarp();
-        wdone += fill;
-        fill = 0;
-        if (NBUF == 2) buf ^= 1;
+        J0 += done0 + 1u;
+        J1 += done1;
     }
 };
 

@@ -105,7 +105,7 @@ class Handle:
 
     # ---- triage / tuning switches (per handle; not part of the public header) ----
     TUNE_KEYS = ("matmul_tc", "matmul_small", "matmul_small_width", "matmul_cluster", "matmul_karatsuba", "matmul_streamk", "matmul_variant", "fuse_rescale",
-                 "rescale_generic", "matvec_warp_kernel", "matvec_seg", "matvec_segs", "matvec_x2", "rescale_ch", "rescale_store", "rescale_fast_sums", "matvec_coreside", "step_schedule")
+                 "rescale_generic", "matvec_warp_kernel", "matvec_seg", "matvec_segs", "matvec_x2", "rescale_ch", "rescale_store", "rescale_fast_sums", "rescale_ctas", "matvec_coreside", "step_schedule")
 
     def tune(self, key: str, value: int) -> None:
         """matmul_tc / matmul_small: -1 auto, 0 never, 1 always; matmul_karatsuba: -1 auto, 0 schoolbook, 1..3 variants;

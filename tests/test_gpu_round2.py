@@ -382,16 +382,17 @@ def test_rescale_store_paths_write_the_same_bytes(handle, P, lb, S, A):
     and a partial last warp; nothing is written past the end."""
     import torch
     rng = np.random.default_rng(P + lb)
-    count = 1000 + 37
+    count = 1000 + 37       # odd: the even class of the TMA path has one row more than the odd class; partial last warp
     cs = random_fr(rng, count)
     cs[:300] = quantized_matrix(rng, 300, 1, P).reshape(300, 4)
     dev = torch.device("cuda", handle.device)
     W = handle.rescale_witness_count(P, lb, S, A)
     tcs = torch.from_numpy(cs.view(np.int64)).to(dev)
     outs = []
-    # the three store paths; the default one also with the witness array starting 1 and 4 witnesses past a 256-byte
-    # boundary, and with the running sums computed both ways (fr::SmallSum / Montgomery step + modular add)
-    for store, off, fast in ((0, 0, 1), (1, 0, 1), (2, 0, 1), (0, 0, 0), (0, 1, 1), (0, 4, 0)):
+    # the store paths (0 = auto: 256-byte-aligned TMA boxes when W % 8 == 4 and the array is 256-byte aligned, else bulk
+    # copies; 1 TMA, 2 STG, 3 bulk), also with the witness array starting 1 and 4 witnesses past a 256-byte boundary (falls back
+    # to bulk copies), and with the running sums computed both ways (fr::SmallSum / Montgomery step + modular add)
+    for store, off, fast in ((0, 0, 0), (1, 0, 1), (2, 0, 1), (3, 0, 0), (3, 0, 1), (0, 1, 1), (0, 4, 0), (0, 8, 0)):
         q = torch.full((count, 4), -1, dtype=torch.int64, device=dev)
         flat = torch.full(((count + 3) * W + 8, 4), -1, dtype=torch.int64, device=dev)   # 3 guard stripes after the end
         wit = flat[off:off + (count + 3) * W].view(count + 3, W, 4)
