@@ -632,7 +632,8 @@ def measure_kernels(h, pkg, torch, device, stream, flush_buf, a_slab, b_dev, buf
     del c_tmp
     # K4: rescale witnesses of this rank's slab: 32 * (1 + 1 + W) bytes per element (read c_s, write q, write W witnesses)
     t_rs = timed(lambda: h.rescale_witness_dev(bufs["c_s"], rows * m, P_BITS, LOOKUP_BITS, bufs["q"], bufs["wit"]))
-    out["rescale_kernel"] = {"kernel": "rescale_kernel", "ms": t_rs, "bound": "hbm", "bytes": rows * m * 32.0 * (2 + W),
+    out["rescale_kernel"] = {"kernel": "rescale_tma_kernel (256-byte-aligned TMA stores of the witness stream; rescale_kernel for other layouts)",
+                             "ms": t_rs, "bound": "hbm", "bytes": rows * m * 32.0 * (2 + W),
                              "achieved": rows * m * 32.0 * (2 + W) / (t_rs * 1e-3) / 1e9,
                              "algorithmic": f"32 B x (1 read + 1 quotient + W={W} witnesses) per element (SURVEY 8d)"}
     # K2: one Freivalds mat-vec with every running sum (C.v of this rank's slab): 64 B per multiply-add

@@ -13,7 +13,7 @@ if [ "$1" = "list" ]; then
   timeout 300 python tools/tc_timeline.py 1024 > gpurun_out/y_timeline.txt 2>&1
 else
   $CMD > gpurun_out/y_plain2.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:"fr_matmul_tc_kernel|tc_split|rescale_kernel|mat_vec_prefix|gamma_powers" -c 11 -o gpurun_out/y_prof $CMD > gpurun_out/y_ncu2.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"fr_matmul_tc_kernel|tc_split|rescale_|mat_vec_prefix|gamma_powers" -c 11 -o gpurun_out/y_prof $CMD > gpurun_out/y_ncu2.log 2>&1
   echo "full capture rc=$?"
 fi
 ls -la gpurun_out/y_*
