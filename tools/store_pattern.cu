@@ -4,7 +4,8 @@
 // no arithmetic at all.  Measured on B200 (W = 60, 1 M elements = 2.0 GB per launch; profiles/r02_store_pattern.txt):
 //   * 32 stripes x 256-byte pieces per burst (the rescale kernel's pattern):       5.3 TB/s at 4 to 12 warps per SM
 //   * the same with W = 56 or 64 (every piece 256-byte ALIGNED):                   5.9-6.1 TB/s
-//   * W = 60 with every lane's pieces cut at the 256-byte boundaries of memory:    5.9 TB/s (mode 5)
+//   * W = 60 with every lane's pieces cut at the 256-byte boundaries of memory:    5.9-6.2 TB/s (mode 5, per-row bulk copies),
+//                                                                                   5.6-5.9 TB/s (mode 6, one TMA box per chunk)
 //   * a warp's burst as one contiguous piece (not the required layout, mode 3):    6.2-6.3 TB/s = the write peak
 //   * direct 16-byte stores from registers into the 32 stripes (mode 1):           1.5-2.2 TB/s
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o variants/store_pattern tools/store_pattern.cu
@@ -14,10 +15,10 @@
 //   mode 3: like mode 0 but every burst of a warp is ONE contiguous piece of memory (not the required layout: shows what
 //           the scatter over 32 stripes costs)
 //   mode 4: like mode 0, single-buffered
-//   mode 6: TMA tensor stores with 256-byte-aligned pieces: the even and the odd stripes of a warp are two 3-D tensors
-//           [128 B][W*32/128 halves][elements / 2]; each class of 16 lanes ships its completed 8-witness chunk as ONE box
-//           {128 B, 2 halves, 16 rows} (the odd class one half earlier: the out-of-range halves of a stripe's first and last
-//           box are clipped by the TMA unit); needs W % 8 == 4
+//   mode 6: TMA tensor stores with 256-byte-aligned pieces (what the library ships, csrc/rescale_dev.cuh WitnessStreamTma): the
+//           even and the odd stripes of a warp are two 3-D tensors [128 B][W*32/128 halves][elements / 2]; each class of 16
+//           lanes ships its completed 8-witness chunk as ONE box {128 B, 2 halves, 16 rows}; the odd class starts with a
+//           one-half head box (a store with a negative coordinate faults); needs W % 8 == 4
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -181,65 +182,73 @@ typedef CUresult (*tma_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// the library's WitnessStreamTma (csrc/rescale_dev.cuh) without the arithmetic
 __global__ void __launch_bounds__(128) store_tma_kernel(const __grid_constant__ CUtensorMap map_even, const __grid_constant__ CUtensorMap map_odd,
-                                                        size_t elements, int W, int dbg) {
+                                                        const __grid_constant__ CUtensorMap map_head, size_t elements, int W) {
     extern __shared__ uint8_t raw[];
     const uint32_t raw_s = smem_addr(raw);
     uint8_t* stage = raw + (((raw_s + 1023u) & ~1023u) - raw_s);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per warp: [class 2][buffer 2] tiles of 16 rows x 256 B (4 KB each, 1024-byte aligned)
-    uint8_t* wbase = stage + (size_t)warp * 16384;
+    // per warp: [class 2][buffer 2] tiles of 16 rows x 256 B (4 KB each) + the 16 x 128 B head tile of the odd class
+    uint8_t* wbase = stage + (size_t)warp * 18432;
     const uint32_t cls = lane & 1, rho = lane >> 1;
-    const uint32_t a = cls ? 4u : 0u;          // misalignment of the class's stripes in witnesses (array base 256-byte aligned)
     uint32_t J0 = 0, J1 = 0;                    // chunks each class has shipped so far (buffer parity), warp-uniform
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t e0 = (size_t)blockIdx.x * blockDim.x + warp * 32; e0 < elements; e0 += stride) {
         const int row0 = (int)(e0 >> 1);
-        const uint32_t base0 = 8u * J0, base1 = 8u * J1 + 4u;       // ring position of witness 0 per class
-        const uint32_t mybase = cls ? base1 : base0;
-        uint32_t done0 = 0, done1 = 0;                              // chunks of this element shipped per class
-        for (int w = 0; w < W; w++) {
-            const uint4 v = make_uint4((uint32_t)(e0 + lane), (uint32_t)w, 0x9e3779b9u, (uint32_t)lane);
-            const uint32_t pos = (mybase + (uint32_t)w) & 15u, buf = pos >> 3, s = pos & 7u, half = s >> 2;
-            uint8_t* line = wbase + (cls * 2 + buf) * 4096 + rho * 256 + half * 128;
-            const uint32_t sw = (2u * rho + half) & 7u, c = 2u * (s & 3u);
+        uint32_t done0 = 0, done1 = 0;
+        for (uint32_t count = 0; count < (uint32_t)W;) {
+            const uint4 v = make_uint4((uint32_t)(e0 + lane), count, 0x9e3779b9u, (uint32_t)lane);
+            uint8_t* line;
+            uint32_t sw, c;
+            if (cls == 1u && count < 4u) {
+                line = wbase + 4 * 4096 + rho * 128;
+                sw = rho & 7u;
+                c = 2u * count;
+            } else {
+                const uint32_t pos = cls ? (8u * J1 + count - 4u) & 15u : (8u * J0 + count) & 15u;
+                const uint32_t buf = pos >> 3, s = pos & 7u, half = s >> 2;
+                line = wbase + (cls * 2 + buf) * 4096 + rho * 256 + half * 128;
+                sw = (2u * rho + half) & 7u;
+                c = 2u * (s & 3u);
+            }
             *reinterpret_cast<uint4*>(line + ((c ^ sw) << 4)) = v;
             *reinterpret_cast<uint4*>(line + (((c + 1u) ^ sw) << 4)) = v;
-            const uint32_t cnt = (uint32_t)w + 1u, ph = cnt & 7u;
+            count++;
+            const uint32_t ph = count & 7u;
             if (ph == 0u || ph == 4u) {
-                const uint32_t c1 = ph == 4u;                        // class 1 completes a chunk when cnt + 4 is a multiple of 8
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (elect_one()) {
-                    const uint32_t jj = c1 ? done1 : done0, bufp = ((c1 ? J1 : J0) + jj) & 1u;
-                    const uint32_t src = smem_addr(wbase + (c1 * 2 + bufp) * 4096);
-                    int h0 = 2 * (int)jj - (c1 ? 1 : 0);
-                    if ((dbg & 1) && h0 < 0) h0 = 0;
-                    const bool skip = (dbg & 2) && c1;
-                    // (the tensor map operand must be the kernel parameter itself: a select between the two would copy them)
-                    if (skip) {
-                    } else if (c1)
-                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_odd),
-                                     "r"(0), "r"(h0), "r"(row0), "r"(src)
-                                     : "memory");
-                    else
+                    if (ph == 0u) {
+                        const uint32_t src = smem_addr(wbase + (0 * 2 + ((J0 + done0) & 1u)) * 4096);
                         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_even),
-                                     "r"(0), "r"(h0), "r"(row0), "r"(src)
+                                     "r"(0), "r"(2 * (int)done0), "r"(row0), "r"(src)
                                      : "memory");
+                    } else if (count == 4u) {
+                        const uint32_t src = smem_addr(wbase + 4 * 4096);
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_head),
+                                     "r"(0), "r"(0), "r"(row0), "r"(src)
+                                     : "memory");
+                    } else {
+                        const uint32_t src = smem_addr(wbase + (1 * 2 + ((J1 + done1) & 1u)) * 4096);
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_odd),
+                                     "r"(0), "r"(2 * (int)done1 + 1), "r"(row0), "r"(src)
+                                     : "memory");
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
                 }
                 __syncwarp();
-                if (c1) done1++;
-                else done0++;
+                if (ph == 0u) done0++;
+                else if (count != 4u) done1++;
             }
         }
-        // end of the stripe (W % 8 == 4): class 0 has 4 witnesses left (the second half of its box is past the stripe: clipped)
+        // end of the stripe (W % 8 == 4): the even class has 4 witnesses left (the second half of its box is past the stripe: clipped)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (elect_one()) {
-            const uint32_t bufp = (J0 + done0) & 1u;
-            const uint32_t src = smem_addr(wbase + (0 * 2 + bufp) * 4096);
+            const uint32_t src = smem_addr(wbase + (0 * 2 + ((J0 + done0) & 1u)) * 4096);
             asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_even), "r"(0),
                          "r"(2 * (int)done0), "r"(row0), "r"(src)
                          : "memory");
@@ -247,8 +256,7 @@ __global__ void __launch_bounds__(128) store_tma_kernel(const __grid_constant__ 
             asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
         }
         __syncwarp();
-        done0++;
-        J0 += done0;
+        J0 += done0 + 1u;
         J1 += done1;
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -256,7 +264,6 @@ __global__ void __launch_bounds__(128) store_tma_kernel(const __grid_constant__ 
 
 int main(int argc, char** argv) {
     const int W = argc > 1 ? atoi(argv[1]) : 60;
-    const int dbg = argc > 2 ? atoi(argv[2]) : 0;
     const size_t elements = 1024 * 1024;
     const size_t bytes = elements * W * 32;
     uint4* out;
@@ -276,7 +283,6 @@ int main(int argc, char** argv) {
     for (int warps : {8, 12}) cfgs.push_back({3, 8, 2, 128, warps / 4});
     for (int warps : {8, 16, 32}) cfgs.push_back({1, 8, 1, 128, warps / 4});
     for (int ctas : {1, 2, 3}) {
-        if (dbg) break;
         const size_t smem = 128 * 33 * 16 + 4 * 32 * 16;
         CK(cudaFuncSetAttribute(store_aligned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         float best = 1e30f;
@@ -313,14 +319,15 @@ int main(int argc, char** argv) {
         cudaDriverEntryPointQueryResult qres;
         CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres));
         tma_encode_fn encode = reinterpret_cast<tma_encode_fn>(fnp);
-        CUtensorMap maps[2];
-        for (int c = 0; c < 2; c++) {
+        CUtensorMap maps[3];   // even stripes, odd stripes, the first 128 bytes of the odd stripes
+        for (int c = 0; c < 3; c++) {
+            const int odd = c >= 1;
             const cuuint64_t dims[3] = {128, (cuuint64_t)(W * 32 / 128), (cuuint64_t)(elements / 2)};
             const cuuint64_t strides[2] = {128, (cuuint64_t)W * 64};
-            const cuuint32_t box[3] = {128, 2, 16};
+            const cuuint32_t box[3] = {128, c == 2 ? 1u : 2u, 16};
             const cuuint32_t estr[3] = {1, 1, 1};
-            const CUresult r = encode(&maps[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (uint8_t*)out + (size_t)c * W * 32, dims, strides, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, (dbg & 4) ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            const CUresult r = encode(&maps[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (uint8_t*)out + (size_t)odd * W * 32, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 fprintf(stderr, "tensor map %d failed: %d\n", c, (int)r);
@@ -328,14 +335,14 @@ int main(int argc, char** argv) {
             }
         }
         for (int ctas : {1, 2, 3}) {
-            const size_t smem = 4 * 16384 + 1024;
+            const size_t smem = 4 * 18432 + 1024;
             CK(cudaFuncSetAttribute(store_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             float best = 1e30f;
             for (int rep = 0; rep < 4; rep++) {
                 CK(cudaMemsetAsync(flush, rep, 256u << 20));
                 if (rep == 1 && ctas == 3) CK(cudaMemsetAsync(out, 0xff, bytes));
                 CK(cudaEventRecord(e0));
-                store_tma_kernel<<<sms * ctas, 128, smem>>>(maps[0], maps[1], elements, W, dbg);
+                store_tma_kernel<<<sms * ctas, 128, smem>>>(maps[0], maps[1], maps[2], elements, W);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
                 CK(cudaGetLastError());
