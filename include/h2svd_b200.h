@@ -66,7 +66,7 @@ uint64_t h2svd_launch_count(h2svd_ctx *ctx);
  * have been called on), so callers such as check_svd_phase0 (src/svd/mod.rs:96,109,112) need not
  * materialise the transpose.  Asserts of the reference (:515) become H2SVD_EINVAL.
  * Several engines compute the same bytes: from 64^3 on (and k >= 32) the product runs on the tensor cores as exact 8-bit
- * integer MMAs (csrc/matmul_tc.cu) -- over 9 x 10 signed byte digits when every operand is a small signed integer in
+ * integer MMAs (csrc/matmul_tc.cu) -- over 9 x 9 signed byte digits when every operand is a small signed integer in
  * standard form (|x| < 2^70: what ZkMatrix::new's quantization produces; detected on the device), else over the 32 x 32
  * byte planes of the full-width Montgomery representation -- smaller products on the integer pipe (csrc/matmul.cu).  The
  * choice is internal; results do not depend on it. */

@@ -28,7 +28,7 @@ def _signed_matrix(rng, rows, cols, bits):
 @pytest.mark.parametrize("n,k,m", [(64, 64, 64), (96, 80, 72), (128, 128, 24), (129, 130, 25), (1, 1024, 300), (300, 257, 47),
                                    (256, 256, 256), (40, 1000, 23)])
 def test_small_operand_engine_matches_oracle_and_full_engine(handle, n, k, m):
-    """Quantized (P = 63) operands: the device detects that every element is a small signed integer and runs the 9 x 10
+    """Quantized (P = 63) operands: the device detects that every element is a small signed integer and runs the 9 x 9
     signed-digit engine; same bytes as the oracle and as the full-width engine, on full, ragged and one-row shapes."""
     rng = np.random.default_rng(n * 31 + k)
     a, b = quantized_matrix(rng, n, k, 63), quantized_matrix(rng, k, m, 63)
